@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 visibility pipeline (BASELINE.json metric: Gmeshlets culled/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (N=1): BASELINE config C2 — procedural 10k-entity / 2M-meshlet city, one 1920x1080 view, two-pass
+occlusion. One *step* = the reference's depth-prepass culling of one steady-state frame
+(forward.rs:266-403): EARLY entity+meshlet cull (pass 1) -> Hi-Z build -> LATE entity+meshlet cull (pass 2),
+5 kernel launches. `value` = scene meshlet instances x views / step time with every input resident in HBM;
+the step rotates over 4 independent copies of the scene + view state (> L2) so inputs come from HBM.
+N>1 (torchrun, one rank per GPU): views are sharded over GPUs with no data-path collective (each rank culls
+its own camera of the replicated city) -> weak scaling; value = sum of meshlets over ranks / max-over-ranks time.
+
+`e2e` = the same metric through the public pass API with HOST buffers: per step the frame-varying inputs
+(entity transforms, entity draws, depth buffer) are copied from pinned host memory, the five stage calls run,
+and the results (both draw-command lists with their counts) are read back to the host — all inside the timed region.
+Static assets (meshlets, mesh infos, materials) stay resident like the reference's GpuAssets.
+
+--impl reference: the reference's CPU implementation of the path = the oracle port (OpenMP, all host cores) on the
+same config; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Gmeshlets culled/s (C2: 10k entities / 2M meshlets, 1920x1080, two-pass occlusion, steady-state frame)"
+UNIT = "Gmeshlets/s"
+N_COPIES = 4
+
+
+def c2_view(scenes, scene, index):
+    """Camera `index` of the C2 city: street-level corner cameras looking into the city (index 0 = the named view)."""
+    lo, hi = scene.aabb_min, scene.aabb_max
+    corners = [(-6.0, -6.0, 30.0), (hi[0] + 2.0, -6.0, -30.0), (-6.0, hi[2] + 2.0, 150.0), (hi[0] + 2.0, hi[2] + 2.0, 210.0)]
+    x, z, yaw = corners[index % 4]
+    yaw = np.radians(yaw + 15.0 * (index // 4))
+    return scenes.perspective_view((x, 2.0, z), (np.sin(yaw), 0.0, np.cos(yaw)), 1920, 1080)
+
+
+class ClockSampler:
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def late_meshlet_algorithmic_bytes(records, n_draws, n_materials=16, passes_vis=2):
+    """SURVEY §8(d) meshlet-stage formula, pass 2, WITHOUT the pyramid term (conservative: sampled texels are not
+    counted): 32*L + 16*R + 12 + 64*E + 400 + 80*mats + 4*R (visibility read) + 4*R (visibility write) + 4 + 28*S."""
+    lanes = int(records["meshlet_count"].sum())
+    R = len(records)
+    E = len(np.unique(records["entity_index"]))
+    return 32 * lanes + 16 * R + 12 + 64 * E + 400 + 80 * n_materials + 4 * R * passes_vis + 4 + 28 * n_draws, lanes, R, E
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: the CPU restatement (oracle port, OpenMP) of the same step on the same config."""
+    if rank != 0:
+        return
+    import oracle_ref as O
+    from orbit_b200 import scenes
+    O.build()
+    scene, _ = scenes.config_c2()
+    view = c2_view(scenes, scene, 0)
+    depth = scenes.make_depth(scene, view)
+    hs = O.HostScene(scene)
+    for _ in range(2):  # reach the steady state (frame 0 fills the visibility bits)
+        O.depth_prepass_culling(hs, view, depth)
+    for _ in range(max(args.warmup, 1)):
+        O.depth_prepass_culling(hs, view, depth)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.depth_prepass_culling(hs, view, depth)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = scene.n_meshlet_instances / dt / 1e9
+    cores = int(O.lib().oracle_threads())
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 city 10k entities / 2M meshlets, 1 view 1920x1080, steady-state frame: early cull + Hi-Z + late cull",
+                       "note": "reference GLSL cannot run here (no Vulkan/Rust); CPU restatement of the shaders (oracle port)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d whole C2 frames (early+Hi-Z+late), OpenMP over %d host threads" % (args.steps, cores)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from orbit_b200 import frame, scenes
+    from orbit_b200.passes import Context
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: orbit_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Context(local_rank)
+    dev = ctx.device
+
+    scene, _ = scenes.config_c2()
+    view = c2_view(scenes, scene, rank)
+    depth_np = scenes.make_depth(scene, view)
+
+    # ---- N_COPIES independent copies of every input + view state (rotation keeps inputs out of L2)
+    copies = []
+    for i in range(N_COPIES):
+        ds = frame.DeviceScene.upload(ctx, scene)
+        vs = frame.ViewState(ctx, ds, (view.width, view.height), name="view%d" % i)
+        d = torch.from_numpy(depth_np).to(dev)
+        pf = frame.PreparedFrame(ctx, ds, vs, view, d, name="c%d_forward_depth_prepass" % i)
+        copies.append(pf)
+    for pf in copies:          # frame 0 + frame 1: reach the steady state, grow scratch, then capture the graph
+        pf.launch(); pf.launch()
+    torch.cuda.synchronize()
+    for pf in copies:
+        pf.capture()
+    torch.cuda.synchronize()
+    code, st = ctx.poll_status()
+    assert code == 0, "capacity overflow in bench"
+
+    # ---- workload facts for the roofline (read once, outside the timed region)
+    pf0 = copies[0]
+    _, late_recs = frame.read_dispatch(pf0.late_dispatch)
+    n_late_draws, _ = frame.read_draws(pf0.late_draws, capacity=0)
+    _, early_recs = frame.read_dispatch(pf0.early_dispatch)
+    n_early_draws, _ = frame.read_draws(pf0.early_draws, capacity=0)
+    late_bytes, late_lanes, late_R, late_E = late_meshlet_algorithmic_bytes(late_recs, n_late_draws)
+    early_lanes = int(early_recs["meshlet_count"].sum())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(max(args.warmup, 3)):
+        copies[i % N_COPIES].replay()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        copies[i % N_COPIES].replay()
+    e1.record()
+    barrier()
+    step_ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    gpu_launches = 5 * args.steps  # graph replays do not pass through the C ABI counter; 5 kernels per step by construction
+
+    # ---- per-kernel times (separate, un-graphed passes with events around single launches; rotation kept)
+    def time_kernel(fn_name, late, reps):
+        ts = []
+        for i in range(reps):
+            pf = copies[i % N_COPIES]
+            s = pf._stream()
+            # run the frame up to the kernel under test so its inputs are the real ones
+            pf.entity(False, s); pf.meshlet(False, s); pf.hiz(s); pf.entity(True, s)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if fn_name == "meshlet_late":
+                a.record(); pf.meshlet(True, s); b.record()
+            else:
+                pf.meshlet(True, s)
+                if fn_name == "hiz":
+                    a.record(); pf.hiz(s); b.record()
+                elif fn_name == "meshlet_early":
+                    a.record(); pf.meshlet(False, s); b.record()
+                elif fn_name == "entity_late":
+                    a.record(); pf.entity(True, s); b.record()
+                elif fn_name == "entity_early":
+                    a.record(); pf.entity(False, s); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        ts = np.array(ts[2:]) if len(ts) > 4 else np.array(ts)
+        return float(np.median(ts)), float(ts.min())
+
+    kreps = 24
+    k_times = {k: time_kernel(k, None, kreps) for k in ("meshlet_late", "meshlet_early", "hiz", "entity_late", "entity_early")}
+
+    # ---- end-to-end through the public pass API with host buffers
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+    h_entities, h_draws, h_depth = pin(scene.entities), pin(scene.entity_draws), torch.from_numpy(depth_np).pin_memory()
+    h_count = torch.zeros(2, dtype=torch.int32).pin_memory()
+    h_out_early = torch.empty(28 * scene.n_meshlet_instances, dtype=torch.uint8).pin_memory()
+    h_out_late = torch.empty(28 * scene.n_meshlet_instances, dtype=torch.uint8).pin_memory()
+    h2d_bytes = h_entities.numel() + h_draws.numel() + h_depth.numel() * 4
+    d2h_bytes_box = [0]
+
+    def e2e_step(i):
+        pf = copies[i % N_COPIES]
+        pf.dscene.scene.entity_buffer.copy_(h_entities, non_blocking=True)
+        pf.dscene.scene.entity_draw_buffer.copy_(h_draws, non_blocking=True)
+        pf.depth.copy_(h_depth, non_blocking=True)
+        out = frame.depth_prepass_culling(ctx, pf.dscene, pf.vstate, view, pf.depth, name="c%d_forward_depth_prepass" % (i % N_COPIES))
+        h_count[0:1].copy_(out["early"][1][:4].view(torch.int32), non_blocking=True)
+        h_count[1:2].copy_(out["late"][1][:4].view(torch.int32), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        ne, nl = int(h_count[0]), int(h_count[1])
+        h_out_early[:28 * ne].copy_(out["early"][1][4:4 + 28 * ne], non_blocking=True)
+        h_out_late[:28 * nl].copy_(out["late"][1][4:4 + 28 * nl], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        d2h_bytes_box[0] = 8 + 28 * (ne + nl)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e2e_steps = max(4, min(args.steps, 40))
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([step_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, e2e_ms = float(t[0]), float(t[1])
+    units = scene.n_meshlet_instances * world
+    value = units / (step_ms * 1e-3) / 1e9
+    e2e_value = units / (e2e_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        late_us = k_times["meshlet_late"][0]
+        achieved = late_bytes / (late_us * 1e-6) / 1e9
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_baseline = cpu_baseline_sample(scene, view, depth_np)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "C2 city 10k entities / 2M meshlets, 1 view 1920x1080 per GPU, steady-state frame: early cull + Hi-Z + late cull",
+                       "l2": "rotating %d independent copies of scene + view state (~%d MB each) so inputs come from HBM" % (
+                           N_COPIES, sum(scene.bytes_summary().values()) // 2 ** 20),
+                       "launch": "one CUDA graph replay per step (5 kernels)", "views": "rank r culls camera r of the replicated city"},
+            "roofline": {"bound": "hbm", "kernel": "meshlet_cull_kernel (late pass, occlusion_pass=2)", "achieved": achieved,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": late_bytes, "launch_us_median": late_us, "launch_us_min": k_times["meshlet_late"][1],
+                         "lanes": late_lanes, "records": late_R, "entities": late_E, "survivors": n_late_draws,
+                         "stage_gmeshlets_per_s": late_lanes / (late_us * 1e-6) / 1e9,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "kernels_us_median": {k: v[0] for k, v in k_times.items()},
+            "hiz_build_us": k_times["hiz"][0],
+            "early_pass": {"lanes": early_lanes, "survivors": n_early_draws,
+                           "stage_gmeshlets_per_s": early_lanes / (k_times["meshlet_early"][0] * 1e-6) / 1e9},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes_box[0]),
+                    "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "what": "pinned host entity transforms + entity draws + depth -> device, 5 stage calls via the pass API, draw lists + counts -> host"},
+            "gpu_launches": gpu_launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def cpu_baseline_sample(scene, view, depth_np, frames=4):
+    """The oracle port timed on this box's host cores: a bounded sample of the same workload."""
+    import oracle_ref as O
+    O.build()
+    hs = O.HostScene(scene)
+    for _ in range(2):
+        O.depth_prepass_culling(hs, view, depth_np)
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        O.depth_prepass_culling(hs, view, depth_np)
+    dt = (time.perf_counter() - t0) / frames
+    cores = int(O.lib().oracle_threads())
+    return {"value": scene.n_meshlet_instances / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "ms_per_step": dt * 1e3,
+            "sample": "%d whole C2 steady-state frames (early+Hi-Z+late) on the oracle port, OpenMP over %d host threads" % (frames, cores)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+/*
+ * orbit_cuda.h — C ABI of liborbit_b200.so: the B200 (sm_100a) visibility pipeline behind Orbit's
+ * culling-pass interface.
+ *
+ * The reference (Thefefe/orbit) has no FFI layer; the seam this library replaces is the set of pass
+ * creation functions in src/passes/draw_gen.rs and src/passes/cluster.rs.  Each entry point below names
+ * the reference function + GPU program it stands in for.  All buffers are raw device pointers in exactly
+ * the reference byte layout (include/orbit_layouts.h), so the Vulkan indirect draws of
+ * src/graphics/context.rs:1092-1111 can consume the outputs unchanged (memory shared through
+ * cudaImportExternalMemory when interop is on; allocated by the caller when headless).
+ *
+ * Conventions
+ *   - return value: 0 = ORBIT_OK, negative = error (orbit_error_string).  The reference has no error
+ *     convention (assert!/unwrap: draw_gen.rs:334,390,123-133); argument errors it would have panicked on
+ *     are reported as ORBIT_ERR_INVALID_ARGUMENT here.
+ *   - every stage call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *     and never synchronises with the host.  Nothing is read back (draw_gen.rs never reads back either).
+ *   - OrbitCullInfo / OrbitClusterParams / OrbitSceneBuffers are HOST structs, copied into kernel parameter
+ *     space at launch; the pointers inside OrbitSceneBuffers are DEVICE pointers.
+ *   - a context owns the small device scratch used by the scan-based compaction (tile descriptors, tickets).
+ *     One context must not be used from two streams concurrently; contexts are independent of each other and
+ *     of the calling thread (the reference records passes from rayon workers: context.rs:1392-1423).
+ *   - output order is deterministic: dispatch records are ordered by (entity-draw index, chunk), draw
+ *     commands by (dispatch record index, lane), compacted clusters and light indices ascending.  The
+ *     reference appends with atomicAdd (entity_cull.comp:211, meshlet_cull.comp:228), i.e. in arbitrary
+ *     order; any order is valid for its consumers, so a fixed one is a drop-in.
+ *   - there is no CPU fallback: without a CUDA device every entry point that needs one fails.
+ */
+#ifndef ORBIT_CUDA_H
+#define ORBIT_CUDA_H
+
+#include <stdint.h>
+#include "orbit_layouts.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBIT_ABI_VERSION 1
+
+enum {
+    ORBIT_OK = 0,
+    ORBIT_ERR_INVALID_ARGUMENT = -1,
+    ORBIT_ERR_CUDA = -2,           /* a CUDA runtime call failed; orbit_last_cuda_error() has the code */
+    ORBIT_ERR_OUT_OF_MEMORY = -3,
+    ORBIT_ERR_NO_DEVICE = -4,
+    ORBIT_ERR_CAPACITY = -5        /* reported by orbit_ctx_poll_status only */
+};
+
+typedef struct orbit_ctx orbit_ctx;
+typedef struct orbit_hiz orbit_hiz;
+
+/* Device-written status, readable after the stream has been synchronised. */
+typedef struct OrbitStatus {
+    uint32_t dispatch_overflow;   /* entity stage produced more records than capacity_records (extra dropped) */
+    uint32_t draw_overflow;       /* meshlet stage produced more draws than capacity_draws (extra dropped)    */
+    uint32_t light_index_overflow;/* light lists exceeded capacity_indices (extra dropped)                    */
+    uint32_t reserved;
+} OrbitStatus;
+
+/* Device pointers to the long-lived scene / asset arrays the culling path reads.
+ * Reference owners: GpuAssets (assets/mod.rs:230-239) and SceneData (scene.rs:358-369). */
+typedef struct OrbitSceneBuffers {
+    const void* entity_draws;       /* EntityDrawBuffer: u32 count @0, OrbitEntityDraw[] @4             */
+    const void* mesh_infos;         /* OrbitMeshInfo[]                                                   */
+    const void* entities;           /* OrbitEntityData[]                                                 */
+    const void* meshlets;           /* OrbitMeshlet[] (32-byte aligned)                                  */
+    const void* materials;          /* GpuMaterialData[] (80-byte stride)                                */
+    uint32_t*   entity_visibility;  /* one bit per entity draw, word = draw_index/32 (forward.rs:150-157) */
+    uint32_t*   meshlet_visibility; /* one word per dispatch record (scene.rs:354,375-382); may be NULL  */
+    uint32_t    entity_draw_count;  /* host copy of the count used to size the launch (draw_gen.rs:377)  */
+    uint32_t    draw_begin;         /* first entity-draw index this call covers (multiple of 32);        */
+    uint32_t    draw_end;           /* one past the last; 0,0 = all. Used to shard one view over GPUs.   */
+    uint32_t    reserved;
+} OrbitSceneBuffers;
+
+/* Geometry of a depth pyramid: DepthPyramid::new, draw_gen.rs:456-459 + math.rs:18-20. Level l is
+ * max(width>>l,1) x max(height>>l,1) texels of f32 starting at texel offset level_offset[l] of one linear
+ * allocation (levels are stored back to back so the whole pyramid is one contiguous broadcastable block). */
+#define ORBIT_HIZ_MAX_LEVELS 16
+typedef struct OrbitHizInfo {
+    uint32_t width, height;       /* level-0 size = [npot(w)/2, npot(h)/2] */
+    uint32_t levels;
+    uint32_t total_texels;
+    uint32_t level_offset[ORBIT_HIZ_MAX_LEVELS];
+    float*   texels;              /* device pointer (NULL from orbit_hiz_geometry) */
+} OrbitHizInfo;
+
+/* Parameters of clustered light assignment = ClusterCullInfo (cluster.rs:186-207) + the mark_active push
+ * block (mark_active.comp:8-23, z_scale/z_bias from ClusterSettings::cluster_grid_info, cluster.rs:63-72). */
+typedef struct OrbitClusterParams {
+    OrbitClusterCullInfo info;
+    float    z_scale;
+    float    z_bias;
+    uint32_t reserved[2];
+} OrbitClusterParams;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int         orbit_abi_version(void);
+const char* orbit_error_string(int code);
+int         orbit_last_cuda_error(void);
+int         orbit_ctx_create(int device, orbit_ctx** out);
+void        orbit_ctx_destroy(orbit_ctx* ctx);
+/* Copies the device-written status words (pinned, host-mapped) and clears them. Caller syncs the stream first. */
+int         orbit_ctx_poll_status(orbit_ctx* ctx, OrbitStatus* out);
+/* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
+uint64_t    orbit_ctx_launch_count(const orbit_ctx* ctx);
+
+/* ---- depth pyramid: DepthPyramid::{new,resize,update,get_current}, draw_gen.rs:451-567 ------------------ */
+int  orbit_hiz_geometry(uint32_t depth_width, uint32_t depth_height, OrbitHizInfo* out);  /* host only */
+int  orbit_hiz_create(orbit_ctx* ctx, uint32_t depth_width, uint32_t depth_height, orbit_hiz** out);
+/* Wrap caller-owned device memory of orbit_hiz_geometry().total_texels floats (interop / torch allocations). */
+int  orbit_hiz_wrap(orbit_ctx* ctx, uint32_t depth_width, uint32_t depth_height, float* texels, orbit_hiz** out);
+void orbit_hiz_destroy(orbit_hiz* hiz);
+int  orbit_hiz_info(const orbit_hiz* hiz, OrbitHizInfo* out);
+/* DepthPyramid::update (draw_gen.rs:510-566) + depth_reduce.comp: builds ALL levels from `depth`
+ * (depth_width x depth_height f32, row-major, reverse-Z) in one launch. */
+int  orbit_hiz_build(orbit_ctx* ctx, orbit_hiz* hiz, const float* depth,
+                     uint32_t depth_width, uint32_t depth_height, void* stream);
+
+/* ---- create_meshlet_dispatch_command (draw_gen.rs:327-380) + entity_cull.comp --------------------------- */
+/* Writes MeshletDispatchBuffer {x,1,1; records[]} and, in pass 2, the entity visibility words.
+ * `hiz` may be NULL unless cull->occlusion_pass == 2. */
+int orbit_entity_cull(orbit_ctx* ctx, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene,
+                      const orbit_hiz* hiz, void* meshlet_dispatch_buffer, uint64_t capacity_records,
+                      void* stream);
+
+/* ---- create_meshlet_draw_commands (draw_gen.rs:382-435) + meshlet_cull.comp ------------------------------ */
+/* Reads the dispatch buffer produced above (its record count is read on the device — the reference's
+ * dispatch_indirect, draw_gen.rs:432), writes MeshletDrawCommandBuffer {count; draws[]} and, in pass 2 with
+ * meshlet occlusion culling on, the meshlet visibility words.
+ * `task_payloads` (nullable): additionally emits, per dispatch record, the MeshTaskPayload the task-shader
+ * twins build (forward_depth_prepass.task:224-256) plus its emitted mesh-task count:
+ * element r = {u32 task_count; OrbitMeshTaskPayload} (44 bytes) for record r.
+ * `capacity_records` is the size of the dispatch buffer in records; the device-side count is clamped to it. */
+int orbit_meshlet_cull(orbit_ctx* ctx, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene,
+                       const orbit_hiz* hiz, const void* meshlet_dispatch_buffer, uint64_t capacity_records,
+                       void* draw_command_buffer, uint64_t capacity_draws,
+                       void* task_payloads, void* stream);
+
+/* ---- compute_clusters (cluster.rs:368-591) + light_cluster/{mark_active,active_cluster_compaction,
+ *      light_culling}.comp --------------------------------------------------------------------------------- */
+/* tile_masks: u32[cx*cy]; depth_bounds: OrbitClusterDepthBounds[cx*cy*cz]; unique_clusters:
+ * CompactedClusterIndexList (16 + 4*cx*cy*cz bytes); offset_count_image: uint2[cx*cy*cz] (inactive texels are
+ * zeroed); light_index_list: ClusterLightIndices (4 + 4*capacity_indices bytes). */
+int orbit_light_cluster(orbit_ctx* ctx, const OrbitClusterParams* params, const float* depth,
+                        const void* lights, void* tile_masks, void* depth_bounds, void* unique_clusters,
+                        void* offset_count_image, void* light_index_list, uint64_t capacity_indices,
+                        void* stream);
+
+/* ---- multi-GPU helper (no reference counterpart) --------------------------------------------- */
+/* Appends `count` draw commands read from src (a MeshletDrawCommandBuffer, device-side count honoured) into
+ * dst (possibly a peer-mapped MeshletDrawCommandBuffer) starting at draw index `dst_first`; when
+ * `total_count` != UINT32_MAX also stores it as dst's header. One coalesced copy kernel; used to assemble the
+ * rank-major survivor list of a meshlet-range-sharded view through NVLink peer stores. */
+int orbit_draws_scatter(orbit_ctx* ctx, const void* src_draw_buffer, void* dst_draw_buffer,
+                        uint32_t dst_first, uint32_t total_count, uint64_t dst_capacity_draws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBIT_CUDA_H */

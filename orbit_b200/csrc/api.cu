@@ -1,0 +1,376 @@
+// api.cu — the C ABI of include/orbit_cuda.h: argument checking, scratch ownership, kernel launches.
+// No torch types, no host synchronisation on the stage calls, no CPU fallback.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "params.cuh"
+
+
+using namespace orbit;
+
+static thread_local int g_last_cuda_error = 0;
+#define CK(expr)                                                       \
+    do {                                                               \
+        cudaError_t e_ = (expr);                                       \
+        if (e_ != cudaSuccess) { g_last_cuda_error = (int)e_; return ORBIT_ERR_CUDA; } \
+    } while (0)
+
+struct orbit_ctx {
+    int device = 0;
+    int sm_count = 0;
+    // scan scratch
+    unsigned long long* status = nullptr;
+    size_t status_capacity = 0;       // descriptors
+    unsigned int* counters = nullptr; // [0]=ticket [1]=done [2]=hiz ticket [3]=scan epoch (device-advanced)
+    // device-written status, pinned + mapped
+    OrbitStatus* status_host = nullptr;
+    OrbitStatus* status_dev = nullptr;
+    // light scratch
+    float4* light_view = nullptr;
+    size_t light_capacity = 0;
+    // tuning (ORBIT_MC_RECS_PER_WARP / ORBIT_MC_CTAS_PER_SM environment overrides, read once)
+    int mc_recs_per_warp = 4;
+    int mc_ctas_per_sm = 0;
+    std::atomic<uint64_t> launches{0};
+};
+
+struct orbit_hiz {
+    OrbitHizInfo info;
+    uint32_t depth_w, depth_h;
+    bool owns;
+    int device;
+};
+
+static int ensure_status(orbit_ctx* c, size_t tiles) {
+    if (tiles <= c->status_capacity) return ORBIT_OK;
+    size_t cap = c->status_capacity ? c->status_capacity : 4096;
+    while (cap < tiles) cap *= 2;
+    if (c->status) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->status)); c->status = nullptr; c->status_capacity = 0; }
+    CK(cudaMalloc(&c->status, cap * sizeof(unsigned long long)));
+    CK(cudaMemset(c->status, 0, cap * sizeof(unsigned long long)));
+    c->status_capacity = cap;
+    return ORBIT_OK;
+}
+
+static ScanState next_scan(orbit_ctx* c) {
+    return ScanState{c->status, c->counters + 0, c->counters + 1, c->counters + 3};
+}
+
+static HizDevice hiz_device(const orbit_hiz* h) {
+    HizDevice d{};
+    if (h) {
+        d.texels = h->info.texels; d.width = h->info.width; d.height = h->info.height; d.levels = h->info.levels;
+        for (int i = 0; i < ORBIT_HIZ_MAX_LEVELS; ++i) d.level_offset[i] = h->info.level_offset[i];
+    }
+    return d;
+}
+
+static uint32_t npot(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+extern "C" {
+
+int orbit_abi_version(void) { return ORBIT_ABI_VERSION; }
+
+const char* orbit_error_string(int code) {
+    switch (code) {
+        case ORBIT_OK: return "ok";
+        case ORBIT_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case ORBIT_ERR_CUDA: return "CUDA runtime error (see orbit_last_cuda_error)";
+        case ORBIT_ERR_OUT_OF_MEMORY: return "out of memory";
+        case ORBIT_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case ORBIT_ERR_CAPACITY: return "an output buffer overflowed its capacity; extra items were dropped";
+        default: return "unknown error";
+    }
+}
+
+int orbit_last_cuda_error(void) { return g_last_cuda_error; }
+
+int orbit_ctx_create(int device, orbit_ctx** out) {
+    if (!out) return ORBIT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { g_last_cuda_error = (int)e; return ORBIT_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) return ORBIT_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(device));
+    orbit_ctx* c = new (std::nothrow) orbit_ctx();
+    if (!c) return ORBIT_ERR_OUT_OF_MEMORY;
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaMalloc(&c->counters, 16 * sizeof(unsigned int)));
+    CK(cudaMemset(c->counters, 0, 16 * sizeof(unsigned int)));
+    { const unsigned int one = 1u; CK(cudaMemcpy(c->counters + 3, &one, sizeof(one), cudaMemcpyHostToDevice)); }
+    CK(cudaHostAlloc(&c->status_host, sizeof(OrbitStatus), cudaHostAllocMapped));
+    std::memset(c->status_host, 0, sizeof(OrbitStatus));
+    CK(cudaHostGetDevicePointer(&c->status_dev, c->status_host, 0));
+    int rc = ensure_status(c, 4096);
+    if (rc != ORBIT_OK) return rc;
+    if (const char* s = std::getenv("ORBIT_MC_RECS_PER_WARP")) { int v = std::atoi(s); if (v == 1 || v == 2 || v == 4) c->mc_recs_per_warp = v; }
+    if (const char* s = std::getenv("ORBIT_MC_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->mc_ctas_per_sm = v; }
+    *out = c;
+    return ORBIT_OK;
+}
+
+void orbit_ctx_destroy(orbit_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view);
+    cudaFreeHost(c->status_host);
+    delete c;
+}
+
+int orbit_ctx_poll_status(orbit_ctx* c, OrbitStatus* out) {
+    if (!c || !out) return ORBIT_ERR_INVALID_ARGUMENT;
+    *out = *c->status_host;
+    std::memset(c->status_host, 0, sizeof(OrbitStatus));
+    return (out->dispatch_overflow || out->draw_overflow || out->light_index_overflow) ? ORBIT_ERR_CAPACITY : ORBIT_OK;
+}
+
+uint64_t orbit_ctx_launch_count(const orbit_ctx* c) { return c ? c->launches.load() : 0; }
+
+// ---- depth pyramid -------------------------------------------------------------------------------------
+int orbit_hiz_geometry(uint32_t dw, uint32_t dh, OrbitHizInfo* out) {
+    if (!out || dw == 0 || dh == 0 || dw > 32768u || dh > 32768u) return ORBIT_ERR_INVALID_ARGUMENT;
+    std::memset(out, 0, sizeof(*out));
+    out->width = npot(dw) / 2u; out->height = npot(dh) / 2u;         // draw_gen.rs:458
+    if (out->width == 0 || out->height == 0) return ORBIT_ERR_INVALID_ARGUMENT;  // a 1-texel-wide depth has no pyramid
+    uint32_t mx = out->width > out->height ? out->width : out->height;
+    uint32_t levels = 0; while (mx) { ++levels; mx >>= 1; }           // math.rs:18-20
+    out->levels = levels;
+    uint32_t off = 0;
+    for (uint32_t l = 0; l < levels; ++l) {
+        out->level_offset[l] = off;
+        uint32_t w = out->width >> l, h = out->height >> l;
+        off += (w ? w : 1u) * (h ? h : 1u);                            // image.rs:531
+    }
+    out->total_texels = off;
+    return ORBIT_OK;
+}
+
+static int hiz_make(orbit_ctx* c, uint32_t dw, uint32_t dh, float* texels, bool owns, orbit_hiz** out) {
+    if (!c || !out) return ORBIT_ERR_INVALID_ARGUMENT;
+    orbit_hiz* h = new (std::nothrow) orbit_hiz();
+    if (!h) return ORBIT_ERR_OUT_OF_MEMORY;
+    int rc = orbit_hiz_geometry(dw, dh, &h->info);
+    if (rc != ORBIT_OK) { delete h; return rc; }
+    h->depth_w = dw; h->depth_h = dh; h->owns = owns; h->device = c->device;
+    if (owns) {
+        cudaError_t e = cudaSetDevice(c->device);
+        if (e == cudaSuccess) e = cudaMalloc(&texels, (size_t)h->info.total_texels * sizeof(float));
+        if (e != cudaSuccess) { g_last_cuda_error = (int)e; delete h; return e == cudaErrorMemoryAllocation ? ORBIT_ERR_OUT_OF_MEMORY : ORBIT_ERR_CUDA; }
+    } else if (!texels || ((uintptr_t)texels & 15u)) {
+        delete h; return ORBIT_ERR_INVALID_ARGUMENT;
+    }
+    h->info.texels = texels;
+    *out = h;
+    return ORBIT_OK;
+}
+
+int orbit_hiz_create(orbit_ctx* c, uint32_t dw, uint32_t dh, orbit_hiz** out) { return hiz_make(c, dw, dh, nullptr, true, out); }
+int orbit_hiz_wrap(orbit_ctx* c, uint32_t dw, uint32_t dh, float* texels, orbit_hiz** out) { return hiz_make(c, dw, dh, texels, false, out); }
+
+void orbit_hiz_destroy(orbit_hiz* h) {
+    if (!h) return;
+    if (h->owns) { cudaSetDevice(h->device); cudaFree(h->info.texels); }
+    delete h;
+}
+
+int orbit_hiz_info(const orbit_hiz* h, OrbitHizInfo* out) {
+    if (!h || !out) return ORBIT_ERR_INVALID_ARGUMENT;
+    *out = h->info;
+    return ORBIT_OK;
+}
+
+int orbit_hiz_build(orbit_ctx* c, orbit_hiz* h, const float* depth, uint32_t dw, uint32_t dh, void* stream) {
+    if (!c || !h || !depth || dw != h->depth_w || dh != h->depth_h) return ORBIT_ERR_INVALID_ARGUMENT;
+    HizBuildParams p{};
+    p.depth = depth; p.texels = h->info.texels; p.depth_w = dw; p.depth_h = dh;
+    p.width = h->info.width; p.height = h->info.height; p.levels = h->info.levels;
+    for (int i = 0; i < ORBIT_HIZ_MAX_LEVELS; ++i) p.level_offset[i] = h->info.level_offset[i];
+    p.ticket = c->counters + 2;
+    CK(launch_hiz_build(p, (cudaStream_t)stream));
+    c->launches += 1;
+    return ORBIT_OK;
+}
+
+// ---- entity stage ----------------------------------------------------------------------------------------
+static int check_cull(const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz, bool meshlet_stage) {
+    if (!cull || !scene) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (cull->cull_plane_count > ORBIT_MAX_CULL_PLANES) return ORBIT_ERR_INVALID_ARGUMENT;  // assert!, draw_gen.rs:334,390
+    if (cull->occlusion_pass > 2u) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (!scene->entities) return ORBIT_ERR_INVALID_ARGUMENT;
+    const bool mocc = cull->meshlet_visibility_buffer != ORBIT_NO_BUFFER;
+    if (meshlet_stage) {
+        if (!scene->meshlets || !scene->materials) return ORBIT_ERR_INVALID_ARGUMENT;
+        if (((uintptr_t)scene->meshlets & 15u) || ((uintptr_t)scene->entities & 15u)) return ORBIT_ERR_INVALID_ARGUMENT;
+        if (mocc && cull->occlusion_pass != 0u && !scene->meshlet_visibility) return ORBIT_ERR_INVALID_ARGUMENT;
+        if (mocc && cull->occlusion_pass == 2u && !hiz) return ORBIT_ERR_INVALID_ARGUMENT;
+    } else {
+        if (!scene->entity_draws || !scene->mesh_infos) return ORBIT_ERR_INVALID_ARGUMENT;
+        if (((uintptr_t)scene->mesh_infos & 15u) || ((uintptr_t)scene->entities & 15u) || ((uintptr_t)scene->entity_draws & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
+        if (cull->occlusion_pass != 0u && !scene->entity_visibility) return ORBIT_ERR_INVALID_ARGUMENT;
+        if (cull->occlusion_pass == 2u && !hiz) return ORBIT_ERR_INVALID_ARGUMENT;
+        if (scene->draw_begin % 32u) return ORBIT_ERR_INVALID_ARGUMENT;
+    }
+    return ORBIT_OK;
+}
+
+int orbit_entity_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
+                      void* meshlet_dispatch_buffer, uint64_t capacity_records, void* stream) {
+    if (!c || !meshlet_dispatch_buffer || ((uintptr_t)meshlet_dispatch_buffer & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
+    int rc = check_cull(cull, scene, hiz, false);
+    if (rc != ORBIT_OK) return rc;
+    uint32_t begin = scene->draw_begin, end = scene->draw_end;
+    if (begin == 0u && end == 0u) end = scene->entity_draw_count;
+    if (end > scene->entity_draw_count) end = scene->entity_draw_count;
+    if (begin > end) return ORBIT_ERR_INVALID_ARGUMENT;
+    const uint32_t n = end - begin;
+    rc = ensure_status(c, (size_t)(n + 255u) / 256u + 1u);
+    if (rc != ORBIT_OK) return rc;
+    EntityCullParams p{};
+    p.cull = *cull; p.hiz = hiz_device(hiz);
+    p.entity_draw_words = (const uint32_t*)scene->entity_draws;
+    p.mesh_infos = (const uint8_t*)scene->mesh_infos;
+    p.entities = (const float4*)scene->entities;
+    p.entity_visibility = scene->entity_visibility;
+    p.dispatch_words = (uint32_t*)meshlet_dispatch_buffer;
+    p.overflow_flag = &c->status_dev->dispatch_overflow;
+    p.capacity_records = capacity_records;
+    p.draw_begin = begin; p.draw_end = end;
+    p.scan = next_scan(c);
+    CK(launch_entity_cull(p, n, (cudaStream_t)stream));
+    c->launches += 1;
+    return ORBIT_OK;
+}
+
+// ---- meshlet stage ---------------------------------------------------------------------------------------
+int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
+                       const void* meshlet_dispatch_buffer, uint64_t capacity_records, void* draw_command_buffer,
+                       uint64_t capacity_draws, void* task_payloads, void* stream) {
+    if (!c || !meshlet_dispatch_buffer || !draw_command_buffer) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)meshlet_dispatch_buffer & 3u) || ((uintptr_t)draw_command_buffer & 3u) || ((uintptr_t)task_payloads & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (capacity_records > 0xFFFFFFFFull) capacity_records = 0xFFFFFFFFull;
+    int rc = check_cull(cull, scene, hiz, true);
+    if (rc != ORBIT_OK) return rc;
+    // The record count lives on the device (the reference's dispatch_indirect); scratch and grid are sized for
+    // the dispatch buffer's capacity and the kernel clamps the device-side count to it.
+    const int rpw = c->mc_recs_per_warp;
+    const uint32_t recs_per_tile = 8u * (uint32_t)rpw;
+    const uint64_t max_records = capacity_records;
+    rc = ensure_status(c, (size_t)((max_records + recs_per_tile - 1u) / recs_per_tile) + 1u);
+    if (rc != ORBIT_OK) return rc;
+    MeshletCullParams p{};
+    p.cull = *cull; p.hiz = hiz_device(hiz);
+    p.dispatch_words = (const uint32_t*)meshlet_dispatch_buffer;
+    p.meshlets = (const uint4*)scene->meshlets;
+    p.entities = (const float4*)scene->entities;
+    p.materials = (const uint8_t*)scene->materials;
+    p.meshlet_visibility = scene->meshlet_visibility;
+    p.draw_words = (uint32_t*)draw_command_buffer;
+    p.task_payloads = (uint32_t*)task_payloads;
+    p.overflow_flag = &c->status_dev->draw_overflow;
+    p.capacity_records = max_records;
+    p.capacity_draws = capacity_draws;
+    p.scan = next_scan(c);
+    int per_sm = c->mc_ctas_per_sm;
+    if (per_sm <= 0) {
+        per_sm = meshlet_cull_max_ctas_per_sm(rpw);
+        if (per_sm <= 0) per_sm = 1;
+        c->mc_ctas_per_sm = per_sm;
+    }
+    uint64_t grid = (uint64_t)c->sm_count * (uint64_t)per_sm;
+    const uint64_t max_tiles = (max_records + recs_per_tile - 1u) / recs_per_tile;
+    if (grid > max_tiles) grid = max_tiles ? max_tiles : 1u;
+    CK(launch_meshlet_cull(p, rpw, (int)grid, (cudaStream_t)stream));
+    c->launches += 1;
+    return ORBIT_OK;
+}
+
+// ---- clustered lights ------------------------------------------------------------------------------------
+int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const float* depth, const void* lights,
+                        void* tile_masks, void* depth_bounds, void* unique_clusters, void* offset_count_image,
+                        void* light_index_list, uint64_t capacity_indices, void* stream) {
+    if (!c || !params || !depth || !tile_masks || !depth_bounds || !unique_clusters || !offset_count_image || !light_index_list)
+        return ORBIT_ERR_INVALID_ARGUMENT;
+    const OrbitClusterCullInfo& ci = params->info;
+    const uint64_t cx = ci.cluster_count[0], cy = ci.cluster_count[1], cz = ci.cluster_count[2];
+    if (cx == 0 || cy == 0 || cz == 0 || cx * cy * cz > 0x7FFFFFFFull || ci.tile_size_px == 0) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (ci.screen_size[0] == 0 || ci.screen_size[1] == 0) return ORBIT_ERR_INVALID_ARGUMENT;
+    // every pixel must map to a tile inside the grid (cluster.rs:41-43 derives counts with div_ceil)
+    if ((ci.screen_size[0] + ci.tile_size_px - 1u) / ci.tile_size_px > cx || (ci.screen_size[1] + ci.tile_size_px - 1u) / ci.tile_size_px > cy)
+        return ORBIT_ERR_INVALID_ARGUMENT;
+    const uint32_t L = ci.global_light_count;
+    if (L != 0 && (!lights || ((uintptr_t)lights & 15u))) return ORBIT_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint64_t clusters = cx * cy * cz;
+    if (L > c->light_capacity) {
+        if (c->light_view) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->light_view)); c->light_view = nullptr; c->light_capacity = 0; }
+        size_t cap = 1024; while (cap < L) cap *= 2;
+        CK(cudaMalloc(&c->light_view, cap * sizeof(float4)));
+        c->light_capacity = cap;
+    }
+    int rc = ensure_status(c, (size_t)(clusters + 255u) / 256u + 1u);
+    if (rc != ORBIT_OK) return rc;
+    ClusterParams p{};
+    p.info = ci; p.z_scale = params->z_scale; p.z_bias = params->z_bias;
+    p.depth = depth; p.lights = (const uint8_t*)lights; p.light_view = c->light_view;
+    p.tile_masks = (uint32_t*)tile_masks; p.depth_bounds = (uint32_t*)depth_bounds;
+    p.unique_clusters = (uint32_t*)unique_clusters; p.offset_count_image = (uint32_t*)offset_count_image;
+    p.light_index_words = (uint32_t*)light_index_list; p.overflow_flag = &c->status_dev->light_index_overflow;
+    p.capacity_indices = capacity_indices;
+    // fill_buffer(.., 0) of masks and bounds: cluster.rs:447-450; inactive image texels are zeroed (unspecified in the reference)
+    CK(cudaMemsetAsync(tile_masks, 0, cx * cy * 4u, s));
+    CK(cudaMemsetAsync(depth_bounds, 0, clusters * 8u, s));
+    CK(cudaMemsetAsync(offset_count_image, 0, clusters * 8u, s));
+    const uint64_t warps = (uint64_t)((ci.screen_size[0] + 31u) / 32u) * ci.screen_size[1];
+    uint64_t grid = (warps + 7u) / 8u;
+    const uint64_t cap_grid = (uint64_t)c->sm_count * 8u;
+    if (grid > cap_grid) grid = cap_grid;
+    CK(launch_mark_active(p, (int)grid, s));
+    p.scan = next_scan(c);
+    CK(launch_compact_clusters(p, s));
+    CK(launch_light_view(p, s));
+    p.scan = next_scan(c);
+    uint64_t lgrid = (clusters + 7u) / 8u;
+    if (lgrid > cap_grid) lgrid = cap_grid;
+    CK(launch_light_culling(p, (int)lgrid, s));
+    c->launches += (L ? 4 : 3);
+    return ORBIT_OK;
+}
+
+int orbit_draws_scatter(orbit_ctx* c, const void* src, void* dst, uint32_t dst_first, uint32_t total_count,
+                        uint64_t dst_capacity_draws, void* stream) {
+    if (!c || !src || !dst) return ORBIT_ERR_INVALID_ARGUMENT;
+    CK(launch_draws_scatter((const uint32_t*)src, (uint32_t*)dst, dst_first, total_count, dst_capacity_draws,
+                            c->sm_count * 4, (cudaStream_t)stream));
+    c->launches += 1;
+    return ORBIT_OK;
+}
+
+}  // extern "C"
+
+namespace orbit {
+// Copies src's commands into dst at command index dst_first (peer-mapped dst allowed): plain coalesced words.
+__global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                            uint32_t dst_first, uint32_t total_count, uint64_t dst_capacity) {
+    const uint32_t n = __ldcg(src);
+    uint64_t m = n;
+    if ((uint64_t)dst_first >= dst_capacity) m = 0; else if ((uint64_t)dst_first + m > dst_capacity) m = dst_capacity - dst_first;
+    const uint64_t words = m * 7u;
+    const uint32_t* s = src + 1;
+    uint32_t* d = dst + 1u + (uint64_t)dst_first * 7u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) d[i] = __ldcg(s + i);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && total_count != 0xFFFFFFFFu) dst[0] = total_count;
+}
+cudaError_t launch_draws_scatter(const uint32_t* src, uint32_t* dst, uint32_t dst_first, uint32_t total_count,
+                                 uint64_t dst_capacity, int grid, cudaStream_t s) {
+    draws_scatter_kernel<<<grid, 256, 0, s>>>(src, dst, dst_first, total_count, dst_capacity);
+    return cudaGetLastError();
+}
+}  // namespace orbit

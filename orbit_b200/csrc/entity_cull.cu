@@ -1,0 +1,149 @@
+// entity_cull.cu — per-entity frustum + two-pass occlusion cull, LOD select, ordered dispatch-record emission.
+//
+// Stands in for shaders/entity_cull.comp:104-245 driven by create_meshlet_dispatch_command
+// (src/passes/draw_gen.rs:327-380).
+//
+// B200 design: one thread per entity draw as in the reference (256 per CTA), but the reference's
+// `atomicAdd(workgroup_count_x, n)` + per-thread serial record loop (entity_cull.comp:211-223) becomes a CTA
+// scan + decoupled look-back (scan.cuh) followed by load-balanced emission: the CTA's records form one
+// contiguous span, thread j writes record j of the span after a binary search for its owning draw, so stores
+// are dense and the record order is (entity-draw index, chunk) regardless of scheduling. The pass-2
+// visibility word is the warp ballot (reference: subgroupBallot with 32-wide subgroups).
+#include "params.cuh"
+
+namespace orbit {
+
+constexpr int kEcThreads = 256;
+
+
+__global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_constant__ EntityCullParams p) {
+    __shared__ uint32_t s_excl[kEcThreads + 1];   // exclusive record offsets of the tile's draws
+    __shared__ uint32_t s_entity[kEcThreads], s_off[kEcThreads], s_cnt[kEcThreads], s_vo[kEcThreads];
+    __shared__ uint32_t s_warp[kEcThreads / 32];
+    __shared__ uint32_t s_tile, s_base;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const OrbitCullInfo& ci = p.cull;
+    const unsigned int epoch = scan_epoch(p.scan);
+    if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t ntiles = gridDim.x;
+
+    const uint32_t count = min(__ldg(p.entity_draw_words), p.draw_end);
+    const uint32_t gid = p.draw_begin + tile * kEcThreads + tid;
+    const uint32_t pass = ci.occlusion_pass;
+    const bool mocc = ci.meshlet_visibility_buffer != ORBIT_NO_BUFFER;
+
+    uint32_t chunks = 0u;
+    bool visible = false;
+    const bool in_range = gid < count;
+    if (in_range) {
+        const uint32_t entity_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 0u);
+        const uint32_t mesh_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 1u);
+        const uint32_t vis_offset = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 2u);
+        const uint8_t* mi = p.mesh_infos + (size_t)mesh_index * 128u;
+        const float4 sph = __ldg(reinterpret_cast<const float4*>(mi));
+        bool vib = true;
+        if (pass == 1u || pass == 2u) vib = ((__ldcg(p.entity_visibility + (gid >> 5)) >> (gid & 31u)) & 1u) != 0u;
+        visible = (pass == 1u) ? vib : true;
+
+        // view * model (entity_cull.comp:131-133)
+        ModelView mv;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 b = __ldg(p.entities + (size_t)entity_index * 8u + k);
+#pragma unroll
+            for (int row = 0; row < 4; ++row)
+                mv.m[k * 4 + row] = add(add(add(mul(ci.view_matrix.m[0][row], b.x), mul(ci.view_matrix.m[1][row], b.y)),
+                                            mul(ci.view_matrix.m[2][row], b.z)), mul(ci.view_matrix.m[3][row], b.w));
+        }
+        mv.scale = largest_scale(mv.m);
+        Sphere s = transform_sphere(mv, sph.x, sph.y, sph.z, sph.w);
+        if (visible) visible = frustum_test(ci, s);
+        if (pass == 2u && visible) visible = occlusion_test(ci, s, p.hiz);
+        bool should_draw = visible;
+        if (pass == 2u) should_draw = visible && (!vib || mocc);
+        if (should_draw) {
+            const float dx = sub(ci.lod_target_pos_view_space[0], s.x);
+            const float dy = sub(ci.lod_target_pos_view_space[1], s.y);
+            const float dz = sub(ci.lod_target_pos_view_space[2], s.z);
+            const float lod_distance = sub(fsqrt(dot3(dx, dy, dz, dx, dy, dz)), s.r);
+            const float f = fdiv(orbit_log2f(fdiv(fmaxf(lod_distance, 0.0f), ci.lod_base)), orbit_log2f(ci.lod_step));
+            uint32_t lod = f2u(fmaxf(add(f, 1.0f), 0.0f));
+            lod = min(max(lod, ci.min_mesh_lod), ci.max_mesh_lod);
+            const uint32_t lod_count = __ldg(reinterpret_cast<const uint32_t*>(mi + 56));
+            const uint32_t li = min(lod, lod_count - 1u) & 7u;
+            const uint2 L = __ldg(reinterpret_cast<const uint2*>(mi + 64) + li);
+            chunks = (L.y + 31u) >> 5;
+            s_entity[tid] = entity_index; s_off[tid] = L.x; s_cnt[tid] = L.y; s_vo[tid] = vis_offset;
+        }
+    }
+    // pass 2: visibility word of these 32 draws (lanes past `count` contribute 0)
+    const uint32_t vis_mask = __ballot_sync(0xFFFFFFFFu, visible);
+    if (pass == 2u && lane == 0u && gid < count) p.entity_visibility[gid >> 5] = vis_mask;
+
+    // ---- CTA exclusive scan of chunk counts
+    uint32_t incl = chunks;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31u) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t warp_base = 0u, tile_total = 0u;
+#pragma unroll
+    for (int w = 0; w < kEcThreads / 32; ++w) {
+        const uint32_t v = s_warp[w];
+        if ((uint32_t)w < warp) warp_base += v;
+        tile_total += v;
+    }
+    s_excl[tid] = warp_base + incl - chunks;
+    if (tid == 0) s_excl[kEcThreads] = tile_total;
+    if (warp == 0u) {
+        const uint32_t base = lookback_exclusive(p.scan, epoch, tile, tile_total);
+        if (lane == 0u) {
+            s_base = base;
+            if (tile == ntiles - 1u) {
+                p.dispatch_words[0] = base + tile_total;   // workgroup_count_x
+                p.dispatch_words[1] = 1u;                  // fill_buffer {.,1,1}: draw_gen.rs:356-363
+                p.dispatch_words[2] = 1u;
+                if ((uint64_t)base + tile_total > p.capacity_records) *p.overflow_flag = 1u;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- load-balanced emission: record j of the tile's span
+    const uint64_t base = s_base;
+    for (uint32_t j = tid; j < tile_total; j += kEcThreads) {
+        // owner = last draw d with s_excl[d] <= j
+        uint32_t lo = 0u, hi = kEcThreads;
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_excl[mid] <= j) lo = mid; else hi = mid;
+        }
+        // draws with zero chunks share an offset with their successor: step to the last one with that offset
+        // is wrong (it owns nothing) — the search above already returns the LAST d with excl[d] <= j, and a
+        // zero-chunk draw d has excl[d] == excl[d+1], so the last such d is the one that owns record j.
+        const uint32_t k = j - s_excl[lo];
+        const uint64_t out = base + j;
+        if (out < p.capacity_records) {
+            uint32_t* rec = p.dispatch_words + 3u + out * 4u;
+            const uint32_t cnt = s_cnt[lo];
+            rec[0] = s_entity[lo];
+            rec[1] = s_off[lo] + 32u * k;
+            rec[2] = min(cnt - 32u * k, 32u);
+            rec[3] = s_vo[lo] + k;   // every earlier chunk of this draw is full, so += count/32 adds exactly 1 each
+        }
+    }
+    if (tid == 0) scan_cta_exit(p.scan, epoch);
+}
+
+cudaError_t launch_entity_cull(const EntityCullParams& p, uint32_t n_draws, cudaStream_t stream) {
+    const uint32_t grid = (n_draws + kEcThreads - 1) / kEcThreads;
+    entity_cull_kernel<<<grid == 0 ? 1 : grid, kEcThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace orbit

@@ -1,0 +1,271 @@
+// light_cluster.cu — clustered light assignment (sm_100a).
+//
+// Stands in for compute_clusters (src/passes/cluster.rs:368-591) and its three compute shaders:
+//   mark_active.comp:27-57               -> mark_active_kernel
+//   active_cluster_compaction.comp:17-44 -> compact_clusters_kernel
+//   light_culling.comp:34-151            -> light_view_kernel + light_culling_kernel
+//
+// B200 design:
+//   * mark_active: 2-3 global atomics per PIXEL in the reference; here lanes of a warp that hit the same
+//     cluster are merged with match.any + redux (max / or) so one lane per distinct cluster issues the atomics.
+//     atomicMax / atomicOr are order-independent, so the result is deterministic.
+//   * compaction: ballot + CTA scan + decoupled look-back instead of atomicAdd: cluster ids come out ascending.
+//   * light culling: the reference recomputes view*light_position for every (cluster, light) pair and walks
+//     the light list twice; here light view-space spheres are computed once (16 B each, L2-resident), one warp
+//     owns one active cluster and tests 32 lights per step, ballot-compacting hits in ascending order into a
+//     256-entry shared-memory list (the reference's cap), and per-cluster ranges are packed in compacted-list
+//     order by a look-back scan instead of atomicAdd.
+#include "params.cuh"
+
+namespace orbit {
+
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mark_active_kernel(const __grid_constant__ ClusterParams p) {
+    const OrbitClusterCullInfo& ci = p.info;
+    const uint32_t W = ci.screen_size[0], H = ci.screen_size[1];
+    const uint32_t cx = ci.cluster_count[0], cy = ci.cluster_count[1], cz = ci.cluster_count[2];
+    // a warp covers 32 consecutive pixels of one row; rows are distributed over warps
+    const uint32_t warps_per_row = (W + 31u) / 32u;
+    const uint64_t total_warps = (uint64_t)warps_per_row * H;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t wi = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < total_warps;
+         wi += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t y = (uint32_t)(wi / warps_per_row);
+        const uint32_t x = (uint32_t)(wi % warps_per_row) * 32u + lane;
+        uint32_t cluster = 0xFFFFFFFFu, tile = 0xFFFFFFFFu, mask = 0u, bmin = 0u, bmax = 0u;
+        if (x < W) {
+            const float d = __ldg(p.depth + (size_t)y * W + x);
+            const uint32_t tx = x / ci.tile_size_px, ty = y / ci.tile_size_px;
+            const float z = fdiv(ci.z_near, d);
+            const uint32_t slice = f2u(fma_(orbit_log2f(z), p.z_scale, p.z_bias));
+            mask = shl1(slice);
+            if (mask != 0u) tile = tx + ty * cx;
+            if (slice < cz) {
+                cluster = tx + ty * cx + slice * cx * cy;
+                bmin = __float_as_uint(sub(1.0f, d));
+                bmax = __float_as_uint(d);
+            }
+        }
+        // merge lanes hitting the same cluster / tile
+        const uint32_t peers_c = __match_any_sync(0xFFFFFFFFu, cluster);
+        const uint32_t mn = __reduce_max_sync(peers_c, bmin);
+        const uint32_t mx = __reduce_max_sync(peers_c, bmax);
+        if (cluster != 0xFFFFFFFFu && lane == (uint32_t)(__ffs((int)peers_c) - 1)) {
+            atomicMax(p.depth_bounds + 2u * (size_t)cluster, mn);
+            atomicMax(p.depth_bounds + 2u * (size_t)cluster + 1u, mx);
+        }
+        const uint32_t peers_t = __match_any_sync(0xFFFFFFFFu, tile);
+        const uint32_t orm = __reduce_or_sync(peers_t, mask);
+        if (tile != 0xFFFFFFFFu && lane == (uint32_t)(__ffs((int)peers_t) - 1)) atomicOr(p.tile_masks + tile, orm);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) compact_clusters_kernel(const __grid_constant__ ClusterParams p) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_tile, s_base;
+    const OrbitClusterCullInfo& ci = p.info;
+    const uint32_t cx = ci.cluster_count[0], cy = ci.cluster_count[1], cz = ci.cluster_count[2];
+    const uint32_t total = cx * cy * cz;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned int epoch = scan_epoch(p.scan);
+    if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t idx = tile * 256u + tid;
+    bool active = false;
+    if (idx < total) {
+        const uint32_t z = idx / (cx * cy);
+        const uint32_t t = idx - z * cx * cy;   // tile index = x + y*cx
+        active = (__ldcg(p.tile_masks + t) & shl1(z)) != 0u;
+    }
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, active);
+    if (lane == 0u) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t warp_base = 0u, tile_total = 0u;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t v = s_warp[w]; if ((uint32_t)w < warp) warp_base += v; tile_total += v; }
+    if (warp == 0u) {
+        const uint32_t base = lookback_exclusive(p.scan, epoch, tile, tile_total);
+        if (lane == 0u) {
+            s_base = base;
+            if (tile == gridDim.x - 1u) {
+                const uint32_t n = base + tile_total;
+                p.unique_clusters[0] = (n + 255u) / 256u;   // div_ceil(cluster_count, 256)
+                p.unique_clusters[1] = 1u;
+                p.unique_clusters[2] = 1u;
+                p.unique_clusters[3] = n;
+            }
+        }
+    }
+    __syncthreads();
+    if (active) p.unique_clusters[4u + s_base + warp_base + __popc(bal & ((1u << lane) - 1u))] = idx;
+    if (tid == 0) scan_cta_exit(p.scan, epoch);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) light_view_kernel(const __grid_constant__ ClusterParams p) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.info.global_light_count) return;
+    const uint8_t* l = p.lights + (size_t)j * 64u;
+    const uint32_t type = __ldg(reinterpret_cast<const uint32_t*>(l));
+    const float4 pos = __ldg(reinterpret_cast<const float4*>(l + 32));      // position xyz, inner_radius
+    const float radius = __ldg(reinterpret_cast<const float*>(l + 60));
+    const float* m = &p.info.world_to_view_matrix.m[0][0];
+    float4 o;
+    o.x = add(add(add(mul(m[0], pos.x), mul(m[4], pos.y)), mul(m[8], pos.z)), mul(m[12], 1.0f));
+    o.y = add(add(add(mul(m[1], pos.x), mul(m[5], pos.y)), mul(m[9], pos.z)), mul(m[13], 1.0f));
+    o.z = add(add(add(mul(m[2], pos.x), mul(m[6], pos.y)), mul(m[10], pos.z)), mul(m[14], 1.0f));
+    o.w = (type == ORBIT_LIGHT_POINT) ? radius : __uint_as_float(0x7F800000u);  // non-point lights always hit
+    p.light_view[j] = o;
+}
+
+constexpr int kLcWarps = 8;
+
+struct Aabb3 { float lo[3], hi[3]; };
+
+__device__ __forceinline__ void unproject(const OrbitClusterCullInfo& ci, float px, float py, float* out) {
+    const float tx = fdiv(px, (float)ci.screen_size[0]), ty = fdiv(py, (float)ci.screen_size[1]);
+    const float clx = sub(mul(tx, 2.0f), 1.0f), cly = sub(mul(sub(1.0f, ty), 2.0f), 1.0f);
+    const float* m = &ci.screen_to_view_matrix.m[0][0];
+    const float vx = add(add(add(mul(m[0], clx), mul(m[4], cly)), mul(m[8], 1.0f)), mul(m[12], 1.0f));
+    const float vy = add(add(add(mul(m[1], clx), mul(m[5], cly)), mul(m[9], 1.0f)), mul(m[13], 1.0f));
+    const float vz = add(add(add(mul(m[2], clx), mul(m[6], cly)), mul(m[10], 1.0f)), mul(m[14], 1.0f));
+    const float vw = add(add(add(mul(m[3], clx), mul(m[7], cly)), mul(m[11], 1.0f)), mul(m[15], 1.0f));
+    out[0] = fdiv(vx, vw); out[1] = fdiv(vy, vw); out[2] = fdiv(vz, vw);
+}
+
+__device__ __forceinline__ void z_plane_point(const float* v, float zd, float* out) {
+    const float dn = add(add(mul(0.0f, v[0]), mul(0.0f, v[1])), mul(-1.0f, v[2]));  // dot((0,0,-1), v)
+    const float t = fdiv(zd, dn);
+    out[0] = mul(v[0], t); out[1] = mul(v[1], t); out[2] = mul(v[2], t);
+}
+
+__device__ __forceinline__ Aabb3 cluster_volume(const ClusterParams& p, uint32_t idx) {
+    const OrbitClusterCullInfo& ci = p.info;
+    const uint32_t cx = ci.cluster_count[0], cy = ci.cluster_count[1];
+    const uint32_t z = idx / (cx * cy);
+    const uint32_t rem = idx - z * cx * cy;
+    const uint32_t y = rem / cx, x = rem - y * cx;
+    const float minx = (float)(x * ci.tile_size_px), miny = (float)(y * ci.tile_size_px);
+    const float maxx = fminf(add(minx, (float)ci.tile_size_px), (float)ci.screen_size[0]);
+    const float maxy = fminf(add(miny, (float)ci.tile_size_px), (float)ci.screen_size[1]);
+    float vmin[3], vmax[3];
+    unproject(ci, minx, miny, vmin);
+    unproject(ci, maxx, maxy, vmax);
+    const float min_d = sub(1.0f, __uint_as_float(__ldcg(p.depth_bounds + 2u * (size_t)idx)));
+    const float max_d = __uint_as_float(__ldcg(p.depth_bounds + 2u * (size_t)idx + 1u));
+    const float cnear = fdiv(ci.z_near, max_d), cfar = fdiv(ci.z_near, min_d);
+    float p0[3], p1[3], p2[3], p3[3];
+    z_plane_point(vmin, cnear, p0); z_plane_point(vmin, cfar, p1);
+    z_plane_point(vmax, cnear, p2); z_plane_point(vmax, cfar, p3);
+    Aabb3 a;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a.lo[k] = fminf(fminf(p0[k], p1[k]), fminf(p2[k], p3[k]));
+        a.hi[k] = fmaxf(fmaxf(p0[k], p1[k]), fmaxf(p2[k], p3[k]));
+    }
+    return a;
+}
+
+__global__ void __launch_bounds__(kLcWarps * 32) light_culling_kernel(const __grid_constant__ ClusterParams p) {
+    __shared__ uint32_t s_list[kLcWarps][ORBIT_MAX_LIGHTS_PER_CLUSTER];
+    __shared__ uint32_t s_warp[kLcWarps];
+    __shared__ uint32_t s_tile;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned int epoch = scan_epoch(p.scan);
+    const uint32_t nactive = __ldcg(p.unique_clusters + 3);
+    const uint32_t ntiles = (nactive + kLcWarps - 1) / kLcWarps;
+    const uint32_t L = p.info.global_light_count;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) {
+            if (tile == 0u && tid == 0) p.light_index_words[0] = 0u;
+            break;
+        }
+        const uint32_t a = tile * kLcWarps + warp;
+        uint32_t count = 0u, idx = 0u;
+        if (a < nactive) {
+            idx = __ldcg(p.unique_clusters + 4u + a);
+            const Aabb3 box = cluster_volume(p, idx);
+            for (uint32_t j0 = 0; j0 < L && count < ORBIT_MAX_LIGHTS_PER_CLUSTER; j0 += 32u) {
+                const uint32_t j = j0 + lane;
+                bool hit = false;
+                if (j < L) {
+                    const float4 s = __ldg(p.light_view + j);
+                    float acc = 0.0f;
+                    const float c[3] = {s.x, s.y, s.z};
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float v = c[k];
+                        if (v < box.lo[k]) { const float t = sub(box.lo[k], v); acc = fma_(t, t, acc); }
+                        if (v > box.hi[k]) { const float t = sub(v, box.hi[k]); acc = fma_(t, t, acc); }
+                    }
+                    hit = acc <= mul(s.w, s.w);
+                }
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
+                if (hit) {
+                    const uint32_t r = count + __popc(bal & ((1u << lane) - 1u));
+                    if (r < ORBIT_MAX_LIGHTS_PER_CLUSTER) s_list[warp][r] = j;
+                }
+                count += __popc(bal);
+            }
+            count = min(count, ORBIT_MAX_LIGHTS_PER_CLUSTER);
+        }
+        if (lane == 0u) s_warp[warp] = count;
+        __syncthreads();
+        if (warp == 0u) {
+            const uint32_t v = lane < (uint32_t)kLcWarps ? s_warp[lane] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int d = 1; d < kLcWarps; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (uint32_t)d) incl += t;
+            }
+            const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, incl, kLcWarps - 1);
+            const uint32_t base = lookback_exclusive(p.scan, epoch, tile, tile_total);
+            if (lane < (uint32_t)kLcWarps) s_warp[lane] = base + incl - v;
+            if (lane == 0u && tile == ntiles - 1u) {
+                p.light_index_words[0] = base + tile_total;
+                if ((uint64_t)base + tile_total > p.capacity_indices) *p.overflow_flag = 1u;
+            }
+        }
+        __syncthreads();
+        if (a < nactive) {
+            const uint32_t off = s_warp[warp];
+            for (uint32_t k = lane; k < count; k += 32u)
+                if ((uint64_t)off + k < p.capacity_indices) p.light_index_words[1u + off + k] = s_list[warp][k];
+            if (lane == 0u) {
+                p.offset_count_image[2u * (size_t)idx] = off;
+                p.offset_count_image[2u * (size_t)idx + 1u] = count;
+            }
+        }
+    }
+    if (tid == 0) scan_cta_exit(p.scan, epoch);
+}
+
+cudaError_t launch_mark_active(const ClusterParams& p, int grid, cudaStream_t s) {
+    mark_active_kernel<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_compact_clusters(const ClusterParams& p, cudaStream_t s) {
+    const uint32_t total = p.info.cluster_count[0] * p.info.cluster_count[1] * p.info.cluster_count[2];
+    compact_clusters_kernel<<<(total + 255u) / 256u, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_light_view(const ClusterParams& p, cudaStream_t s) {
+    const uint32_t L = p.info.global_light_count;
+    if (L == 0) return cudaSuccess;
+    light_view_kernel<<<(L + 255u) / 256u, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_light_culling(const ClusterParams& p, int grid, cudaStream_t s) {
+    light_culling_kernel<<<grid, kLcWarps * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace orbit

@@ -1,0 +1,75 @@
+// params.cuh — kernel parameter blocks (passed by value as __grid_constant__) and launcher prototypes shared by
+// api.cu and the kernel translation units.
+#pragma once
+#include "orbit_device.cuh"
+#include "scan.cuh"
+
+namespace orbit {
+
+struct MeshletCullParams {
+    OrbitCullInfo cull;
+    HizDevice hiz;
+    const uint32_t* dispatch_words;   // MeshletDispatchBuffer as u32[]: x,y,z then 4 words per record
+    const uint4* meshlets;            // 2 x uint4 per meshlet
+    const float4* entities;           // 8 x float4 per entity (model matrix = first 4)
+    const uint8_t* materials;
+    uint32_t* meshlet_visibility;
+    uint32_t* draw_words;             // MeshletDrawCommandBuffer as u32[]: count then 7 words per command
+    uint32_t* task_payloads;          // nullable, 11 words per record
+    uint32_t* overflow_flag;          // host-mapped status word
+    uint64_t capacity_records;
+    uint64_t capacity_draws;
+    ScanState scan;
+};
+
+struct EntityCullParams {
+    OrbitCullInfo cull;
+    HizDevice hiz;
+    const uint32_t* entity_draw_words;   // EntityDrawBuffer as u32[]: count then 3 words per draw
+    const uint8_t* mesh_infos;           // 128 B each
+    const float4* entities;              // 8 x float4 each
+    uint32_t* entity_visibility;
+    uint32_t* dispatch_words;            // MeshletDispatchBuffer as u32[]: x,y,z then 4 words per record
+    uint32_t* overflow_flag;
+    uint64_t capacity_records;
+    uint32_t draw_begin, draw_end;       // sub-range of draws covered by this launch (begin % 32 == 0)
+    ScanState scan;
+};
+
+struct HizBuildParams {
+    const float* depth;
+    float* texels;
+    uint32_t depth_w, depth_h;
+    uint32_t width, height, levels;
+    uint32_t level_offset[ORBIT_HIZ_MAX_LEVELS];
+    unsigned int* ticket;  // zero on entry, re-zeroed by the last CTA
+};
+
+struct ClusterParams {
+    OrbitClusterCullInfo info;
+    float z_scale, z_bias;
+    const float* depth;
+    const uint8_t* lights;            // OrbitLightData[]
+    float4* light_view;               // scratch: (view xyz, outer_radius or +inf for non-point lights)
+    uint32_t* tile_masks;
+    uint32_t* depth_bounds;           // 2 words per cluster
+    uint32_t* unique_clusters;        // 4-word header + indices
+    uint32_t* offset_count_image;     // 2 words per cluster
+    uint32_t* light_index_words;      // count + indices
+    uint32_t* overflow_flag;
+    uint64_t capacity_indices;
+    ScanState scan;
+};
+
+cudaError_t launch_meshlet_cull(const MeshletCullParams&, int recs_per_warp, int grid, cudaStream_t);
+int meshlet_cull_max_ctas_per_sm(int recs_per_warp);
+cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, cudaStream_t);
+cudaError_t launch_hiz_build(const HizBuildParams&, cudaStream_t);
+cudaError_t launch_mark_active(const ClusterParams&, int grid, cudaStream_t);
+cudaError_t launch_compact_clusters(const ClusterParams&, cudaStream_t);
+cudaError_t launch_light_view(const ClusterParams&, cudaStream_t);
+cudaError_t launch_light_culling(const ClusterParams&, int grid, cudaStream_t);
+cudaError_t launch_draws_scatter(const uint32_t* src, uint32_t* dst, uint32_t dst_first, uint32_t total_count,
+                                 uint64_t dst_capacity, int grid, cudaStream_t);
+
+}  // namespace orbit

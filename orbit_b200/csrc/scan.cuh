@@ -1,0 +1,91 @@
+// scan.cuh — device-wide ordered compaction support: single-pass scan with decoupled look-back.
+//
+// Replaces the reference's `atomicAdd` appends (entity_cull.comp:211, meshlet_cull.comp:228,
+// active_cluster_compaction.comp:30, light_culling.comp:133) with a deterministic exclusive prefix over tiles.
+// A tile publishes {epoch, flag, value} as ONE 64-bit word, so no fence is needed between flag and value, and
+// the epoch makes every descriptor of an earlier launch read as "not ready" — no memset between launches.
+// The epoch lives in device memory and is advanced by the last CTA of every launch (graph-replay safe).
+// Tiles are handed out by an atomic ticket, so a tile's predecessors are always owned by running CTAs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace orbit {
+
+struct ScanState {
+    unsigned long long* status;  // one descriptor per tile
+    unsigned int* ticket;        // next tile to hand out
+    unsigned int* done;          // CTAs that finished (the last one resets ticket/done for the next launch)
+    unsigned int* epoch;         // launch id in DEVICE memory (1..2^30-1), advanced by the last CTA of each launch,
+                                 // so a CUDA graph that replays the same kernel node still gets a fresh epoch
+};
+
+// Every thread of a scan kernel reads the epoch once at kernel start (it only changes at the very end of a launch).
+__device__ __forceinline__ unsigned int scan_epoch(const ScanState& st) { return __ldcg(st.epoch); }
+
+enum : unsigned int { kFlagAggregate = 1u, kFlagInclusive = 2u };
+
+__device__ __forceinline__ unsigned long long pack_status(unsigned int epoch, unsigned int flag, unsigned int value) {
+    return ((unsigned long long)((epoch << 2) | flag) << 32) | value;
+}
+__device__ __forceinline__ void publish(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long peek(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by all 32 lanes of ONE warp of the CTA that owns `tile`. Returns the exclusive prefix of `aggregate`
+// over tiles 0..tile-1 (same value in every lane) and publishes this tile's inclusive prefix.
+__device__ __forceinline__ unsigned int lookback_exclusive(const ScanState& st, unsigned int epoch, unsigned int tile, unsigned int aggregate) {
+    const unsigned int lane = threadIdx.x & 31u;
+    if (tile == 0u) {
+        if (lane == 0u) publish(st.status, pack_status(epoch, kFlagInclusive, aggregate));
+        return 0u;
+    }
+    if (lane == 0u) publish(st.status + tile, pack_status(epoch, kFlagAggregate, aggregate));
+    unsigned int exclusive = 0u;
+    int pos = (int)tile - 1;
+    while (true) {
+        const int idx = pos - (int)lane;
+        unsigned int flag, value;
+        if (idx >= 0) {
+            while (true) {
+                unsigned long long w = peek(st.status + idx);
+                unsigned int hi = (unsigned int)(w >> 32);
+                if ((hi >> 2) == epoch && (hi & 3u) != 0u) { flag = hi & 3u; value = (unsigned int)w; break; }
+                __nanosleep(32);
+            }
+        } else {
+            flag = kFlagInclusive; value = 0u;  // virtual tile -1: inclusive prefix 0
+        }
+        const unsigned int incl = __ballot_sync(0xFFFFFFFFu, flag == kFlagInclusive);
+        // lanes are ordered nearest predecessor first; stop at the first inclusive descriptor
+        const unsigned int first = (unsigned int)__ffs((int)incl) - 1u;  // incl != 0 eventually (virtual tile)
+        const bool take = (incl == 0u) || (lane <= first);
+        unsigned int v = take ? value : 0u;
+        v = __reduce_add_sync(0xFFFFFFFFu, v);
+        exclusive += v;
+        if (incl != 0u) break;
+        pos -= 32;
+    }
+    if (lane == 0u) publish(st.status + tile, pack_status(epoch, kFlagInclusive, exclusive + aggregate));
+    return exclusive;
+}
+
+// Every CTA calls this once on exit (one thread). The last CTA re-arms the ticket for the next launch.
+__device__ __forceinline__ void scan_cta_exit(const ScanState& st, unsigned int epoch) {
+    __threadfence();
+    unsigned int prev = atomicAdd(st.done, 1u);
+    if (prev + 1u == gridDim.x) {
+        *st.ticket = 0u;
+        *st.done = 0u;
+        unsigned int next = (epoch + 1u) & 0x3FFFFFFFu;
+        *st.epoch = next ? next : 1u;
+        __threadfence();
+    }
+}
+
+}  // namespace orbit

@@ -1,0 +1,184 @@
+"""The caller protocol of the culling passes, as ForwardRenderer / ShadowRenderer drive them.
+
+    ForwardRenderer::render_depth_prepass   src/passes/forward.rs:213-430
+        EARLY (pass 1, VisibilityRead) -> Hi-Z update -> LATE (pass 2, VisibilityWrite)
+    ForwardRenderer::render                 src/passes/forward.rs:518-548   MAIN (pass 1 again, updated bits)
+    ShadowRenderer::render_shadow_map       src/passes/shadow_renderer.rs:391-403,693-707   pass 0, orthographic
+
+The reference rasterises between the passes; here the depth buffer that feeds the Hi-Z build is an input
+(bench / tests generate it procedurally, a real host would share its depth attachment through
+cudaImportExternalMemory).
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import layouts as L
+from .passes import (AssetGraphData, Context, CullInfo, DepthPyramid, OcclusionCullInfo, Projection, SceneGraphData,
+                     create_meshlet_dispatch_command, create_meshlet_draw_commands)
+
+
+@dataclass
+class DeviceScene:
+    assets: AssetGraphData
+    scene: SceneGraphData
+    n_visibility_words: int
+    n_entities: int
+
+    @staticmethod
+    def upload(context: Context, s, draw_begin=0, draw_end=0, lights=None):
+        assets = AssetGraphData(context.upload(s.mesh_infos), context.upload(s.meshlets), context.upload(s.materials))
+        scene = SceneGraphData(entity_draw_count=s.n_entities, entity_draw_buffer=context.upload(s.entity_draws),
+                               entity_buffer=context.upload(s.entities), draw_begin=draw_begin, draw_end=draw_end,
+                               record_capacity=s.n_records_lod0, draw_capacity=s.n_meshlet_instances)
+        if lights is not None:
+            scene.light_count = len(lights)
+            scene.light_data_buffer = context.upload(lights)
+        return DeviceScene(assets, scene, s.n_visibility_words, s.n_entities)
+
+
+class ViewState:
+    """Cross-frame state of one view: the two visibility bitmasks (forward.rs:104-106,150-157; scene.rs:364) and
+    the depth pyramid. The reference never clears the bitmasks; the harness defines frame 0 as all zeros."""
+
+    def __init__(self, context, dscene, size, name="view"):
+        self.entity_visibility = torch.zeros((dscene.n_entities + 31) // 32 + 1, dtype=torch.int32, device=context.device)
+        self.meshlet_visibility = torch.zeros(max(dscene.n_visibility_words, 1), dtype=torch.int32, device=context.device)
+        self.depth_pyramid = DepthPyramid(context, name + "_depth_pyramid", size)
+
+
+def projection_of(view):
+    if view.projection_type == L.PROJ_PERSPECTIVE:
+        return Projection.perspective(view.fov, view.near)
+    return Projection.orthographic(view.half_width, view.near, view.far)
+
+
+def cull_info_for(view, occlusion: OcclusionCullInfo, frustum_culling=True):
+    return CullInfo(view_matrix=view.view, view_space_cull_planes=view.planes if frustum_culling else [],
+                    projection=projection_of(view), occlusion_culling=occlusion,
+                    lod_range=view.lod_range, lod_base=view.lod_base, lod_step=view.lod_step,
+                    lod_target_pos_view_space=view.lod_target_view)
+
+
+def cull_pass(context, name, dscene, cull_info, task_payloads=None):
+    """create_meshlet_dispatch_command + create_meshlet_draw_commands for one CullInfo."""
+    _, dispatch = create_meshlet_dispatch_command(context, name, dscene.assets, dscene.scene, cull_info)
+    draws = create_meshlet_draw_commands(context, name, dscene.assets, dscene.scene, cull_info, dispatch, task_payloads)
+    return dispatch, draws
+
+
+def depth_prepass_culling(context, dscene, vstate, view, depth_buffer, meshlet_occlusion=True, name="forward_depth_prepass"):
+    """EARLY -> Hi-Z -> LATE (forward.rs:266-403). Returns {(stage): (dispatch_buffer, draw_buffer)}."""
+    mvis = vstate.meshlet_visibility if meshlet_occlusion else None
+    early = cull_info_for(view, OcclusionCullInfo("read", vstate.entity_visibility, mvis))
+    out = {"early": cull_pass(context, "early_" + name, dscene, early)}
+    vstate.depth_pyramid.update(depth_buffer)
+    late = cull_info_for(view, OcclusionCullInfo("write", vstate.entity_visibility, mvis, vstate.depth_pyramid,
+                                                 noskip_alphamode=0, aspect_ratio=view.aspect))
+    out["late"] = cull_pass(context, "late_" + name, dscene, late)
+    return out
+
+
+def main_pass_culling(context, dscene, vstate, view, meshlet_occlusion=True, name="forward"):
+    """MAIN pass (forward.rs:518-548): pass 1 with the bits the late pass just wrote."""
+    mvis = vstate.meshlet_visibility if meshlet_occlusion else None
+    info = cull_info_for(view, OcclusionCullInfo("read", vstate.entity_visibility, mvis))
+    return cull_pass(context, name, dscene, info)
+
+
+def shadow_pass_culling(context, dscene, view, name="shadow"):
+    """One cascade (shadow_renderer.rs:693-707): pass 0, no occlusion."""
+    return cull_pass(context, name, dscene, cull_info_for(view, OcclusionCullInfo("none")))
+
+
+def read_dispatch(buf):
+    """Device MeshletDispatchBuffer -> (count, records ndarray)."""
+    hdr = buf[:12].cpu().numpy().view(np.uint32)
+    n = int(hdr[0])
+    recs = buf[12:12 + 16 * n].cpu().numpy().view(L.dispatch_dtype)
+    return hdr.copy(), recs
+
+
+def read_draws(buf, capacity=None):
+    n = int(buf[:4].cpu().numpy().view(np.uint32)[0])
+    m = n if capacity is None else min(n, capacity)
+    return n, buf[4:4 + 28 * m].cpu().numpy().view(L.draw_command_dtype)
+
+
+class PreparedFrame:
+    """One view's depth-prepass culling (EARLY -> Hi-Z -> LATE) with every argument packed once.
+
+    The reference re-declares the passes each frame on its render graph; the packed form is the CUDA analogue:
+    five asynchronous launches on one stream, optionally captured into a CUDA graph (`capture()` / `replay()`) so
+    a frame costs one graph launch. Safe to replay: the scan epoch and tickets live in device memory."""
+
+    def __init__(self, context, dscene, vstate, view, depth_buffer, meshlet_occlusion=True, name="forward_depth_prepass"):
+        import ctypes as C
+        from . import _lib
+        from .passes import _ptr, _scene_buffers
+        self.context, self.dscene, self.vstate, self.view, self.depth = context, dscene, vstate, view, depth_buffer
+        self._lib, self._C, self._ptr = _lib.lib(), C, _ptr
+        mvis = vstate.meshlet_visibility if meshlet_occlusion else None
+        early = cull_info_for(view, OcclusionCullInfo("read", vstate.entity_visibility, mvis))
+        late = cull_info_for(view, OcclusionCullInfo("write", vstate.entity_visibility, mvis, vstate.depth_pyramid,
+                                                     noskip_alphamode=0, aspect_ratio=view.aspect))
+        self.g_early, self.g_late = early.to_gpu(), late.to_gpu()
+        self.sb_early = _scene_buffers(dscene.assets, dscene.scene, early)
+        self.sb_late = _scene_buffers(dscene.assets, dscene.scene, late)
+        sc = dscene.scene
+        self.rcap = int(sc.record_capacity) or 1_000_000
+        self.dcap = int(sc.draw_capacity) or 1_000_000
+        mk = context.create_transient
+        self.early_dispatch = mk("early_" + name + "_meshlet_dispatch_buffer", L.DISPATCH_HEADER + 16 * self.rcap)
+        self.early_draws = mk("early_" + name + "_meshlet_draw_command_buffer", L.DRAW_HEADER + 28 * self.dcap)
+        self.late_dispatch = mk("late_" + name + "_meshlet_dispatch_buffer", L.DISPATCH_HEADER + 16 * self.rcap)
+        self.late_draws = mk("late_" + name + "_meshlet_draw_command_buffer", L.DRAW_HEADER + 28 * self.dcap)
+        self.graph = None
+        h, w = depth_buffer.shape
+        self._hw = (w, h)
+
+    def _stream(self):
+        return self._C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def entity(self, late, s=None):
+        C, lib, p = self._C, self._lib, self._ptr
+        s = s or self._stream()
+        g, sb, out = (self.g_late, self.sb_late, self.late_dispatch) if late else (self.g_early, self.sb_early, self.early_dispatch)
+        rc = lib.orbit_entity_cull(self.context._h, C.byref(g), C.byref(sb), self.vstate.depth_pyramid._h if late else None,
+                                   p(out), self.rcap, s)
+        if rc:
+            raise RuntimeError("orbit_entity_cull: %d" % rc)
+
+    def meshlet(self, late, s=None):
+        C, lib, p = self._C, self._lib, self._ptr
+        s = s or self._stream()
+        g, sb, disp, out = ((self.g_late, self.sb_late, self.late_dispatch, self.late_draws) if late
+                            else (self.g_early, self.sb_early, self.early_dispatch, self.early_draws))
+        rc = lib.orbit_meshlet_cull(self.context._h, C.byref(g), C.byref(sb), self.vstate.depth_pyramid._h if late else None,
+                                    p(disp), self.rcap, p(out), self.dcap, None, s)
+        if rc:
+            raise RuntimeError("orbit_meshlet_cull: %d" % rc)
+
+    def hiz(self, s=None):
+        s = s or self._stream()
+        rc = self._lib.orbit_hiz_build(self.context._h, self.vstate.depth_pyramid._h, self._ptr(self.depth), self._hw[0], self._hw[1], s)
+        if rc:
+            raise RuntimeError("orbit_hiz_build: %d" % rc)
+
+    def launch(self):
+        s = self._stream()
+        self.entity(False, s); self.meshlet(False, s); self.hiz(s); self.entity(True, s); self.meshlet(True, s)
+
+    def capture(self):
+        self.launch()  # warm: scratch growth / occupancy queries must not happen during capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.launch()
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
