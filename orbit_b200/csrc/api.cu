@@ -28,12 +28,16 @@ struct orbit_ctx {
     // device-written status, pinned + mapped
     OrbitStatus* status_host = nullptr;
     OrbitStatus* status_dev = nullptr;
+    // meshlet stage scratch: one draw mask per dispatch record
+    uint32_t* draw_masks = nullptr;
+    size_t draw_mask_capacity = 0;
     // light scratch
     float4* light_view = nullptr;
     size_t light_capacity = 0;
     // tuning (ORBIT_MC_RECS_PER_WARP / ORBIT_MC_CTAS_PER_SM environment overrides, read once)
     int mc_recs_per_warp = 4;
     int mc_ctas_per_sm = 0;
+    int mc_occupancy = 0;             // cached cudaOccupancyMaxActiveBlocksPerMultiprocessor of the meshlet kernel
     std::atomic<uint64_t> launches{0};
 };
 
@@ -110,7 +114,7 @@ int orbit_ctx_create(int device, orbit_ctx** out) {
     CK(cudaHostGetDevicePointer(&c->status_dev, c->status_host, 0));
     int rc = ensure_status(c, 4096);
     if (rc != ORBIT_OK) return rc;
-    if (const char* s = std::getenv("ORBIT_MC_RECS_PER_WARP")) { int v = std::atoi(s); if (v == 1 || v == 2 || v == 4) c->mc_recs_per_warp = v; }
+    if (const char* s = std::getenv("ORBIT_MC_RECS_PER_WARP")) { int v = std::atoi(s); if (v == 2 || v == 4 || v == 8) c->mc_recs_per_warp = v; }
     if (const char* s = std::getenv("ORBIT_MC_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->mc_ctas_per_sm = v; }
     *out = c;
     return ORBIT_OK;
@@ -120,7 +124,7 @@ void orbit_ctx_destroy(orbit_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view);
+    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->draw_masks);
     cudaFreeHost(c->status_host);
     delete c;
 }
@@ -261,10 +265,13 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     // The record count lives on the device (the reference's dispatch_indirect); scratch and grid are sized for
     // the dispatch buffer's capacity and the kernel clamps the device-side count to it.
     const int rpw = c->mc_recs_per_warp;
-    const uint32_t recs_per_tile = 8u * (uint32_t)rpw;
     const uint64_t max_records = capacity_records;
-    rc = ensure_status(c, (size_t)((max_records + recs_per_tile - 1u) / recs_per_tile) + 1u);
-    if (rc != ORBIT_OK) return rc;
+    if (max_records > c->draw_mask_capacity) {
+        if (c->draw_masks) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->draw_masks)); c->draw_masks = nullptr; c->draw_mask_capacity = 0; }
+        size_t cap = 65536; while (cap < max_records) cap *= 2;
+        CK(cudaMalloc(&c->draw_masks, cap * sizeof(uint32_t)));
+        c->draw_mask_capacity = cap;
+    }
     MeshletCullParams p{};
     p.cull = *cull; p.hiz = hiz_device(hiz);
     p.dispatch_words = (const uint32_t*)meshlet_dispatch_buffer;
@@ -275,18 +282,18 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     p.draw_words = (uint32_t*)draw_command_buffer;
     p.task_payloads = (uint32_t*)task_payloads;
     p.overflow_flag = &c->status_dev->draw_overflow;
+    p.draw_masks = c->draw_masks;
     p.capacity_records = max_records;
     p.capacity_draws = capacity_draws;
     p.scan = next_scan(c);
+    // one co-resident grid (CTAs wait on each other's aggregates): never more CTAs than fit at once
+    if (c->mc_occupancy <= 0) c->mc_occupancy = meshlet_cull_max_ctas_per_sm(rpw);
+    const int occ = c->mc_occupancy;
     int per_sm = c->mc_ctas_per_sm;
-    if (per_sm <= 0) {
-        per_sm = meshlet_cull_max_ctas_per_sm(rpw);
-        if (per_sm <= 0) per_sm = 1;
-        c->mc_ctas_per_sm = per_sm;
-    }
-    uint64_t grid = (uint64_t)c->sm_count * (uint64_t)per_sm;
-    const uint64_t max_tiles = (max_records + recs_per_tile - 1u) / recs_per_tile;
-    if (grid > max_tiles) grid = max_tiles ? max_tiles : 1u;
+    if (per_sm <= 0 || per_sm > occ) per_sm = occ > 0 ? occ : 1;
+    const uint64_t grid = (uint64_t)c->sm_count * (uint64_t)per_sm;
+    rc = ensure_status(c, (size_t)grid + 1u);
+    if (rc != ORBIT_OK) return rc;
     CK(launch_meshlet_cull(p, rpw, (int)grid, (cudaStream_t)stream));
     c->launches += 1;
     return ORBIT_OK;

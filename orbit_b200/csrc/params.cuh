@@ -17,6 +17,7 @@ struct MeshletCullParams {
     uint32_t* draw_words;             // MeshletDrawCommandBuffer as u32[]: count then 7 words per command
     uint32_t* task_payloads;          // nullable, 11 words per record
     uint32_t* overflow_flag;          // host-mapped status word
+    uint32_t* draw_masks;             // scratch: one draw mask per dispatch record (phase 1 -> phase 2)
     uint64_t capacity_records;
     uint64_t capacity_draws;
     ScanState scan;
@@ -63,6 +64,7 @@ struct ClusterParams {
 
 cudaError_t launch_meshlet_cull(const MeshletCullParams&, int recs_per_warp, int grid, cudaStream_t);
 int meshlet_cull_max_ctas_per_sm(int recs_per_warp);
+int meshlet_cull_tile_records(int recs_per_warp);
 cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, cudaStream_t);
 cudaError_t launch_hiz_build(const HizBuildParams&, cudaStream_t);
 cudaError_t launch_mark_active(const ClusterParams&, int grid, cudaStream_t);

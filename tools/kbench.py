@@ -37,7 +37,7 @@ def main():
     scene, _ = scenes.config_c2()
     view = bench.c2_view(scenes, scene, 0)
     depth_np = scenes.make_depth(scene, view)
-    configs = [(None, None)] if which == "default" else list(itertools.product([1, 2, 4], [1, 2, 3, 4, 6, 8]))
+    configs = [(None, None)] if which == "default" else list(itertools.product([2, 4, 8], [1, 2, 3]))
     for rpw, cps in configs:
         if rpw is not None:
             os.environ["ORBIT_MC_RECS_PER_WARP"] = str(rpw)
