@@ -277,6 +277,31 @@ void oracle_hiz_geometry(uint32_t dw, uint32_t dh, OrbitHizInfo* out) { hiz_geom
 float oracle_log2f(float x) { return orbit_log2f(x); }
 uint32_t oracle_hiz_level(float x, uint32_t levels) { return hiz_level(x, levels, nullptr); }
 
+// Leaf predicates exposed for unit tests (tests/test_oracle_leaf.py).
+// project_sphere + sphere_closest_depth (entity_cull.comp:83-102,152-163). c = view-space centre as the
+// shader sees it BEFORE the in-place negation of z. out = {aabb.x, aabb.y, aabb.z, aabb.w, depth, cullable}.
+void oracle_project_sphere(float cx, float cy, float cz, float r_model, float scale, float z_near, float p00, float p11, float* out) {
+    float zp = -cz;
+    float r = r_model * scale, nr = -r;
+    out[5] = (zp >= std::fmaf(r_model, scale, z_near)) ? 1.0f : 0.0f;
+    float c0 = -cx, c1 = -zp;
+    float sx = std::sqrt(std::fmaf(nr, r, dot2(c0, c1, c0, c1)));
+    float minx0 = sx * c0 + nr * c1, minx1 = r * c0 + sx * c1, maxx0 = sx * c0 + r * c1, maxx1 = nr * c0 + sx * c1;
+    float d0 = -cy;
+    float sy = std::sqrt(std::fmaf(nr, r, dot2(d0, c1, d0, c1)));
+    float miny0 = sy * d0 + nr * c1, miny1 = r * d0 + sy * c1, maxy0 = sy * d0 + r * c1, maxy1 = nr * d0 + sy * c1;
+    float a0 = minx0 / minx1 * p00, a1 = miny0 / miny1 * p11, a2 = maxx0 / maxx1 * p00, a3 = maxy0 / maxy1 * p11;
+    out[0] = std::fmaf(a0, 0.5f, 0.5f); out[1] = std::fmaf(a3, -0.5f, 0.5f);
+    out[2] = std::fmaf(a2, 0.5f, 0.5f); out[3] = std::fmaf(a1, -0.5f, 0.5f);
+    out[4] = z_near / std::fmaf(-r_model, scale, zp);
+}
+
+// coneCull (meshlet_cull.comp:104-106) in the perspective case: returns 1 when the meshlet is back-facing.
+int oracle_cone_cull(float cx, float cy, float cz, float r, float ax, float ay, float az, float cutoff) {
+    V3 c{cx, cy, cz}, a{ax, ay, az};
+    return dot3(c, a) >= std::fmaf(cutoff, length3(c), r) ? 1 : 0;
+}
+
 // depth_reduce.comp applied level by level (draw_gen.rs:538-564).
 void oracle_hiz_build(const float* depth, uint32_t dw, uint32_t dh, float* texels) {
     OrbitHizInfo g; hiz_geometry(dw, dh, &g);

@@ -1,0 +1,117 @@
+"""Multi-GPU sharding of the visibility pipeline. One process per GPU, torch.distributed for the
+plumbing (NCCL over NVLink on the GPU box, gloo in the CPU tests). The reference is single-GPU; this is new.
+
+Two ways the path shards:
+  1. by VIEW (shadow cascades, many-camera batches): independent units, no data-path collective —
+     `views_for_rank`.
+  2. by MESHLET RANGE of one huge view (C3): the entity-draw array is cut into `world` contiguous ranges with
+     equal LOD-0 meshlet sums (boundaries multiples of 32 draws so visibility words stay disjoint); each rank
+     culls its range; the exchange step is (a) broadcast of the small Hi-Z pyramid from the rank that owns the
+     depth buffer and (b) an all-gather of survivor counts followed by an all-gather of the survivor lists into
+     the rank-major draw list — `partition_draws`, `broadcast_pyramid`, `exchange_survivors`.
+"""
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+DRAW_BYTES = 28
+
+
+def views_for_rank(n_views: int, rank: int, world: int) -> List[int]:
+    """View v is culled by rank v mod world."""
+    return [v for v in range(n_views) if v % world == rank]
+
+
+def partition_draws(meshlet_counts: Sequence[int], world: int) -> List[Tuple[int, int]]:
+    """Cuts draws [0, N) into `world` contiguous ranges of (nearly) equal meshlet sums whose interior boundaries
+    are multiples of 32 draws (entity visibility words are indexed by draw/32). Ranges may be empty."""
+    c = np.asarray(meshlet_counts, dtype=np.int64)
+    n = len(c)
+    prefix = np.concatenate([[0], np.cumsum(c)])
+    total = int(prefix[-1])
+    cuts = [0]
+    for k in range(1, world):
+        target = total * k / world
+        i = int(np.searchsorted(prefix, target, side="left"))
+        i = int(round(i / 32.0)) * 32
+        i = min(max(i, cuts[-1]), n)
+        cuts.append(i)
+    cuts.append(n)
+    return [(cuts[k], cuts[k + 1]) for k in range(world)]
+
+
+def broadcast_pyramid(texels: torch.Tensor, src: int = 0, group=None) -> None:
+    """The pyramid is one contiguous f32 allocation (5.6 MB at 1080p, 22.4 MB at 4K): one broadcast."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(texels, src=src, group=group)
+
+
+def exchange_survivors(local_draw_buffer: torch.Tensor, out_buffer: torch.Tensor = None, group=None):
+    """local_draw_buffer: uint8 MeshletDrawCommandBuffer of this rank (u32 count @0, 28-byte commands @4).
+    Returns (global MeshletDrawCommandBuffer in rank-major order, per-rank counts). Every rank gets the full list."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = local_draw_buffer.device
+    count = local_draw_buffer[:4].view(torch.int32).clone()
+    if world == 1:
+        n = int(count.item())
+        return local_draw_buffer[:4 + DRAW_BYTES * n], [n]
+    counts = torch.zeros(world, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(counts, count, group=group)
+    counts_h = [int(v) for v in counts.cpu().tolist()]
+    total, mx = sum(counts_h), max(counts_h)
+    rank = dist.get_rank(group)
+    # NCCL has no all-gather-v: pad every rank's list to the longest one
+    send = torch.zeros(max(mx, 1) * DRAW_BYTES, dtype=torch.uint8, device=dev)
+    send[:counts_h[rank] * DRAW_BYTES] = local_draw_buffer[4:4 + counts_h[rank] * DRAW_BYTES]
+    gathered = torch.empty(world * send.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, send, group=group)
+    if out_buffer is None or out_buffer.numel() < 4 + DRAW_BYTES * total:
+        out_buffer = torch.empty(4 + DRAW_BYTES * total, dtype=torch.uint8, device=dev)
+    out_buffer[:4] = torch.tensor([total], dtype=torch.int32, device=dev).view(torch.uint8)
+    off = 4
+    for r in range(world):
+        nb = counts_h[r] * DRAW_BYTES
+        out_buffer[off:off + nb] = gathered[r * send.numel():r * send.numel() + nb]
+        off += nb
+    return out_buffer[:4 + DRAW_BYTES * total], counts_h
+
+
+class ShardedView:
+    """One huge view culled by `world` GPUs (BASELINE config C3). Rank 0 owns the depth buffer and builds the
+    pyramid; every rank culls its entity-draw range with the CUDA passes; survivors are all-gathered."""
+
+    def __init__(self, context, scene, view, depth_np, rank, world):
+        from . import frame
+        self.frame = frame
+        self.context, self.view, self.rank, self.world = context, view, rank, world
+        lod0 = scene.mesh_infos["mesh_lods"][:, 0, 1][scene.draws["mesh_index"]]
+        self.ranges = partition_draws(lod0, world)
+        b, e = self.ranges[rank]
+        if b == e:            # empty range: keep the launch legal
+            e = b
+        self.dscene = frame.DeviceScene.upload(context, scene, draw_begin=b, draw_end=e if e > b else b)
+        self.empty = (e <= b)
+        self.vstate = frame.ViewState(context, self.dscene, (view.width, view.height))
+        self.depth = torch.from_numpy(depth_np).to(context.device) if rank == 0 else torch.zeros(
+            (view.height, view.width), dtype=torch.float32, device=context.device)
+        self.prepared = frame.PreparedFrame(context, self.dscene, self.vstate, view, self.depth)
+
+    def step(self, exchange=True):
+        """One two-pass frame: early cull (local range) -> Hi-Z on rank 0 + broadcast -> late cull -> gather."""
+        pf = self.prepared
+        if not self.empty:
+            pf.entity(False); pf.meshlet(False)
+        if self.rank == 0:
+            pf.hiz()
+        broadcast_pyramid(self.vstate.depth_pyramid.texels, src=0)
+        if not self.empty:
+            pf.entity(True); pf.meshlet(True)
+        else:
+            pf.early_draws[:4].zero_(); pf.late_draws[:4].zero_()
+        if not exchange:
+            return None
+        early, _ = exchange_survivors(pf.early_draws)
+        late, _ = exchange_survivors(pf.late_draws)
+        return early, late

@@ -1,0 +1,161 @@
+//! Rust binding of liborbit_b200.so (include/orbit_cuda.h) — the module a fork of Thefefe/orbit would add next to
+//! `src/passes/draw_gen.rs` to route the culling passes through CUDA. SOURCE ONLY: never compiled (no Rust
+//! toolchain in the build image). Layouts are the reference's own `#[repr(C)]` structs, so `GpuCullInfo`,
+//! `GpuEntityDraw`, `GpuMeshlet`, … from `src/passes/draw_gen.rs:208-237`, `src/scene.rs:120-133`,
+//! `src/assets/mod.rs:18-122` can be passed as they are.
+#![allow(non_camel_case_types)]
+use std::ffi::c_void;
+
+pub const ORBIT_OK: i32 = 0;
+pub const ORBIT_NO_BUFFER: u32 = 0xFFFF_FFFF;
+pub const ORBIT_HIZ_MAX_LEVELS: usize = 16;
+
+#[repr(C)] pub struct orbit_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct orbit_hiz { _p: [u8; 0] }
+
+/// = `GpuCullInfo` (draw_gen.rs:208-237), 400 bytes.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct OrbitCullInfo {
+    pub view_matrix: [f32; 16],
+    pub reprojection_matrix: [f32; 16],
+    pub cull_planes: [[f32; 4]; 12],
+    pub cull_plane_count: u32,
+    pub alpha_mode_flags: u32,
+    pub noskip_alpha_mode: u32,
+    pub occlusion_pass: u32,
+    pub visibility_buffer: u32,
+    pub meshlet_visibility_buffer: u32,
+    pub depth_pyramid: u32,
+    pub secondary_depth_pyramid: u32,
+    pub projection_type: u32,
+    pub p00_or_width_recip_x2: f32,
+    pub p11_or_height_recip_x2: f32,
+    pub z_near: f32,
+    pub z_far: f32,
+    pub lod_base: f32,
+    pub lod_step: f32,
+    pub min_mesh_lod: u32,
+    pub lod_target_pos_view_space: [f32; 3],
+    pub max_mesh_lod: u32,
+}
+const _: () = assert!(std::mem::size_of::<OrbitCullInfo>() == 400);
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct OrbitSceneBuffers {
+    pub entity_draws: *const c_void,
+    pub mesh_infos: *const c_void,
+    pub entities: *const c_void,
+    pub meshlets: *const c_void,
+    pub materials: *const c_void,
+    pub entity_visibility: *mut u32,
+    pub meshlet_visibility: *mut u32,
+    pub entity_draw_count: u32,
+    pub draw_begin: u32,
+    pub draw_end: u32,
+    pub reserved: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct OrbitHizInfo {
+    pub width: u32, pub height: u32, pub levels: u32, pub total_texels: u32,
+    pub level_offset: [u32; ORBIT_HIZ_MAX_LEVELS],
+    pub texels: *mut f32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct OrbitClusterCullInfo {
+    pub world_to_view_matrix: [f32; 16],
+    pub screen_to_view_matrix: [f32; 16],
+    pub cluster_count: [u32; 3],
+    pub tile_size_px: u32,
+    pub screen_size: [u32; 2],
+    pub z_near: f32,
+    pub z_far: f32,
+    pub unique_cluster_buffer: u32, pub cluster_offset_image: u32, pub light_index_buffer: u32, pub depth_bounds_buffer: u32,
+    pub global_light_count: u32, pub global_light_list: u32, pub _padding: [u32; 2],
+}
+const _: () = assert!(std::mem::size_of::<OrbitClusterCullInfo>() == 192);
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct OrbitClusterParams { pub info: OrbitClusterCullInfo, pub z_scale: f32, pub z_bias: f32, pub reserved: [u32; 2] }
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct OrbitStatus { pub dispatch_overflow: u32, pub draw_overflow: u32, pub light_index_overflow: u32, pub reserved: u32 }
+
+extern "C" {
+    pub fn orbit_abi_version() -> i32;
+    pub fn orbit_error_string(code: i32) -> *const std::os::raw::c_char;
+    pub fn orbit_last_cuda_error() -> i32;
+    pub fn orbit_ctx_create(device: i32, out: *mut *mut orbit_ctx) -> i32;
+    pub fn orbit_ctx_destroy(ctx: *mut orbit_ctx);
+    pub fn orbit_ctx_poll_status(ctx: *mut orbit_ctx, out: *mut OrbitStatus) -> i32;
+    pub fn orbit_ctx_launch_count(ctx: *const orbit_ctx) -> u64;
+    pub fn orbit_hiz_geometry(depth_width: u32, depth_height: u32, out: *mut OrbitHizInfo) -> i32;
+    pub fn orbit_hiz_create(ctx: *mut orbit_ctx, depth_width: u32, depth_height: u32, out: *mut *mut orbit_hiz) -> i32;
+    pub fn orbit_hiz_wrap(ctx: *mut orbit_ctx, depth_width: u32, depth_height: u32, texels: *mut f32, out: *mut *mut orbit_hiz) -> i32;
+    pub fn orbit_hiz_destroy(hiz: *mut orbit_hiz);
+    pub fn orbit_hiz_info(hiz: *const orbit_hiz, out: *mut OrbitHizInfo) -> i32;
+    pub fn orbit_hiz_build(ctx: *mut orbit_ctx, hiz: *mut orbit_hiz, depth: *const f32, depth_width: u32, depth_height: u32, stream: *mut c_void) -> i32;
+    pub fn orbit_entity_cull(ctx: *mut orbit_ctx, cull: *const OrbitCullInfo, scene: *const OrbitSceneBuffers, hiz: *const orbit_hiz,
+                             meshlet_dispatch_buffer: *mut c_void, capacity_records: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_meshlet_cull(ctx: *mut orbit_ctx, cull: *const OrbitCullInfo, scene: *const OrbitSceneBuffers, hiz: *const orbit_hiz,
+                              meshlet_dispatch_buffer: *const c_void, capacity_records: u64, draw_command_buffer: *mut c_void,
+                              capacity_draws: u64, task_payloads: *mut c_void, stream: *mut c_void) -> i32;
+    pub fn orbit_light_cluster(ctx: *mut orbit_ctx, params: *const OrbitClusterParams, depth: *const f32, lights: *const c_void,
+                               tile_masks: *mut c_void, depth_bounds: *mut c_void, unique_clusters: *mut c_void,
+                               offset_count_image: *mut c_void, light_index_list: *mut c_void, capacity_indices: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_draws_scatter(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, dst_draw_buffer: *mut c_void, dst_first: u32,
+                               total_count: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
+}
+
+/// Safe-ish wrappers shaped like the reference entry points (draw_gen.rs:327-389, 456-566).
+pub struct Context(*mut orbit_ctx);
+unsafe impl Send for Context {}
+
+#[derive(Debug)]
+pub struct Error(pub i32);
+fn check(rc: i32) -> Result<(), Error> { if rc == ORBIT_OK { Ok(()) } else { Err(Error(rc)) } }
+
+impl Context {
+    pub fn new(device: i32) -> Result<Self, Error> {
+        let mut p = std::ptr::null_mut();
+        check(unsafe { orbit_ctx_create(device, &mut p) })?;
+        Ok(Self(p))
+    }
+    /// create_meshlet_dispatch_command (draw_gen.rs:327-380): `cull` is `CullInfo::to_gpu()` reinterpreted.
+    pub unsafe fn create_meshlet_dispatch_command(&self, cull: &OrbitCullInfo, scene: &OrbitSceneBuffers, hiz: *const orbit_hiz,
+                                                  meshlet_dispatch_buffer: *mut c_void, capacity_records: u64, stream: *mut c_void) -> Result<(), Error> {
+        check(orbit_entity_cull(self.0, cull, scene, hiz, meshlet_dispatch_buffer, capacity_records, stream))
+    }
+    /// create_meshlet_draw_commands (draw_gen.rs:382-435).
+    pub unsafe fn create_meshlet_draw_commands(&self, cull: &OrbitCullInfo, scene: &OrbitSceneBuffers, hiz: *const orbit_hiz,
+                                               meshlet_dispatch_buffer: *const c_void, capacity_records: u64,
+                                               draw_command_buffer: *mut c_void, capacity_draws: u64, stream: *mut c_void) -> Result<(), Error> {
+        check(orbit_meshlet_cull(self.0, cull, scene, hiz, meshlet_dispatch_buffer, capacity_records, draw_command_buffer,
+                                 capacity_draws, std::ptr::null_mut(), stream))
+    }
+}
+impl Drop for Context { fn drop(&mut self) { unsafe { orbit_ctx_destroy(self.0) } } }
+
+/// DepthPyramid (draw_gen.rs:451-567) over orbit_hiz.
+pub struct DepthPyramid { hiz: *mut orbit_hiz, size: [u32; 2], pub usable: bool }
+impl DepthPyramid {
+    pub fn new(ctx: &Context, [width, height]: [u32; 2]) -> Result<Self, Error> {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { orbit_hiz_create(ctx.0, width, height, &mut h) })?;
+        Ok(Self { hiz: h, size: [width, height], usable: false })
+    }
+    pub unsafe fn update(&mut self, ctx: &Context, depth_buffer: *const f32, stream: *mut c_void) -> Result<(), Error> {
+        check(orbit_hiz_build(ctx.0, self.hiz, depth_buffer, self.size[0], self.size[1], stream))?;
+        self.usable = true;
+        Ok(())
+    }
+    pub fn get_current(&self) -> *const orbit_hiz { self.hiz }
+}
+impl Drop for DepthPyramid { fn drop(&mut self) { unsafe { orbit_hiz_destroy(self.hiz) } } }

@@ -1,0 +1,115 @@
+"""CPU: the C-ABI library loads, exports every symbol include/orbit_cuda.h declares, refuses to run without a
+GPU (no CPU fallback), and the Python / C views of every layout agree byte for byte."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from orbit_b200 import _lib
+from orbit_b200 import layouts as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "orbit_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(orbit_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.PROTOTYPES), (declared ^ set(_lib.PROTOTYPES))
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.orbit_abi_version() == 1
+    assert lib.orbit_error_string(0) == b"ok"
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    assert _lib.lib().orbit_ctx_create(0, C.byref(h)) == _lib.ERR_NO_DEVICE
+    from orbit_b200.passes import Context
+    with pytest.raises(RuntimeError):
+        Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "orbit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle_ref" not in text and "liborbit_oracle" not in text and "oracle/" not in text, f
+
+
+def test_layouts_match_c_header(tmp_path):
+    src = tmp_path / "layout_probe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "orbit_cuda.h"
+#define P(T) printf(#T " %zu\n", sizeof(T))
+#define O(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+  P(OrbitCullInfo); P(OrbitEntityData); P(OrbitEntityDraw); P(OrbitMeshInfo); P(OrbitMeshlet); P(OrbitMeshletDispatch);
+  P(OrbitMeshletDrawCommand); P(OrbitMeshTaskPayload); P(OrbitLightData); P(OrbitClusterCullInfo); P(OrbitClusterParams);
+  P(OrbitSceneBuffers); P(OrbitHizInfo); P(OrbitStatus);
+  O(OrbitCullInfo, cull_planes); O(OrbitCullInfo, occlusion_pass); O(OrbitCullInfo, p00_or_width_recip_x2); O(OrbitCullInfo, lod_base);
+  O(OrbitCullInfo, lod_target_pos_view_space); O(OrbitCullInfo, max_mesh_lod);
+  O(OrbitClusterCullInfo, tile_size_px); O(OrbitClusterCullInfo, z_near); O(OrbitClusterCullInfo, global_light_count);
+  O(OrbitClusterParams, z_scale); O(OrbitSceneBuffers, entity_draw_count); O(OrbitHizInfo, level_offset); O(OrbitHizInfo, texels);
+  O(OrbitMeshlet, cone_axis); O(OrbitMeshlet, material_index); O(OrbitMeshInfo, mesh_lods); O(OrbitLightData, outer_radius);
+  return 0; }''')
+    exe = tmp_path / "probe"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.rsplit(" ", 1) for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    got = {k: int(v) for k, v in got.items()}
+    py_sizes = {"OrbitCullInfo": C.sizeof(L.CullInfo), "OrbitEntityData": L.entity_dtype.itemsize, "OrbitEntityDraw": L.entity_draw_dtype.itemsize,
+                "OrbitMeshInfo": L.mesh_info_dtype.itemsize, "OrbitMeshlet": L.meshlet_dtype.itemsize, "OrbitMeshletDispatch": L.dispatch_dtype.itemsize,
+                "OrbitMeshletDrawCommand": L.draw_command_dtype.itemsize, "OrbitMeshTaskPayload": 40, "OrbitLightData": L.light_dtype.itemsize,
+                "OrbitClusterCullInfo": C.sizeof(L.ClusterCullInfo), "OrbitClusterParams": C.sizeof(L.ClusterParams),
+                "OrbitSceneBuffers": C.sizeof(L.SceneBuffers), "OrbitHizInfo": C.sizeof(L.HizInfo), "OrbitStatus": C.sizeof(L.Status)}
+    for k, v in py_sizes.items():
+        assert got[k] == v, (k, got[k], v)
+    offs = {"OrbitCullInfo.cull_planes": L.CullInfo.cull_planes.offset, "OrbitCullInfo.occlusion_pass": L.CullInfo.occlusion_pass.offset,
+            "OrbitCullInfo.p00_or_width_recip_x2": L.CullInfo.p00_or_width_recip_x2.offset, "OrbitCullInfo.lod_base": L.CullInfo.lod_base.offset,
+            "OrbitCullInfo.lod_target_pos_view_space": L.CullInfo.lod_target_pos_view_space.offset, "OrbitCullInfo.max_mesh_lod": L.CullInfo.max_mesh_lod.offset,
+            "OrbitClusterCullInfo.tile_size_px": L.ClusterCullInfo.tile_size_px.offset, "OrbitClusterCullInfo.z_near": L.ClusterCullInfo.z_near.offset,
+            "OrbitClusterCullInfo.global_light_count": L.ClusterCullInfo.global_light_count.offset, "OrbitClusterParams.z_scale": L.ClusterParams.z_scale.offset,
+            "OrbitSceneBuffers.entity_draw_count": L.SceneBuffers.entity_draw_count.offset, "OrbitHizInfo.level_offset": L.HizInfo.level_offset.offset,
+            "OrbitHizInfo.texels": L.HizInfo.texels.offset,
+            "OrbitMeshlet.cone_axis": L.meshlet_dtype.fields["cone_axis"][1], "OrbitMeshlet.material_index": L.meshlet_dtype.fields["material_index"][1],
+            "OrbitMeshInfo.mesh_lods": L.mesh_info_dtype.fields["mesh_lods"][1], "OrbitLightData.outer_radius": L.light_dtype.fields["outer_radius"][1]}
+    for k, v in offs.items():
+        assert got[k] == v, (k, got[k], v)
+    # reference numbers
+    assert got["OrbitCullInfo"] == 400 and got["OrbitClusterCullInfo"] == 192 and got["OrbitMeshlet"] == 32 and got["OrbitMeshletDrawCommand"] == 28
+
+
+def test_hiz_geometry_matches_reference_sizing():
+    """DepthPyramid::new (draw_gen.rs:456-459) + mip_levels_from_size (math.rs:18-20): 1080p -> 1024^2, 11 mips,
+    1 398 101 texels; 4K -> 2048^2, 12 mips."""
+    from orbit_b200 import scenes
+    for (w, h), (pw, ph, lv, tot) in {(1920, 1080): (1024, 1024, 11, 1398101), (3840, 2160): (2048, 2048, 12, 5592405),
+                                      (1280, 720): (1024, 512, 11, None), (100, 60): (64, 32, 7, None), (2, 2): (1, 1, 1, 1)}.items():
+        info = L.HizInfo()
+        assert _lib.lib().orbit_hiz_geometry(w, h, C.byref(info)) == 0
+        assert (info.width, info.height, info.levels) == (pw, ph, lv)
+        if tot:
+            assert info.total_texels == tot
+        pw2, ph2, lv2, offs, tot2 = scenes.hiz_geometry(w, h)
+        assert (pw2, ph2, lv2, tot2) == (pw, ph, lv, info.total_texels)
+        assert list(info.level_offset[:lv]) == offs
+    assert _lib.lib().orbit_hiz_geometry(0, 5, C.byref(L.HizInfo())) == _lib.ERR_INVALID_ARGUMENT
+
+
+def test_argument_errors_without_gpu():
+    lib = _lib.lib()
+    assert lib.orbit_entity_cull(None, None, None, None, None, 0, None) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.orbit_meshlet_cull(None, None, None, None, None, 0, None, 0, None, None) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.orbit_hiz_build(None, None, None, 1, 1, None) == _lib.ERR_INVALID_ARGUMENT

@@ -1,0 +1,62 @@
+"""CPU: the header-only C++ host mirror (include/orbit_passes.hpp) compiles with g++ and packs GpuCullInfo
+byte-for-byte like the Python packer (both restate CullInfo::to_gpu, draw_gen.rs:121-203)."""
+import os
+import subprocess
+
+import numpy as np
+
+from orbit_b200 import scenes
+from orbit_b200.passes import CullInfo, OcclusionCullInfo, Projection
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SRC = r'''
+#include <cstdio>
+#include "orbit_passes.hpp"
+int main() {
+    using namespace orbit_host;
+    CullInfo c;
+    float vm[16]; for (int i = 0; i < 16; ++i) vm[i] = 0.25f * (float)(i + 1);
+    std::memcpy(c.view_matrix, vm, 64);
+    for (int i = 0; i < 5 * 4; ++i) c.view_space_cull_planes.push_back(0.125f * (float)i - 1.0f);
+    c.projection = Projection::perspective(1.5707963705062866f, 0.01f);
+    c.occlusion_culling.kind = OcclusionCullInfo::VisibilityWrite;
+    c.occlusion_culling.visibility_buffer = (uint32_t*)0x10; c.occlusion_culling.meshlet_visibility_buffer = (uint32_t*)0x10;
+    c.occlusion_culling.depth_pyramid = (orbit_hiz*)0x10; c.occlusion_culling.aspect_ratio = 1920.0f / 1080.0f;
+    c.lod_range_start = 1; c.lod_range_end = 6; c.lod_base = 8.0f; c.lod_step = 1.5f;
+    c.lod_target_pos_view_space[0] = 1; c.lod_target_pos_view_space[1] = 2; c.lod_target_pos_view_space[2] = 3;
+    OrbitCullInfo g = c.to_gpu();
+    fwrite(&g, sizeof(g), 1, stdout);
+    CullInfo o = c; o.projection = Projection::orthographic(50.0f, -10.0f, 300.0f); o.occlusion_culling.aspect_ratio = 2.0f;
+    g = o.to_gpu(); fwrite(&g, sizeof(g), 1, stdout);
+    ClusterSettings s; s.screen_resolution[0] = 1920; s.screen_resolution[1] = 1080; float zs, zb; s.cluster_grid_info(0.01f, zs, zb);
+    fwrite(&zs, 4, 1, stdout); fwrite(&zb, 4, 1, stdout);
+    return 0;
+}
+'''
+
+
+def test_cpp_host_mirror_packs_like_python(tmp_path):
+    src = tmp_path / "host.cpp"; src.write_text(SRC)
+    exe = tmp_path / "host"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", os.path.join(ROOT, "orbit_b200", "lib"), "-lorbit_b200", "-Wl,-rpath," + os.path.join(ROOT, "orbit_b200", "lib")])
+    raw = subprocess.check_output([str(exe)])
+    assert len(raw) == 808
+    vm = (0.25 * (np.arange(16, dtype=np.float32) + 1)).reshape(4, 4).T          # memory is column-major
+    planes = (0.125 * np.arange(20, dtype=np.float32) - 1.0).reshape(5, 4)
+    m = object()
+    py = CullInfo(vm, planes, Projection.perspective(float(np.float32(1.5707963705062866)), 0.01),
+                  OcclusionCullInfo("write", m, m, m, 0, aspect_ratio=float(np.float32(1920.0) / np.float32(1080.0))),
+                  lod_range=(1, 6), lod_base=8.0, lod_step=1.5, lod_target_pos_view_space=(1, 2, 3)).to_gpu()
+    a, b = np.frombuffer(raw[:400], np.uint8), np.frombuffer(bytes(py), np.uint8)
+    diff = np.nonzero(a != b)[0]
+    # tan() of the two libms may differ in the last ulp of p00/p11 (offsets 356..363); everything else is identical
+    assert set(diff.tolist()) <= set(range(356, 364)), diff
+    assert np.allclose(a[356:364].view(np.float32), b[356:364].view(np.float32), rtol=3e-7)
+    po = CullInfo(vm, planes, Projection.orthographic(50.0, -10.0, 300.0), OcclusionCullInfo("write", m, m, m, 0, aspect_ratio=2.0),
+                  lod_range=(1, 6), lod_base=8.0, lod_step=1.5, lod_target_pos_view_space=(1, 2, 3)).to_gpu()
+    assert raw[400:800] == bytes(po)
+    zs, zb = np.frombuffer(raw[800:808], np.float32)
+    pzs, pzb = scenes.cluster_grid_info(0.01, 200.0, 32)
+    assert abs(zs - pzs) < 1e-5 and abs(zb - pzb) < 1e-4
