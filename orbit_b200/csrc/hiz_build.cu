@@ -51,14 +51,47 @@ __device__ void hiz_tail(const HizBuildParams& p, uint32_t first) {
     }
 }
 
-__global__ void __launch_bounds__(256) hiz_small_kernel(const __grid_constant__ HizBuildParams p) { hiz_tail(p, 0u); }
+// Top of the pyramid by the last CTA: level `first-1` (at most 4096 texels) is pulled into shared memory with one
+// round of L2 loads, then every remaining level is reduced out of shared memory (no global round trip per level).
+__device__ void hiz_tail_smem(const HizBuildParams& p, uint32_t first, float* s_a, float* s_b) {
+    uint32_t sw = max(p.width >> (first - 1u), 1u), sh = max(p.height >> (first - 1u), 1u);
+    const float* src_g = p.texels + p.level_offset[first - 1u];
+    for (uint32_t i = threadIdx.x; i < sw * sh; i += blockDim.x) s_a[i] = ld_cg(src_g + i);
+    __syncthreads();
+    float* src = s_a;
+    float* dst = s_b;
+    for (uint32_t l = first; l < p.levels; ++l) {
+        const uint32_t w = max(p.width >> l, 1u), h = max(p.height >> l, 1u);
+        float* out = p.texels + p.level_offset[l];
+        for (uint32_t i = threadIdx.x; i < w * h; i += blockDim.x) {
+            const uint32_t x = i % w, y = i / w;
+            const uint32_t x0 = min(2u * x, sw - 1u), x1 = min(2u * x + 1u, sw - 1u);
+            const uint32_t y0 = min(2u * y, sh - 1u), y1 = min(2u * y + 1u, sh - 1u);
+            const float v = fminf(fminf(src[y0 * sw + x0], src[y0 * sw + x1]), fminf(src[y1 * sw + x0], src[y1 * sw + x1]));
+            dst[i] = v;
+            out[i] = v;
+        }
+        __syncthreads();
+        float* t = src; src = dst; dst = t;
+        sw = w; sh = h;
+    }
+}
+
+__global__ void __launch_bounds__(256) hiz_small_kernel(const __grid_constant__ HizBuildParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    hiz_tail(p, 0u);
+}
 
 __global__ void __launch_bounds__(256) hiz_build_kernel(const __grid_constant__ HizBuildParams p) {
     __shared__ float s_l3[8][8];
     __shared__ bool s_last;
+    __shared__ float s_top_a[4096], s_top_b[1024];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tiles_x = p.width >> 6;
     const uint32_t tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    pdl_launch_dependents();
+    pdl_wait();
 
     // ---- level 0: lane owns columns 2*lane, 2*lane+1 of rows warp*8 .. warp*8+7 of the tile
     const uint32_t x_a = tx * 64u + 2u * lane;
@@ -143,15 +176,16 @@ __global__ void __launch_bounds__(256) hiz_build_kernel(const __grid_constant__ 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    hiz_tail(p, 7u);
+    if ((p.width >> 6) * (p.height >> 6) <= 4096u) hiz_tail_smem(p, 7u, s_top_a, s_top_b);
+    else hiz_tail(p, 7u);
 }
 
 cudaError_t launch_hiz_build(const HizBuildParams& p, cudaStream_t stream) {
     if (p.width >= 64u && p.height >= 64u && p.levels >= 7u) {
         const uint32_t grid = (p.width >> 6) * (p.height >> 6);
-        hiz_build_kernel<<<grid, 256, 0, stream>>>(p);
+        return launch_kernel(hiz_build_kernel, dim3(grid), dim3(256), 0, stream, p);
     } else {
-        hiz_small_kernel<<<1, 256, 0, stream>>>(p);
+        return launch_kernel(hiz_small_kernel, dim3(1), dim3(256), 0, stream, p);
     }
     return cudaGetLastError();
 }

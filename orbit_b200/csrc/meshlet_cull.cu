@@ -7,24 +7,26 @@
 // B200 design (not the reference's one-workgroup-per-record + atomicAdd). Measured on C2 the stage is bound by
 // instruction issue before HBM (IEEE-exact division / square root of the projection math), so the design
 // minimises executed warp-instructions and never blocks a CTA:
-//   * one co-resident grid; the record count is read on the device (the reference's dispatch_indirect, no host
-//     round trip) and split STATICALLY into one contiguous range per CTA and per warp, so ordered compaction
-//     needs no serial prefix chain: phase 1 tests every lane and counts, each CTA publishes ONE aggregate, sums
-//     the aggregates of all lower CTAs itself (a flat gather, not a hop-by-hop look-back — measured: look-back
-//     over thousands of small tiles propagates only 32 tiles per L2 round trip and dominated the runtime), and
-//     phase 2 emits the commands of its range at the now-known offset;
+//   * TWO launches. `meshlet_test_kernel` is embarrassingly parallel: persistent warps take tiles of R records
+//     CYCLICALLY (tile = global warp id + k * total warps), test every lane and leave one draw mask per record in
+//     an L2-resident scratch array — no inter-CTA ordering at all, so hot regions of the scene are spread over
+//     all SMs (a contiguous static split measured 2-3x slower: the CTAs owning the visible part of the city made
+//     everyone wait). `meshlet_emit_kernel` then orders and writes the survivors: contiguous record ranges per
+//     CTA, popcount sums, ONE published aggregate per CTA, a flat gather of all lower aggregates (no hop-by-hop
+//     look-back: that propagates only 32 tiles per L2 round trip and dominated v1/v2), and the commands are
+//     rebuilt from 16 B of each surviving meshlet (L2 hits). The record count is read on the device (the
+//     reference's dispatch_indirect) — no host round trip;
 //   * lane = meshlet of a record, exactly the reference's 32-lane group, so ballots are the reference's
-//     visibility words; all meshlet loads of a tile are issued up front as 2 x 128-bit non-coherent loads per
-//     lane (1 KB contiguous per record, R KB in flight per warp);
+//     visibility words; the meshlets of a tile (R records x 1 KB contiguous) are staged into shared memory by
+//     TMA bulk copies (cp.async.bulk + mbarrier, one copy per record issued by R lanes), so R KB per warp are in
+//     flight without holding registers, and the next tile's copy is issued as soon as the current one is consumed;
 //   * view*model is computed once per record by 16 lanes (two records per step) and broadcast through shared
 //     memory — the reference recomputes the 4x4 product in every lane;
 //   * pass 1: only lanes whose visibility bit is set can be visible, so they are PACKED across the tile's
 //     records before any meshlet is loaded or tested (the early pass touches only last frame's survivors);
 //   * pass 2: lanes surviving frustum + cone are PACKED into a per-warp queue and the expensive Hi-Z projection
 //     runs on full warps of survivors instead of once per record at ~17% lane occupancy;
-//   * survivors are ranked by ballot + popc; phase 1 leaves one draw mask per record in an L2-resident scratch
-//     array, phase 2 re-reads the 16 B it needs of each surviving meshlet (L2 hits) and stores the command:
-//     draw order = (record index, lane), independent of scheduling.
+//   * survivors are ranked by ballot + popc; draw order = (record index, lane), independent of scheduling.
 #include "params.cuh"
 
 namespace orbit {
@@ -33,12 +35,42 @@ constexpr int kMcWarps = 8;
 constexpr int kMcThreads = kMcWarps * 32;
 constexpr int kMvStride = 20;   // 16 matrix entries + scale, padded
 
+// ---- TMA bulk copy + mbarrier plumbing (PTX; SASS: UBLKCP / SYNCS) --------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 struct ItemTest {
     Sphere s;
     bool pre_visible;   // passed frustum + cone
 };
 
 // frustum + cone for one meshlet against the model-view matrix `mv` (17 floats in shared memory)
+// kProj: 0 perspective, 1 orthographic, -1 decided at run time from ci.projection_type
+template <int kProj>
 __device__ __forceinline__ ItemTest test_item(const OrbitCullInfo& ci, const float* __restrict__ mv, const uint4 ma, const uint32_t cone) {
     ItemTest out;
     const float4 c0 = *reinterpret_cast<const float4*>(mv + 0);
@@ -76,11 +108,12 @@ __device__ __forceinline__ ItemTest test_item(const OrbitCullInfo& ci, const flo
         const float axx = add(add(add(mul(c0.x, kx), mul(c1.x, ky)), mul(c2.x, kz)), mul(c3.x, 0.0f));
         const float axy = add(add(add(mul(c0.y, kx), mul(c1.y, ky)), mul(c2.y, kz)), mul(c3.y, 0.0f));
         const float axz = add(add(add(mul(c0.z, kx), mul(c1.z, ky)), mul(c2.z, kz)), mul(c3.z, 0.0f));
-        if (ci.projection_type == 0u) {
+        const uint32_t proj = kProj >= 0 ? (uint32_t)kProj : ci.projection_type;
+        if (proj == 0u) {
             const float lhs = dot3(px, py, pz, axx, axy, axz);
             const float len = fsqrt(dot3(px, py, pz, px, py, pz));
             visible = !(lhs >= fma_(cutoff, len, s.r));
-        } else if (ci.projection_type == 1u) {
+        } else if (proj == 1u) {
             const float camx = sub(px, 0.0f), camy = sub(py, 0.0f), camz = sub(pz, -1.0f);
             const float qx = sub(px, camx), qy = sub(py, camy), qz = sub(pz, camz);
             const float lhs = dot3(qx, qy, qz, axx, axy, axz);
@@ -115,299 +148,491 @@ __device__ __forceinline__ void store_command(uint32_t* __restrict__ dst, uint32
 }
 
 template <int R>
-__global__ void __launch_bounds__(kMcThreads) meshlet_cull_kernel(const __grid_constant__ MeshletCullParams p) {
+struct __align__(128) WarpSmem {
+    uint4 meshlets[R * 64];        // R records x 32 meshlets x 2 x 16 B, filled by TMA (packed mode: item list aliases this)
+    float mv[R][kMvStride];        // view*model + scale per record
+    float q[6][64];                // ring buffer of Hi-Z candidates: x, y, z, r, r_model, scale
+    uint32_t qid[64];              //   (record << 5) | lane
+    uint32_t mask[R];              // per-record visible / draw masks under construction
+    unsigned long long bar;        // mbarrier of the TMA copies
+};
+
+// Survivor counts are accumulated per CHUNK of consecutive records by the test kernel (integer atomics: the sums are
+// order-independent) so that the emit kernel can order its output with a shared-memory scan instead of an
+// inter-CTA exchange. Chunk size: a multiple of 32 records such that there are at most kMaxChunks chunks.
+constexpr uint32_t kMaxChunks = 2048u;
+__device__ __forceinline__ uint32_t chunk_records(uint32_t nrec) {
+    const uint32_t per = (nrec + kMaxChunks - 1u) / kMaxChunks;
+    return max(32u, (per + 31u) & ~31u);
+}
+
+// view * model (+ largest column scale) for every record of a tile: 16 lanes per record, two records per step
+template <int R>
+__device__ __forceinline__ void tile_model_view(const MeshletCullParams& p, float* mv_base, uint32_t my_word, uint32_t lane,
+                                                float v0, float v1, float v2, float v3) {
+#pragma unroll
+    for (int st = 0; st < R / 2; ++st) {
+        const uint32_t half = lane >> 4, e = lane & 15u;
+        const uint32_t ent = __shfl_sync(0xFFFFFFFFu, my_word, (2 * st + half) * 4 + 0);
+        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, my_word, (2 * st + half) * 4 + 2);
+        if (cnt != 0u) {
+            const float4 b = __ldg(p.entities + (size_t)ent * 8u + (e >> 2));
+            mv_base[(2 * st + half) * kMvStride + e] = add(add(add(mul(v0, b.x), mul(v1, b.y)), mul(v2, b.z)), mul(v3, b.w));
+        }
+    }
+    __syncwarp();
+    if (lane < (uint32_t)R) mv_base[lane * kMvStride + 16] = largest_scale(mv_base + lane * kMvStride);
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Direct mode: pass 0, pass 2, and pass 1 without a meshlet visibility buffer — every lane of every record is
+// tested. kPass2 = (occlusion_pass == 2 && meshlet occlusion culling on); kProj as in test_item.
+template <int R, bool kPass2, int kProj>
+__global__ void __launch_bounds__(kMcThreads, 3) meshlet_test_direct_kernel(const __grid_constant__ MeshletCullParams p) {
     static_assert(R == 2 || R == 4 || R == 8, "records per warp tile");
-    __shared__ __align__(16) float s_mv[kMcWarps][R][kMvStride];
-    __shared__ uint32_t s_items[kMcWarps][R * 32];
-    __shared__ float s_q[kMcWarps][6][64];
-    __shared__ uint32_t s_qid[kMcWarps][64];
-    __shared__ uint32_t s_mask[kMcWarps][R];
-    __shared__ uint32_t s_warp_total[kMcWarps];
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    WarpSmem<R>* const all = reinterpret_cast<WarpSmem<R>*>(s_raw);
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
+    WarpSmem<R>& ws = all[warp];
     const OrbitCullInfo& ci = p.cull;
-    const unsigned int epoch = scan_epoch(p.scan);
+    pdl_launch_dependents();
+    pdl_wait();
     uint32_t nrec = __ldcg(p.dispatch_words);  // workgroup_count_x written by the entity stage
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
-    const uint32_t pass = ci.occlusion_pass;
-    const bool mocc = ci.meshlet_visibility_buffer != ORBIT_NO_BUFFER;
-    const bool use_vis = (pass == 1u || pass == 2u) && mocc;
-    const bool pass2 = (pass == 2u) && mocc;
-    const bool packed_mode = (pass == 1u) && use_vis;
-    // static contiguous partition: CTA range, then warp range (multiples of R so tiles never straddle warps)
+    const uint32_t chunk_rec = chunk_records(nrec);
+    uint32_t* const chunk_counts = p.chunk_counts + (__ldcg(p.chunk_parity) & 1u) * kMaxChunks;
+    // cyclic tile assignment over all warps of the grid: balances hot and cold regions of the record list
     const uint32_t tiles_total = (nrec + R - 1) / R;
-    const uint32_t cta_t0 = (uint32_t)(((uint64_t)tiles_total * blockIdx.x) / gridDim.x);
-    const uint32_t cta_t1 = (uint32_t)(((uint64_t)tiles_total * (blockIdx.x + 1u)) / gridDim.x);
-    const uint32_t w_t0 = cta_t0 + (uint32_t)(((uint64_t)(cta_t1 - cta_t0) * warp) / kMcWarps);
-    const uint32_t w_t1 = cta_t0 + (uint32_t)(((uint64_t)(cta_t1 - cta_t0) * (warp + 1u)) / kMcWarps);
+    const uint32_t w_stride = gridDim.x * kMcWarps;
+    const uint32_t w_t0 = blockIdx.x * kMcWarps + warp;
+    const uint32_t w_t1 = tiles_total;
     // row `lane&3` of the view matrix, for the 16-lane view*model product
     const uint32_t vrow_i = lane & 3u;
     const float v0 = ci.view_matrix.m[0][vrow_i], v1 = ci.view_matrix.m[1][vrow_i];
     const float v2 = ci.view_matrix.m[2][vrow_i], v3 = ci.view_matrix.m[3][vrow_i];
-    float* const mv_base = &s_mv[warp][0][0];
+    float* const mv_base = &ws.mv[0][0];
+    const uint32_t bar = smem_addr(&ws.bar);
+    const uint32_t buf = smem_addr(&ws.meshlets[0]);
+    if (lane == 0u) { mbar_init(bar, R); mbar_fence_init(); }
+    __syncwarp();
+    uint32_t parity = 0u;
 
-    // =========================================== phase 1: test + count ===========================================
-    uint32_t warp_count = 0u;
-    uint32_t next_word = 0u;
-    if (w_t0 < w_t1 && lane < 4u * R && w_t0 * R + (lane >> 2) < nrec) next_word = __ldcg(p.dispatch_words + 3u + (size_t)w_t0 * R * 4u + lane);
-    for (uint32_t tile = w_t0; tile < w_t1; ++tile) {
+    // record words of a tile: lane l < 4R holds word l (entity, meshlet_offset, meshlet_count, visibility_offset per record)
+    auto load_words = [&](uint32_t tile) -> uint32_t {
+        uint32_t w = 0u;
+        if (tile < w_t1 && lane < 4u * R && tile * R + (lane >> 2) < nrec) w = __ldcg(p.dispatch_words + 3u + (size_t)tile * R * 4u + lane);
+        return w;
+    };
+    // lane r < R issues the bulk copy of record r (count x 32 B) and arrives on the barrier
+    auto issue_tma = [&](uint32_t words) {
+        const uint32_t off = __shfl_sync(0xFFFFFFFFu, words, (lane * 4u + 1u) & 31u);
+        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, words, (lane * 4u + 2u) & 31u);
+        if (lane < (uint32_t)R) {
+            if (cnt != 0u) {
+                const uint32_t bytes = min(cnt, 32u) * 32u;
+                mbar_arrive_expect_tx(bar, bytes);
+                tma_load_1d(buf + lane * 1024u, p.meshlets + 2u * (size_t)off, bytes, bar);
+            } else {
+                mbar_arrive(bar);
+            }
+        }
+    };
+
+    uint32_t warp_total = 0u;   // survivors found by this warp (lets the emit kernel skip everything when zero)
+    uint32_t cur_word = load_words(w_t0);
+    uint32_t next_word = load_words(w_t0 + w_stride);
+    if (w_t0 < w_t1) issue_tma(cur_word);
+    uint32_t qhead = 0u;   // ring-buffer read position (entries [qhead, qhead+qn) mod 64 are pending)
+    for (uint32_t tile = w_t0; tile < w_t1; tile += w_stride) {
         const uint32_t rec0 = tile * R;
-        const uint32_t my_word = next_word;
-        // prefetch the next tile's records
-        next_word = 0u;
-        if (tile + 1u < w_t1 && lane < 4u * R && rec0 + R + (lane >> 2) < nrec) next_word = __ldcg(p.dispatch_words + 3u + (size_t)(rec0 + R) * 4u + lane);
-        uint32_t r_offset[R], r_count[R], r_vo[R], r_entity[R];
+        const uint32_t my_word = cur_word;
+        cur_word = next_word;
+        next_word = load_words(tile + 2u * w_stride);
+        // ---- lane r keeps count / visibility offset / visibility word of record r
+        const uint32_t my_cnt = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 2u) & 31u);
+        const uint32_t my_vo = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 3u) & 31u);
+        uint32_t vw = 0xFFFFFFFFu;   // pass 2: last frame's visibility (decides should_draw); otherwise unused
+        if (kPass2 && lane < (uint32_t)R && my_cnt != 0u) vw = __ldcg(p.meshlet_visibility + my_vo);
+        tile_model_view<R>(p, mv_base, my_word, lane, v0, v1, v2, v3);
+
+        uint32_t vis_mask[R], packed[R];
+        uint32_t qn = 0u;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            r_entity[r] = __shfl_sync(0xFFFFFFFFu, my_word, r * 4 + 0);
-            r_offset[r] = __shfl_sync(0xFFFFFFFFu, my_word, r * 4 + 1);
-            r_count[r] = __shfl_sync(0xFFFFFFFFu, my_word, r * 4 + 2);   // 0 for records past the end
-            r_vo[r] = __shfl_sync(0xFFFFFFFFu, my_word, r * 4 + 3);
-        }
-        // ---- visibility words: lane r loads the word of record r
-        uint32_t vw = 0xFFFFFFFFu;
-        {
-            const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 2u) & 31u);
-            const uint32_t vo = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 3u) & 31u);
-            if (use_vis && lane < (uint32_t)R && cnt != 0u) vw = __ldcg(p.meshlet_visibility + vo);
-        }
-        // ---- direct mode: all meshlet loads up front
-        uint4 ma[R];
-        uint32_t cone[R], packed[R];
-        if (!packed_mode) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                ma[r] = make_uint4(0, 0, 0, 0); cone[r] = 0u; packed[r] = 0u;
-                if (lane < r_count[r]) {
-                    const uint4* m = p.meshlets + 2u * ((size_t)r_offset[r] + lane);
-                    ma[r] = __ldg(m);
-                    const uint4 b = __ldg(m + 1);
-                    cone[r] = b.x; packed[r] = b.w;
-                }
+            const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, my_word, r * 4 + 2);   // 0 for records past the end
+            vis_mask[r] = 0u; packed[r] = 0u;
+            if (cnt == 0u) continue;   // warp-uniform
+            bool pre = false;
+            ItemTest t;
+            if (lane < cnt) {
+                const uint4 a = ws.meshlets[r * 64 + lane * 2];
+                const uint4 b = ws.meshlets[r * 64 + lane * 2 + 1];
+                packed[r] = b.w;
+                t = test_item<kProj>(ci, mv_base + r * kMvStride, a, b.x);
+                pre = t.pre_visible;
             }
-        }
-        // ---- view * model for every record of the tile: 16 lanes per record, two records per step
-        __syncwarp();
-#pragma unroll
-        for (int st = 0; st < R / 2; ++st) {
-            const uint32_t half = lane >> 4, e = lane & 15u;
-            const uint32_t ent = half ? r_entity[2 * st + 1] : r_entity[2 * st];
-            const uint32_t cnt = half ? r_count[2 * st + 1] : r_count[2 * st];
-            if (cnt != 0u) {
-                const float4 b = __ldg(p.entities + (size_t)ent * 8u + (e >> 2));
-                mv_base[(2 * st + half) * kMvStride + e] = add(add(add(mul(v0, b.x), mul(v1, b.y)), mul(v2, b.z)), mul(v3, b.w));
-            }
-        }
-        __syncwarp();
-        if (lane < (uint32_t)R) mv_base[lane * kMvStride + 16] = largest_scale(mv_base + lane * kMvStride);
-        uint32_t vis_word[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) vis_word[r] = __shfl_sync(0xFFFFFFFFu, vw, r);
-        __syncwarp();
-
-        uint32_t my_draw_mask = 0u;   // lane r keeps the draw mask of record r
-
-        if (!packed_mode) {
-            // ------------------------------- direct mode (pass 0 / pass 2) -------------------------------
-            uint32_t vis_mask[R];
-            uint32_t qn = 0u;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                vis_mask[r] = 0u;
-                if (r_count[r] == 0u) continue;   // warp-uniform
-                bool pre = false;
-                ItemTest t;
-                if (lane < r_count[r]) {
-                    t = test_item(ci, mv_base + r * kMvStride, ma[r], cone[r]);
-                    pre = t.pre_visible;
+            const uint32_t pre_mask = __ballot_sync(0xFFFFFFFFu, pre);
+            vis_mask[r] = pre_mask;
+            if (kPass2) {
+                // queue the survivors for the Hi-Z test; run it whenever a full warp of them is waiting
+                if (lane == 0u) ws.mask[r] = pre_mask;
+                if (pre) {
+                    const uint32_t slot = (qhead + qn + __popc(pre_mask & lt)) & 63u;
+                    ws.q[0][slot] = t.s.x; ws.q[1][slot] = t.s.y; ws.q[2][slot] = t.s.z;
+                    ws.q[3][slot] = t.s.r; ws.q[4][slot] = t.s.r_model; ws.q[5][slot] = t.s.s;
+                    ws.qid[slot] = ((uint32_t)r << 5) | lane;
                 }
-                const uint32_t pre_mask = __ballot_sync(0xFFFFFFFFu, pre);
-                vis_mask[r] = pre_mask;
-                if (pass2) {
-                    // queue the survivors for the Hi-Z test; run it whenever a full warp of them is waiting
-                    if (lane == 0u) s_mask[warp][r] = pre_mask;
-                    if (pre) {
-                        const uint32_t slot = qn + __popc(pre_mask & lt);
-                        s_q[warp][0][slot] = t.s.x; s_q[warp][1][slot] = t.s.y; s_q[warp][2][slot] = t.s.z;
-                        s_q[warp][3][slot] = t.s.r; s_q[warp][4][slot] = t.s.r_model; s_q[warp][5][slot] = t.s.s;
-                        s_qid[warp][slot] = ((uint32_t)r << 5) | lane;
-                    }
-                    qn += __popc(pre_mask);
-                    __syncwarp();
-                    if (qn >= 32u) {
-                        Sphere s;
-                        s.x = s_q[warp][0][lane]; s.y = s_q[warp][1][lane]; s.z = s_q[warp][2][lane];
-                        s.r = s_q[warp][3][lane]; s.r_model = s_q[warp][4][lane]; s.s = s_q[warp][5][lane];
-                        const uint32_t id = s_qid[warp][lane];
-                        if (!occlusion_test(ci, s, p.hiz)) atomicAnd(&s_mask[warp][id >> 5], ~(1u << (id & 31u)));
-                        const uint32_t rem = qn - 32u;
-                        float tx = 0, ty = 0, tz = 0, tr = 0, tm = 0, ts = 0; uint32_t tid2 = 0;
-                        if (lane < rem) {
-                            tx = s_q[warp][0][32 + lane]; ty = s_q[warp][1][32 + lane]; tz = s_q[warp][2][32 + lane];
-                            tr = s_q[warp][3][32 + lane]; tm = s_q[warp][4][32 + lane]; ts = s_q[warp][5][32 + lane];
-                            tid2 = s_qid[warp][32 + lane];
-                        }
-                        __syncwarp();
-                        if (lane < rem) {
-                            s_q[warp][0][lane] = tx; s_q[warp][1][lane] = ty; s_q[warp][2][lane] = tz;
-                            s_q[warp][3][lane] = tr; s_q[warp][4][lane] = tm; s_q[warp][5][lane] = ts;
-                            s_qid[warp][lane] = tid2;
-                        }
-                        qn = rem;
-                        __syncwarp();
-                    }
-                }
-            }
-            if (pass2) {
-                if (lane < qn) {
-                    Sphere s;
-                    s.x = s_q[warp][0][lane]; s.y = s_q[warp][1][lane]; s.z = s_q[warp][2][lane];
-                    s.r = s_q[warp][3][lane]; s.r_model = s_q[warp][4][lane]; s.s = s_q[warp][5][lane];
-                    const uint32_t id = s_qid[warp][lane];
-                    if (!occlusion_test(ci, s, p.hiz)) atomicAnd(&s_mask[warp][id >> 5], ~(1u << (id & 31u)));
-                }
+                qn += __popc(pre_mask);
                 __syncwarp();
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (r_count[r] == 0u) continue;
-                    vis_mask[r] = s_mask[warp][r];
-                    if (lane == 0u) p.meshlet_visibility[r_vo[r]] = vis_mask[r];   // ballot(visible), meshlet_cull.comp:235-242
+                if (qn >= 32u) {
+                    const uint32_t slot = (qhead + lane) & 63u;
+                    Sphere s;
+                    s.x = ws.q[0][slot]; s.y = ws.q[1][slot]; s.z = ws.q[2][slot];
+                    s.r = ws.q[3][slot]; s.r_model = ws.q[4][slot]; s.s = ws.q[5][slot];
+                    const uint32_t id = ws.qid[slot];
+                    if (!occlusion_test<kProj>(ci, s, p.hiz)) atomicAnd(&ws.mask[id >> 5], ~(1u << (id & 31u)));
+                    qhead = (qhead + 32u) & 63u;
+                    qn -= 32u;
+                    __syncwarp();
                 }
             }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const bool visible = ((vis_mask[r] >> lane) & 1u) != 0u;
-                const bool vib = ((vis_word[r] >> lane) & 1u) != 0u;   // all ones when visibility is not in use
-                const bool sd = draw_rule(ci, p, visible, vib, pass2, packed[r]);
-                const uint32_t dm = __ballot_sync(0xFFFFFFFFu, sd);
-                if (lane == (uint32_t)r) my_draw_mask = dm;
-                warp_count += __popc(dm);
+        }
+        // every lane has read its meshlets: the staging buffer is free -> start the next tile's copy now
+        __syncwarp();
+        if (tile + w_stride < w_t1) issue_tma(cur_word);
+        if (kPass2) {
+            if (lane < qn) {
+                const uint32_t slot = (qhead + lane) & 63u;
+                Sphere s;
+                s.x = ws.q[0][slot]; s.y = ws.q[1][slot]; s.z = ws.q[2][slot];
+                s.r = ws.q[3][slot]; s.r_model = ws.q[4][slot]; s.s = ws.q[5][slot];
+                const uint32_t id = ws.qid[slot];
+                if (!occlusion_test<kProj>(ci, s, p.hiz)) atomicAnd(&ws.mask[id >> 5], ~(1u << (id & 31u)));
             }
-        } else {
-            // ------------------------------- packed mode (pass 1) -------------------------------
-            // Only lanes whose visibility bit is set can be visible (visible = visible_in_buffer,
-            // meshlet_cull.comp:137): pack them across the tile's records, then load + test only those.
-            uint32_t n_items = 0u;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t act = r_count[r] >= 32u ? 0xFFFFFFFFu : ((1u << r_count[r]) - 1u);
-                const uint32_t m = vis_word[r] & act;
-                if ((m >> lane) & 1u) s_items[warp][n_items + __popc(m & lt)] = ((uint32_t)r << 5) | lane;
-                n_items += __popc(m);
-            }
-            if (lane < (uint32_t)R) s_mask[warp][lane] = 0u;
+            qhead = (qhead + qn) & 63u;
             __syncwarp();
-            for (uint32_t k = 0; k * 32u < n_items; ++k) {
-                const uint32_t i = k * 32u + lane;
-                const uint32_t id = i < n_items ? s_items[warp][i] : 0u;
-                const uint32_t moff = __shfl_sync(0xFFFFFFFFu, my_word, (id >> 5) * 4u + 1u);
-                if (i < n_items) {
-                    const uint32_t r = id >> 5, j = id & 31u;
-                    const uint4* m = p.meshlets + 2u * ((size_t)moff + j);
-                    const uint4 a = __ldg(m), b = __ldg(m + 1);
-                    const ItemTest t = test_item(ci, mv_base + r * kMvStride, a, b.x);
-                    if (draw_rule(ci, p, t.pre_visible, true, false, b.w)) atomicOr(&s_mask[warp][r], 1u << j);
-                }
-            }
-            __syncwarp();
-            if (lane < (uint32_t)R) my_draw_mask = s_mask[warp][lane];
-            warp_count += __reduce_add_sync(0xFFFFFFFFu, __popc(my_draw_mask));
+            if (lane < (uint32_t)R && my_cnt != 0u) p.meshlet_visibility[my_vo] = ws.mask[lane];   // ballot(visible), meshlet_cull.comp:235-242
+#pragma unroll
+            for (int r = 0; r < R; ++r) vis_mask[r] = ws.mask[r] & vis_mask[r];
             __syncwarp();
         }
-        // one draw mask per record, kept L2-resident for phase 2
-        if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = my_draw_mask;
-    }
-
-    // =========================================== order the ranges ===========================================
-    if (lane == 0u) s_warp_total[warp] = warp_count;
-    __syncthreads();
-    if (warp == 0u) {
-        const uint32_t v = lane < (uint32_t)kMcWarps ? s_warp_total[lane] : 0u;
-        uint32_t incl = v;
+        uint32_t my_draw_mask = 0u;   // lane r keeps the draw mask of record r
 #pragma unroll
-        for (int d = 1; d < kMcWarps; d <<= 1) {
+        for (int r = 0; r < R; ++r) {
+            const uint32_t vword = __shfl_sync(0xFFFFFFFFu, vw, r);   // all ones when visibility is not in use
+            const bool visible = ((vis_mask[r] >> lane) & 1u) != 0u;
+            const bool vib = ((vword >> lane) & 1u) != 0u;
+            const bool sd = draw_rule(ci, p, visible, vib, kPass2, packed[r]);
+            const uint32_t dm = __ballot_sync(0xFFFFFFFFu, sd);
+            if (lane == (uint32_t)r) my_draw_mask = dm;
+        }
+        // one draw mask per record, kept L2-resident for the emit kernel; survivors counted per chunk
+        if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = my_draw_mask;
+        const uint32_t tile_total = __reduce_add_sync(0xFFFFFFFFu, __popc(my_draw_mask));
+        if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + rec0 / chunk_rec, tile_total);
+        warp_total += tile_total;
+    }
+    if (lane == 0u && warp_total != 0u) atomicAdd(p.draw_total, warp_total);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed mode: pass 1 with a meshlet visibility buffer. Only lanes whose visibility bit is set can be visible
+// (visible = visible_in_buffer, meshlet_cull.comp:137), so they are packed across the tile's records and only
+// those meshlets are loaded and tested. Latency-bound (little work per tile): small shared-memory footprint so
+// that many warps are resident, and the visibility words and model matrices are fetched in parallel.
+template <int R>
+struct __align__(16) PackedSmem {
+    float mv[R][kMvStride];
+    uint32_t items[R * 32];
+    uint32_t mask[R];
+};
+
+template <int R>
+__global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(const __grid_constant__ MeshletCullParams p) {
+    __shared__ PackedSmem<R> s_all[kMcWarps];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    PackedSmem<R>& ws = s_all[warp];
+    const OrbitCullInfo& ci = p.cull;
+    pdl_launch_dependents();
+    pdl_wait();
+    uint32_t nrec = __ldcg(p.dispatch_words);
+    if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
+    const uint32_t chunk_rec = chunk_records(nrec);
+    uint32_t* const chunk_counts = p.chunk_counts + (__ldcg(p.chunk_parity) & 1u) * kMaxChunks;
+    const uint32_t tiles_total = (nrec + R - 1) / R;
+    const uint32_t w_stride = gridDim.x * kMcWarps;
+    const uint32_t vrow_i = lane & 3u;
+    const float v0 = ci.view_matrix.m[0][vrow_i], v1 = ci.view_matrix.m[1][vrow_i];
+    const float v2 = ci.view_matrix.m[2][vrow_i], v3 = ci.view_matrix.m[3][vrow_i];
+    float* const mv_base = &ws.mv[0][0];
+    uint32_t warp_total = 0u;
+    for (uint32_t tile = blockIdx.x * kMcWarps + warp; tile < tiles_total; tile += w_stride) {
+        const uint32_t rec0 = tile * R;
+        uint32_t my_word = 0u;
+        if (lane < 4u * R && rec0 + (lane >> 2) < nrec) my_word = __ldcg(p.dispatch_words + 3u + (size_t)rec0 * 4u + lane);
+        const uint32_t my_cnt = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 2u) & 31u);
+        const uint32_t my_vo = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 3u) & 31u);
+        uint32_t vw = 0u;
+        if (lane < (uint32_t)R && my_cnt != 0u) vw = __ldcg(p.meshlet_visibility + my_vo) & (my_cnt >= 32u ? 0xFFFFFFFFu : ((1u << my_cnt) - 1u));
+        tile_model_view<R>(p, mv_base, my_word, lane, v0, v1, v2, v3);   // issued before vw is consumed: the loads overlap
+        uint32_t n_items = 0u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t m = __shfl_sync(0xFFFFFFFFu, vw, r);
+            if ((m >> lane) & 1u) ws.items[n_items + __popc(m & lt)] = ((uint32_t)r << 5) | lane;
+            n_items += __popc(m);
+        }
+        if (lane < (uint32_t)R) ws.mask[lane] = 0u;
+        __syncwarp();
+        for (uint32_t k = 0; k * 32u < n_items; ++k) {
+            const uint32_t i = k * 32u + lane;
+            const uint32_t id = i < n_items ? ws.items[i] : 0u;
+            const uint32_t moff = __shfl_sync(0xFFFFFFFFu, my_word, (id >> 5) * 4u + 1u);
+            if (i < n_items) {
+                const uint32_t r = id >> 5, j = id & 31u;
+                const uint4* m = p.meshlets + 2u * ((size_t)moff + j);
+                const uint4 a = __ldg(m), b = __ldg(m + 1);
+                const ItemTest t = test_item<-1>(ci, mv_base + r * kMvStride, a, b.x);
+                if (draw_rule(ci, p, t.pre_visible, true, false, b.w)) atomicOr(&ws.mask[r], 1u << j);
+            }
+        }
+        __syncwarp();
+        uint32_t my_draw_mask = 0u;
+        if (lane < (uint32_t)R) my_draw_mask = ws.mask[lane];
+        __syncwarp();
+        if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = my_draw_mask;
+        const uint32_t tile_total = __reduce_add_sync(0xFFFFFFFFu, __popc(my_draw_mask));
+        if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + rec0 / chunk_rec, tile_total);
+        warp_total += tile_total;
+    }
+    if (lane == 0u && warp_total != 0u) atomicAdd(p.draw_total, warp_total);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Second launch: ordered, OUTPUT-BALANCED emission with no inter-CTA exchange.
+//   1. every CTA loads the (at most 2048) per-chunk survivor counts the test kernel accumulated and scans them in
+//      shared memory: chunk prefix P. (Earlier versions published per-CTA aggregates and gathered them — three
+//      more dependent global round trips in a kernel whose whole runtime is a handful of round trips.)
+//   2. the T outputs are split evenly over all warps of the grid; a warp binary-searches P for the chunk holding
+//      its first output, walks that chunk's draw masks 32 records at a time, and writes its outputs. Survivors
+//      cluster in the visible part of the scene, so splitting by RECORDS leaves a few CTAs with 10-16x the average
+//      work; splitting by OUTPUTS gives every warp the same number.
+//   3. the counts of the OTHER parity are zeroed for the next call; the last CTA flips the parity.
+constexpr int kEmitWarps = 8;
+__global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __grid_constant__ MeshletCullParams p) {
+    __shared__ uint32_t s_prefix[kMaxChunks];            // inclusive survivor count up to chunk c
+    __shared__ uint32_t s_warp_total[kEmitWarps];
+    __shared__ uint32_t s_rec[kEmitWarps][4][32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool want_payload = p.task_payloads != nullptr;
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t parity = __ldcg(p.chunk_parity) & 1u;
+    const uint32_t grand_total = __ldcg(p.draw_total);
+    uint32_t nrec = __ldcg(p.dispatch_words);
+    if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
+    const uint32_t* const counts = p.chunk_counts + parity * kMaxChunks;
+    // zero the other parity's counters for the next call (it runs after this kernel in stream order)
+    for (uint32_t i = blockIdx.x * blockDim.x + tid; i < kMaxChunks; i += gridDim.x * blockDim.x) p.chunk_counts[(parity ^ 1u) * kMaxChunks + i] = 0u;
+    const uint32_t gw = blockIdx.x * kEmitWarps + warp, GW = gridDim.x * kEmitWarps;
+    if (grand_total != 0u) {
+        const uint32_t chunk_rec = chunk_records(nrec);
+        const uint32_t nchunks = (nrec + chunk_rec - 1u) / chunk_rec;
+        // ---- 1. chunk counts -> inclusive prefix in shared memory (8 consecutive chunks per thread)
+        uint32_t v[8], local = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t i = tid * 8u + (uint32_t)k;
+            v[k] = i < nchunks ? __ldcg(counts + i) : 0u;
+            local += v[k];
+        }
+        uint32_t incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= (uint32_t)d) incl += t;
         }
-        const uint32_t cta_total = __shfl_sync(0xFFFFFFFFu, incl, kMcWarps - 1);
-        if (lane == 0u) publish(p.scan.status + blockIdx.x, pack_status(epoch, kFlagAggregate, cta_total));
-        // flat gather of every lower CTA's aggregate (all CTAs are co-resident and finish phase 1 together)
-        uint32_t sum = 0u;
-        for (uint32_t i = lane; i < blockIdx.x; i += 32u) {
-            while (true) {
-                const unsigned long long w = peek(p.scan.status + i);
-                if ((unsigned int)(w >> 34) == epoch) { sum += (unsigned int)w; break; }
-                __nanosleep(64);
-            }
-        }
-        const uint32_t base = __reduce_add_sync(0xFFFFFFFFu, sum);
-        if (lane < (uint32_t)kMcWarps) s_warp_total[lane] = base + incl - v;   // global exclusive offset of each warp
-        if (blockIdx.x == gridDim.x - 1u && lane == 0u) {
-            p.draw_words[0] = base + cta_total;   // exact count even when it exceeds capacity
-            if ((uint64_t)base + cta_total > p.capacity_draws) *p.overflow_flag = 1u;
-        }
-    }
-    __syncthreads();
-
-    // =========================================== phase 2: emit ===========================================
-    uint32_t off = s_warp_total[warp];
-    const bool want_payload = p.task_payloads != nullptr;
-    if (warp_count != 0u || want_payload) {
-        for (uint32_t tile = w_t0; tile < w_t1; ++tile) {
-            const uint32_t rec0 = tile * R;
-            uint32_t my_word = 0u;
-            if (lane < 4u * R && rec0 + (lane >> 2) < nrec) my_word = __ldcg(p.dispatch_words + 3u + (size_t)rec0 * 4u + lane);
-            uint32_t dmask = 0u;
-            if (lane < (uint32_t)R && rec0 + lane < nrec) dmask = __ldcg(p.draw_masks + rec0 + lane);
+        if (lane == 31u) s_warp_total[warp] = incl;
+        __syncthreads();
+        uint32_t run = incl - local;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t dm = __shfl_sync(0xFFFFFFFFu, dmask, r);
-                const uint32_t entity = __shfl_sync(0xFFFFFFFFu, my_word, r * 4 + 0);
-                const uint32_t moff = __shfl_sync(0xFFFFFFFFu, my_word, r * 4 + 1);
-                if ((dm >> lane) & 1u) {
-                    const uint4 b = __ldg(p.meshlets + 2u * ((size_t)moff + lane) + 1);
-                    const uint64_t idx = (uint64_t)off + __popc(dm & lt);
-                    if (idx < p.capacity_draws) store_command(p.draw_words + 1u + idx * 7u, b.y, b.z, b.w, entity, moff + lane);
+        for (int w = 0; w < kEmitWarps; ++w) if ((uint32_t)w < warp) run += s_warp_total[w];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { run += v[k]; s_prefix[tid * 8u + (uint32_t)k] = run; }
+        __syncthreads();
+        const uint32_t total = s_prefix[kMaxChunks - 1u];
+        if (blockIdx.x == 0 && tid == 0) {
+            p.draw_words[0] = total;   // exact count even when it exceeds capacity
+            if ((uint64_t)total > p.capacity_draws) *p.overflow_flag = 1u;
+        }
+        // ---- 2. my share of the outputs
+        const uint32_t o_begin = (uint32_t)(((uint64_t)total * gw) / GW);
+        const uint32_t o_end = (uint32_t)(((uint64_t)total * (gw + 1u)) / GW);
+        uint32_t* const sr = &s_rec[warp][0][0];
+        if (o_begin < o_end) {
+            // chunk holding output o_begin: first c with P[c] > o_begin
+            uint32_t lo = 0u, hi = nchunks - 1u;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_prefix[mid] > o_begin) hi = mid; else lo = mid + 1u;
+            }
+            uint32_t running = lo ? s_prefix[lo - 1u] : 0u;               // outputs before record `rec`
+            uint32_t rec = lo * chunk_rec;
+            while (running < o_end && rec < nrec) {
+                const uint32_t my = rec + lane;
+                uint32_t dm = 0u, entity = 0u, moff = 0u;
+                if (my < nrec) dm = __ldcg(p.draw_masks + my);
+                const uint32_t pc = __popc(dm);
+                uint32_t inc = pc;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= (uint32_t)d) inc += t;
                 }
-                off += __popc(dm);
-                if (want_payload && rec0 + r < nrec) {
-                    // MeshTaskPayload + emitted task count, indices ascending by lane (the task shader's atomicAdd
-                    // order is arbitrary): lane q packs index bytes 4q..4q+3
-                    uint32_t* tp = p.task_payloads + (size_t)(rec0 + r) * 11u;
-                    if (lane < 8u) {
-                        uint32_t packed_idx = 0u, m = dm;
-                        for (uint32_t k = 0; k < 4u * lane && m; ++k) m &= m - 1u;
-                        for (uint32_t k = 0; k < 4u && m; ++k) { packed_idx |= (uint32_t)(__ffs((int)m) - 1) << (8u * k); m &= m - 1u; }
-                        tp[3u + lane] = packed_idx;
+                const uint32_t step_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                if (running + step_total > o_begin) {
+                    if (dm != 0u) {
+                        entity = __ldcg(p.dispatch_words + 3u + (size_t)my * 4u + 0u);
+                        moff = __ldcg(p.dispatch_words + 3u + (size_t)my * 4u + 1u);
                     }
-                    if (lane == 8u) tp[0] = __popc(dm);
-                    if (lane == 9u) tp[1] = entity;
-                    if (lane == 10u) tp[2] = moff;
+                    __syncwarp();
+                    sr[lane] = inc; sr[32 + lane] = dm; sr[64 + lane] = entity; sr[96 + lane] = moff;
+                    __syncwarp();
+                    const uint32_t l0 = o_begin > running ? o_begin - running : 0u;            // first local output of mine
+                    const uint32_t l1 = min(step_total, o_end - running);                      // one past my last local output
+                    for (uint32_t ol = l0 + lane; ol < l1; ol += 32u) {
+                        uint32_t a = 0u, b = 31u;
+#pragma unroll
+                        for (int it = 0; it < 5; ++it) {
+                            const uint32_t mid = (a + b) >> 1;
+                            if (sr[mid] > ol) b = mid; else a = mid + 1u;
+                        }
+                        const uint32_t r = a;
+                        const uint32_t excl = r ? sr[r - 1u] : 0u;
+                        uint32_t m = sr[32 + r];
+                        for (uint32_t k = ol - excl; k != 0u; --k) m &= m - 1u;   // (ol-excl)-th survivor of the record
+                        const uint32_t j = (uint32_t)__ffs((int)m) - 1u;
+                        const uint32_t midx = sr[96 + r] + j;
+                        const uint4 mb = __ldg(p.meshlets + 2u * (size_t)midx + 1);
+                        const uint64_t idx = (uint64_t)running + ol;
+                        if (idx < p.capacity_draws) store_command(p.draw_words + 1u + idx * 7u, mb.y, mb.z, mb.w, sr[64 + r], midx);
+                    }
                 }
+                running += step_total;
+                rec += 32u;
             }
         }
+    } else if (blockIdx.x == 0 && tid == 0) {
+        p.draw_words[0] = 0u;   // nothing survived (the steady-state late pass)
     }
+    if (want_payload) {
+        // MeshTaskPayload + emitted task count per record (record-parallel; indices ascending by lane — the task
+        // shader's atomicAdd order is arbitrary): one warp per record, lane q packs index bytes 4q..4q+3
+        for (uint32_t r = gw; r < nrec; r += GW) {
+            const uint32_t rdm = __ldcg(p.draw_masks + r);
+            uint32_t* tp = p.task_payloads + (size_t)r * 11u;
+            if (lane < 8u) {
+                uint32_t packed_idx = 0u, m = rdm;
+                for (uint32_t k = 0; k < 4u * lane && m; ++k) m &= m - 1u;
+                for (uint32_t k = 0; k < 4u && m; ++k) { packed_idx |= (uint32_t)(__ffs((int)m) - 1) << (8u * k); m &= m - 1u; }
+                tp[3u + lane] = packed_idx;
+            }
+            if (lane == 8u) tp[0] = __popc(rdm);
+            if (lane == 9u) tp[1] = __ldcg(p.dispatch_words + 3u + (size_t)r * 4u + 0u);
+            if (lane == 10u) tp[2] = __ldcg(p.dispatch_words + 3u + (size_t)r * 4u + 1u);
+        }
+    }
+    // ---- 3. last CTA out: re-arm the survivor total and flip the parity
     __syncthreads();
-    if (threadIdx.x == 0) scan_cta_exit(p.scan, epoch);
-}
-
-cudaError_t launch_meshlet_cull(const MeshletCullParams& p, int recs_per_warp, int grid, cudaStream_t stream) {
-    switch (recs_per_warp) {
-        case 2: meshlet_cull_kernel<2><<<grid, kMcThreads, 0, stream>>>(p); break;
-        case 8: meshlet_cull_kernel<8><<<grid, kMcThreads, 0, stream>>>(p); break;
-        default: meshlet_cull_kernel<4><<<grid, kMcThreads, 0, stream>>>(p); break;
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(p.emit_done, 1u);
+        if (prev + 1u == gridDim.x) { *p.emit_done = 0u; *p.draw_total = 0u; *p.chunk_parity = parity ^ 1u; }
     }
-    return cudaGetLastError();
 }
 
-int meshlet_cull_max_ctas_per_sm(int recs_per_warp) {
+// ---- launch plumbing ---------------------------------------------------------------------------------------
+struct TestVariant { bool packed; bool pass2; int proj; };
+static TestVariant variant_of(const OrbitCullInfo& ci) {
+    const bool mocc = ci.meshlet_visibility_buffer != ORBIT_NO_BUFFER;
+    TestVariant v;
+    v.packed = ci.occlusion_pass == 1u && mocc;
+    v.pass2 = ci.occlusion_pass == 2u && mocc;
+    v.proj = ci.projection_type <= 1u ? (int)ci.projection_type : -1;
+    return v;
+}
+
+template <int R, bool kPass2, int kProj>
+static cudaError_t launch_direct(const MeshletCullParams& p, int grid, cudaStream_t stream, int* occupancy) {
+    const size_t smem = sizeof(WarpSmem<R>) * kMcWarps;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(meshlet_test_direct_kernel<R, kPass2, kProj>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (occupancy) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_direct_kernel<R, kPass2, kProj>, kMcThreads, smem);
+        return cudaSuccess;
+    }
+    return launch_kernel(meshlet_test_direct_kernel<R, kPass2, kProj>, dim3(grid), dim3(kMcThreads), smem, stream, p);
+}
+
+template <int R>
+static cudaError_t launch_test(const MeshletCullParams& p, int grid, cudaStream_t stream, int* occupancy) {
+    const TestVariant v = variant_of(p.cull);
+    if (v.packed) {
+        if (occupancy) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_packed_kernel<R>, kMcThreads, 0); return cudaSuccess; }
+        return launch_kernel(meshlet_test_packed_kernel<R>, dim3(grid), dim3(kMcThreads), 0, stream, p);
+    }
+    if (v.pass2) {
+        if (v.proj == 0) return launch_direct<R, true, 0>(p, grid, stream, occupancy);
+        if (v.proj == 1) return launch_direct<R, true, 1>(p, grid, stream, occupancy);
+        return launch_direct<R, true, -1>(p, grid, stream, occupancy);
+    }
+    if (v.proj == 0) return launch_direct<R, false, 0>(p, grid, stream, occupancy);
+    if (v.proj == 1) return launch_direct<R, false, 1>(p, grid, stream, occupancy);
+    return launch_direct<R, false, -1>(p, grid, stream, occupancy);
+}
+
+static cudaError_t launch_test_r(const MeshletCullParams& p, int recs_per_warp, int grid, cudaStream_t stream, int* occupancy) {
+    switch (recs_per_warp) {
+        case 2: return launch_test<2>(p, grid, stream, occupancy);
+        case 8: return launch_test<8>(p, grid, stream, occupancy);
+        default: return launch_test<4>(p, grid, stream, occupancy);
+    }
+}
+
+// Index of the kernel variant a CullInfo selects (api.cu caches one occupancy per variant).
+int meshlet_cull_variant_index(const OrbitCullInfo& ci) {
+    const TestVariant v = variant_of(ci);
+    return v.packed ? 0 : 1 + (v.pass2 ? 3 : 0) + (v.proj + 1);
+}
+
+int meshlet_cull_max_ctas_per_sm(const MeshletCullParams& p, int recs_per_warp) {
     int n = 0;
-    switch (recs_per_warp) {
-        case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, meshlet_cull_kernel<2>, kMcThreads, 0); break;
-        case 8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, meshlet_cull_kernel<8>, kMcThreads, 0); break;
-        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, meshlet_cull_kernel<4>, kMcThreads, 0); break;
+    launch_test_r(p, recs_per_warp, 0, nullptr, &n);
+    return n;
+}
+
+cudaError_t launch_meshlet_cull(const MeshletCullParams& p, int recs_per_warp, int grid, int emit_grid, cudaStream_t stream) {
+    if (grid > 0) {
+        cudaError_t e = launch_test_r(p, recs_per_warp, grid, stream, nullptr);
+        if (e != cudaSuccess) return e;
     }
+    if (emit_grid > 0) return launch_kernel(meshlet_emit_kernel, dim3(emit_grid), dim3(kEmitWarps * 32), 0, stream, p);
+    return cudaSuccess;
+}
+
+int meshlet_emit_max_ctas_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, meshlet_emit_kernel, kEmitWarps * 32, 0);
     return n;
 }
 

@@ -127,9 +127,12 @@ ORBIT_DEV float hiz_sample(const HizDevice& hz, uint32_t lvl, float u, float v) 
 
 // Occlusion block shared by the entity and meshlet stages. In the perspective case s.z is negated in place
 // (the entity stage's LOD distance later reads the negated value, as in the reference).
+// kProj: 0 perspective, 1 orthographic, -1 decided at run time from ci.projection_type.
+template <int kProj = -1>
 ORBIT_DEV bool occlusion_test(const OrbitCullInfo& ci, Sphere& s, const HizDevice& hz) {
     float ax, ay, az, aw, depth;
-    if (ci.projection_type == 0u) {
+    const uint32_t proj = kProj >= 0 ? (uint32_t)kProj : ci.projection_type;
+    if (proj == 0u) {
         float zp = -s.z;
         s.z = zp;
         bool cullable = zp >= fma_(s.r_model, s.s, ci.z_near);
@@ -150,7 +153,7 @@ ORBIT_DEV bool occlusion_test(const OrbitCullInfo& ci, Sphere& s, const HizDevic
         ax = fma_(a0, 0.5f, 0.5f); ay = fma_(a3, -0.5f, 0.5f);
         az = fma_(a2, 0.5f, 0.5f); aw = fma_(a1, -0.5f, 0.5f);
         depth = fdiv(ci.z_near, fma_(-s.r_model, s.s, zp));
-    } else if (ci.projection_type == 1u) {
+    } else if (proj == 1u) {
         float sr = ci.p00_or_width_recip_x2;
         float ctrx = mul(s.x, sr), ctry = mul(s.y, sr);
         float box = mul(sr, s.r);

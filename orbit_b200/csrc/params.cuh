@@ -6,6 +6,20 @@
 
 namespace orbit {
 
+// Launch helper; adds programmatic stream serialization (PDL) when ORBIT_PDL is set (off by default, see api.cu).
+bool pdl_enabled();
+template <typename P>
+inline cudaError_t launch_kernel(void (*kernel)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const P& params) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 struct MeshletCullParams {
     OrbitCullInfo cull;
     HizDevice hiz;
@@ -17,7 +31,11 @@ struct MeshletCullParams {
     uint32_t* draw_words;             // MeshletDrawCommandBuffer as u32[]: count then 7 words per command
     uint32_t* task_payloads;          // nullable, 11 words per record
     uint32_t* overflow_flag;          // host-mapped status word
-    uint32_t* draw_masks;             // scratch: one draw mask per dispatch record (phase 1 -> phase 2)
+    uint32_t* draw_masks;             // scratch: one draw mask per dispatch record (test kernel -> emit kernel)
+    uint32_t* draw_total;             // scratch: survivors counted by the test kernel (re-zeroed by the emit kernel)
+    uint32_t* chunk_counts;           // scratch: 2 x 2048 per-chunk survivor counts (double-buffered by parity)
+    uint32_t* chunk_parity;           // scratch: which half the current call uses (flipped by the emit kernel)
+    uint32_t* emit_done;              // scratch: CTAs of the emit kernel that have finished
     uint64_t capacity_records;
     uint64_t capacity_draws;
     ScanState scan;
@@ -62,10 +80,13 @@ struct ClusterParams {
     ScanState scan;
 };
 
-cudaError_t launch_meshlet_cull(const MeshletCullParams&, int recs_per_warp, int grid, cudaStream_t);
-int meshlet_cull_max_ctas_per_sm(int recs_per_warp);
+cudaError_t launch_meshlet_cull(const MeshletCullParams&, int recs_per_warp, int grid, int emit_grid, cudaStream_t);
+int meshlet_emit_max_ctas_per_sm();
+int meshlet_cull_max_ctas_per_sm(const MeshletCullParams&, int recs_per_warp);
+int meshlet_cull_variant_index(const OrbitCullInfo&);
 int meshlet_cull_tile_records(int recs_per_warp);
-cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, cudaStream_t);
+cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t);
+int entity_cull_max_ctas_per_sm();
 cudaError_t launch_hiz_build(const HizBuildParams&, cudaStream_t);
 cudaError_t launch_mark_active(const ClusterParams&, int grid, cudaStream_t);
 cudaError_t launch_compact_clusters(const ClusterParams&, cudaStream_t);

@@ -12,6 +12,13 @@
 
 namespace orbit {
 
+// Programmatic dependent launch (PDL): every kernel of the pipeline lets its successor be scheduled early
+// (`launch_dependents` at entry) and waits for its predecessor's results right before its first global access
+// (`wait`), so the ~2 us launch ramp of each of the 7 small dependent kernels of a frame overlaps the previous
+// kernel instead of adding to it. Both are no-ops when a kernel is launched without the PDL attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct ScanState {
     unsigned long long* status;  // one descriptor per tile
     unsigned int* ticket;        // next tile to hand out
@@ -75,13 +82,42 @@ __device__ __forceinline__ unsigned int lookback_exclusive(const ScanState& st, 
     return exclusive;
 }
 
+// Flat gather: sum of the aggregates published (flag kFlagAggregate, this epoch) by CTAs [0, n), computed by ONE warp.
+// All loads of a batch are issued before any is checked, so a fully published prefix costs one L2 round trip per
+// 256 CTAs instead of one per CTA; descriptors that are not ready yet are re-polled.
+__device__ __forceinline__ unsigned int gather_lower_aggregates(const ScanState& st, unsigned int epoch, unsigned int n) {
+    const unsigned int lane = threadIdx.x & 31u;
+    unsigned int sum = 0u;
+    for (unsigned int base = 0u; base < n; base += 256u) {
+        unsigned long long w[8];
+        unsigned int pending = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned int i = base + (unsigned int)k * 32u + lane;
+            w[k] = 0ull;
+            if (i < n) { w[k] = peek(st.status + i); pending |= 1u << k; }
+        }
+        while (pending) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if ((pending >> k) & 1u) {
+                    if ((unsigned int)(w[k] >> 34) == epoch) { sum += (unsigned int)w[k]; pending &= ~(1u << k); }
+                    else w[k] = peek(st.status + base + (unsigned int)k * 32u + lane);
+                }
+            }
+        }
+    }
+    return __reduce_add_sync(0xFFFFFFFFu, sum);
+}
+
 // Every CTA calls this once on exit (one thread). The last CTA re-arms the ticket for the next launch.
-__device__ __forceinline__ void scan_cta_exit(const ScanState& st, unsigned int epoch) {
+__device__ __forceinline__ void scan_cta_exit(const ScanState& st, unsigned int epoch, unsigned int* also_zero = nullptr) {
     __threadfence();
     unsigned int prev = atomicAdd(st.done, 1u);
     if (prev + 1u == gridDim.x) {
         *st.ticket = 0u;
         *st.done = 0u;
+        if (also_zero) *also_zero = 0u;
         unsigned int next = (epoch + 1u) & 0x3FFFFFFFu;
         *st.epoch = next ? next : 1u;
         __threadfence();

@@ -17,19 +17,30 @@ from orbit_b200 import frame, scenes
 from orbit_b200.passes import Context
 
 
-def time_frame(ctx, copies, reps=20):
-    names = ["entity_early", "meshlet_early", "hiz", "entity_late", "meshlet_late"]
-    acc = {n: [] for n in names}
-    for i in range(reps):
-        pf = copies[i % len(copies)]
-        s = pf._stream()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-        ev[0].record(); pf.entity(False, s); ev[1].record(); pf.meshlet(False, s); ev[2].record(); pf.hiz(s)
-        ev[3].record(); pf.entity(True, s); ev[4].record(); pf.meshlet(True, s); ev[5].record()
+def time_frame(ctx, copies, reps=7, per_graph=8):
+    """Per-stage device time: a CUDA graph of `per_graph` back-to-back launches of ONE stage rotating over the
+    scene copies (no CPU in the loop, inputs out of L2), replayed `reps` times; reports us per launch."""
+    stages = {"entity_early": lambda pf, s: pf.entity(False, s), "meshlet_early": lambda pf, s: pf.meshlet(False, s),
+              "hiz": lambda pf, s: pf.hiz(s), "entity_late": lambda pf, s: pf.entity(True, s),
+              "meshlet_late": lambda pf, s: pf.meshlet(True, s)}
+    out = {}
+    for name, fn in stages.items():
+        for pf in copies:          # consistent steady-state inputs for every stage
+            pf.launch()
         torch.cuda.synchronize()
-        for k, n in enumerate(names):
-            acc[n].append(ev[k].elapsed_time(ev[k + 1]) * 1e3)
-    return {n: (float(np.median(v[3:])), float(np.min(v[3:]))) for n, v in acc.items()}
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(per_graph):
+                pf = copies[i % len(copies)]
+                fn(pf, pf._stream())
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3 / per_graph)
+        out[name] = (float(np.median(ts[1:])), float(np.min(ts[1:])))
+    return out
 
 
 def main():
@@ -37,7 +48,7 @@ def main():
     scene, _ = scenes.config_c2()
     view = bench.c2_view(scenes, scene, 0)
     depth_np = scenes.make_depth(scene, view)
-    configs = [(None, None)] if which == "default" else list(itertools.product([2, 4, 8], [1, 2, 3]))
+    configs = [(None, None)] if which == "default" else list(itertools.product([2, 4, 8], [2, 3, 4, 6]))
     for rpw, cps in configs:
         if rpw is not None:
             os.environ["ORBIT_MC_RECS_PER_WARP"] = str(rpw)
