@@ -9,7 +9,7 @@ occlusion. One *step* = the reference's depth-prepass culling of one steady-stat
 7 kernel launches (the meshlet stage is a test kernel + an emit kernel). `value` = scene meshlet instances x views / step time with every input resident in HBM;
 the step rotates over 4 independent copies of the scene + view state (> L2) so inputs come from HBM.
 N>1 (torchrun, one rank per GPU): views are sharded over GPUs with no data-path collective (each rank culls
-its own camera of the replicated city) -> weak scaling; value = sum of meshlets over ranks / max-over-ranks time.
+its own instance of the C2 view on a replicated city) -> weak scaling; value = sum of meshlets over ranks / max-over-ranks time.
 
 `e2e` = the same metric through the public pass API with HOST buffers: per step the frame-varying inputs
 (entity transforms, entity draws, depth buffer) are copied from pinned host memory, the five stage calls run,
@@ -149,7 +149,7 @@ def run_ours(args, rank, world, local_rank):
     dev = ctx.device
 
     scene, _ = scenes.config_c2()
-    view = c2_view(scenes, scene, rank)
+    view = c2_view(scenes, scene, 0)   # every rank culls its own instance of the named C2 view (equal work per GPU: weak scaling)
     depth_np = scenes.make_depth(scene, view)
 
     # ---- N_COPIES independent copies of every input + view state (rotation keeps inputs out of L2)
@@ -289,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": "C2 city 10k entities / 2M meshlets, 1 view 1920x1080 per GPU, steady-state frame: early cull + Hi-Z + late cull",
                        "l2": "rotating %d independent copies of scene + view state (~%d MB each) so inputs come from HBM" % (
                            N_COPIES, sum(scene.bytes_summary().values()) // 2 ** 20),
-                       "launch": "one CUDA graph replay per step (7 kernels: 2x entity_cull, 2x meshlet_test+meshlet_emit, hiz_build)", "views": "rank r culls camera r of the replicated city"},
+                       "launch": "one CUDA graph replay per step (7 kernels: 2x entity_cull, 2x meshlet_test+meshlet_emit, hiz_build)", "views": "every rank culls its own instance of the C2 view on a replicated scene; no data-path collective"},
             "roofline": {"bound": "hbm", "kernel": "meshlet_test_direct_kernel<4,pass2,persp> + meshlet_emit_kernel (late pass, occlusion_pass=2)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": late_bytes, "launch_us_median": late_us, "launch_us_min": k_times["meshlet_late"][1],

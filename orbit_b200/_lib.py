@@ -8,7 +8,7 @@ import os
 from . import layouts as L
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "liborbit_b200.so")
+LIB_PATH = os.environ.get("ORBIT_B200_LIB") or os.path.join(HERE, "lib", "liborbit_b200.so")   # override: experiments only
 
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_NO_DEVICE, ERR_CAPACITY = 0, -1, -2, -3, -4, -5
 

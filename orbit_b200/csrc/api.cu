@@ -345,7 +345,7 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
         CK(cudaMalloc(&c->light_view, cap * sizeof(float4)));
         c->light_capacity = cap;
     }
-    int rc = ensure_status(c, (size_t)(clusters + 255u) / 256u + 1u);
+    int rc = ensure_status(c, (size_t)clusters + 1u);   // light culling scans one tile per active cluster
     if (rc != ORBIT_OK) return rc;
     ClusterParams p{};
     p.info = ci; p.z_scale = params->z_scale; p.z_bias = params->z_bias;
@@ -358,7 +358,7 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
     CK(cudaMemsetAsync(tile_masks, 0, cx * cy * 4u, s));
     CK(cudaMemsetAsync(depth_bounds, 0, clusters * 8u, s));
     CK(cudaMemsetAsync(offset_count_image, 0, clusters * 8u, s));
-    const uint64_t warps = (uint64_t)((ci.screen_size[0] + 31u) / 32u) * ci.screen_size[1];
+    const uint64_t warps = (uint64_t)((ci.screen_size[0] + 31u) / 32u) * ((ci.screen_size[1] + 3u) / 4u);
     uint64_t grid = (warps + 7u) / 8u;
     const uint64_t cap_grid = (uint64_t)c->sm_count * 8u;
     if (grid > cap_grid) grid = cap_grid;
@@ -367,8 +367,9 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
     CK(launch_compact_clusters(p, s));
     CK(launch_light_view(p, s));
     p.scan = next_scan(c);
-    uint64_t lgrid = (clusters + 7u) / 8u;
-    if (lgrid > cap_grid) lgrid = cap_grid;
+    uint64_t lgrid = clusters;                       // one CTA per active cluster, persistent: at most 2 x 1024 threads per SM
+    const uint64_t lcap = (uint64_t)c->sm_count * 2u;
+    if (lgrid > lcap) lgrid = lcap;
     CK(launch_light_culling(p, (int)lgrid, s));
     c->launches += (L ? 4 : 3);
     return ORBIT_OK;

@@ -8,13 +8,15 @@
 // B200 design:
 //   * mark_active: 2-3 global atomics per PIXEL in the reference; here lanes of a warp that hit the same
 //     cluster are merged with match.any + redux (max / or) so one lane per distinct cluster issues the atomics.
-//     atomicMax / atomicOr are order-independent, so the result is deterministic.
+//     atomicMax / atomicOr are order-independent, so the result is deterministic; an L2 read first skips the
+//     atomic when the stored value already covers ours (same-address atomics serialise, reads do not).
 //   * compaction: ballot + CTA scan + decoupled look-back instead of atomicAdd: cluster ids come out ascending.
 //   * light culling: the reference recomputes view*light_position for every (cluster, light) pair and walks
-//     the light list twice; here light view-space spheres are computed once (16 B each, L2-resident), one warp
-//     owns one active cluster and tests 32 lights per step, ballot-compacting hits in ascending order into a
-//     256-entry shared-memory list (the reference's cap), and per-cluster ranges are packed in compacted-list
-//     order by a look-back scan instead of atomicAdd.
+//     the light list twice; here light view-space spheres are computed once (16 B each, L2-resident), a 1024-thread
+//     CTA owns one active cluster, each of its 32 warps tests a contiguous stripe of the lights 32 at a time and
+//     ballot-compacts hits in ascending order into shared memory; stripes are concatenated in order up to the
+//     reference's cap of 256, and per-cluster ranges are packed in compacted-list order by a look-back scan
+//     instead of atomicAdd.
 #include "params.cuh"
 
 namespace orbit {
@@ -25,39 +27,52 @@ __global__ void __launch_bounds__(256) mark_active_kernel(const __grid_constant_
     const OrbitClusterCullInfo& ci = p.info;
     const uint32_t W = ci.screen_size[0], H = ci.screen_size[1];
     const uint32_t cx = ci.cluster_count[0], cy = ci.cluster_count[1], cz = ci.cluster_count[2];
-    // a warp covers 32 consecutive pixels of one row; rows are distributed over warps
+    // a warp covers 32 consecutive pixels of kRows consecutive rows per step (kRows independent loads in flight)
+    constexpr uint32_t kRows = 4u;
     const uint32_t warps_per_row = (W + 31u) / 32u;
-    const uint64_t total_warps = (uint64_t)warps_per_row * H;
+    const uint32_t row_groups = (H + kRows - 1u) / kRows;
+    const uint64_t total_warps = (uint64_t)warps_per_row * row_groups;
     const uint32_t lane = threadIdx.x & 31u;
     for (uint64_t wi = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < total_warps;
          wi += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
-        const uint32_t y = (uint32_t)(wi / warps_per_row);
+        const uint32_t y0 = (uint32_t)(wi / warps_per_row) * kRows;
         const uint32_t x = (uint32_t)(wi % warps_per_row) * 32u + lane;
-        uint32_t cluster = 0xFFFFFFFFu, tile = 0xFFFFFFFFu, mask = 0u, bmin = 0u, bmax = 0u;
-        if (x < W) {
-            const float d = __ldg(p.depth + (size_t)y * W + x);
-            const uint32_t tx = x / ci.tile_size_px, ty = y / ci.tile_size_px;
-            const float z = fdiv(ci.z_near, d);
-            const uint32_t slice = f2u(fma_(orbit_log2f(z), p.z_scale, p.z_bias));
-            mask = shl1(slice);
-            if (mask != 0u) tile = tx + ty * cx;
-            if (slice < cz) {
-                cluster = tx + ty * cx + slice * cx * cy;
-                bmin = __float_as_uint(sub(1.0f, d));
-                bmax = __float_as_uint(d);
+        float dv[kRows];
+#pragma unroll
+        for (uint32_t k = 0; k < kRows; ++k) dv[k] = (x < W && y0 + k < H) ? __ldg(p.depth + (size_t)(y0 + k) * W + x) : 0.0f;
+#pragma unroll
+        for (uint32_t k = 0; k < kRows; ++k) {
+            const uint32_t y = y0 + k;
+            uint32_t cluster = 0xFFFFFFFFu, tile = 0xFFFFFFFFu, mask = 0u, bmin = 0u, bmax = 0u;
+            if (x < W && y < H) {
+                const float d = dv[k];
+                const uint32_t tx = x / ci.tile_size_px, ty = y / ci.tile_size_px;
+                const float z = fdiv(ci.z_near, d);
+                const uint32_t slice = f2u(fma_(orbit_log2f(z), p.z_scale, p.z_bias));
+                mask = shl1(slice);
+                if (mask != 0u) tile = tx + ty * cx;
+                if (slice < cz) {
+                    cluster = tx + ty * cx + slice * cx * cy;
+                    bmin = __float_as_uint(sub(1.0f, d));
+                    bmax = __float_as_uint(d);
+                }
             }
+            // merge lanes hitting the same cluster / tile
+            const uint32_t peers_c = __match_any_sync(0xFFFFFFFFu, cluster);
+            const uint32_t mn = __reduce_max_sync(peers_c, bmin);
+            const uint32_t mx = __reduce_max_sync(peers_c, bmax);
+            if (cluster != 0xFFFFFFFFu && lane == (uint32_t)(__ffs((int)peers_c) - 1)) {
+                // values only grow: a (possibly stale) read that is already >= ours makes the atomic a no-op, and
+                // plain L2 reads of one address are not serialised the way same-address atomics are
+                uint32_t* b = p.depth_bounds + 2u * (size_t)cluster;
+                if (__ldcg(b) < mn) atomicMax(b, mn);
+                if (__ldcg(b + 1) < mx) atomicMax(b + 1, mx);
+            }
+            const uint32_t peers_t = __match_any_sync(0xFFFFFFFFu, tile);
+            const uint32_t orm = __reduce_or_sync(peers_t, mask);
+            if (tile != 0xFFFFFFFFu && lane == (uint32_t)(__ffs((int)peers_t) - 1) && (__ldcg(p.tile_masks + tile) & orm) != orm)
+                atomicOr(p.tile_masks + tile, orm);
         }
-        // merge lanes hitting the same cluster / tile
-        const uint32_t peers_c = __match_any_sync(0xFFFFFFFFu, cluster);
-        const uint32_t mn = __reduce_max_sync(peers_c, bmin);
-        const uint32_t mx = __reduce_max_sync(peers_c, bmax);
-        if (cluster != 0xFFFFFFFFu && lane == (uint32_t)(__ffs((int)peers_c) - 1)) {
-            atomicMax(p.depth_bounds + 2u * (size_t)cluster, mn);
-            atomicMax(p.depth_bounds + 2u * (size_t)cluster + 1u, mx);
-        }
-        const uint32_t peers_t = __match_any_sync(0xFFFFFFFFu, tile);
-        const uint32_t orm = __reduce_or_sync(peers_t, mask);
-        if (tile != 0xFFFFFFFFu && lane == (uint32_t)(__ffs((int)peers_t) - 1)) atomicOr(p.tile_masks + tile, orm);
     }
 }
 
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(256) light_view_kernel(const __grid_constant__
     p.light_view[j] = o;
 }
 
-constexpr int kLcWarps = 8;
+constexpr int kLcWarps = 32;
 
 struct Aabb3 { float lo[3], hi[3]; };
 
@@ -169,34 +184,48 @@ __device__ __forceinline__ Aabb3 cluster_volume(const ClusterParams& p, uint32_t
     return a;
 }
 
+// One CTA of kLcWarps warps per active cluster (persistent over clusters through a ticket). The light list is cut
+// into kLcWarps contiguous stripes, one per warp; a warp tests 32 lights per step and ballot-compacts its hits
+// in ascending order into its own shared-memory list (at most 256 entries can ever be used). The stripes are then
+// concatenated in warp order up to the reference's cap of 256, and the cluster's range in the global list comes
+// from a look-back scan over clusters in compacted-list order. With few active clusters (typical: ~100 of 3456)
+// this spreads each cluster's L tests over 1024 threads instead of one warp (measured 716 us -> see profiles/).
 __global__ void __launch_bounds__(kLcWarps * 32) light_culling_kernel(const __grid_constant__ ClusterParams p) {
-    __shared__ uint32_t s_list[kLcWarps][ORBIT_MAX_LIGHTS_PER_CLUSTER];
+    extern __shared__ uint32_t s_dyn[];                       // kLcWarps x 256 hit lists
     __shared__ uint32_t s_warp[kLcWarps];
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile, s_off;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t* const my_list = s_dyn + warp * ORBIT_MAX_LIGHTS_PER_CLUSTER;
     const unsigned int epoch = scan_epoch(p.scan);
     const uint32_t nactive = __ldcg(p.unique_clusters + 3);
-    const uint32_t ntiles = (nactive + kLcWarps - 1) / kLcWarps;
     const uint32_t L = p.info.global_light_count;
+    const uint32_t per = (L + kLcWarps - 1) / kLcWarps;
+    const uint32_t j_begin = min(warp * per, L), j_end = min(j_begin + per, L);
     while (true) {
         __syncthreads();
         if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
         __syncthreads();
         const uint32_t tile = s_tile;
-        if (tile >= ntiles) {
+        if (tile >= nactive) {
             if (tile == 0u && tid == 0) p.light_index_words[0] = 0u;
             break;
         }
-        const uint32_t a = tile * kLcWarps + warp;
-        uint32_t count = 0u, idx = 0u;
-        if (a < nactive) {
-            idx = __ldcg(p.unique_clusters + 4u + a);
-            const Aabb3 box = cluster_volume(p, idx);
-            for (uint32_t j0 = 0; j0 < L && count < ORBIT_MAX_LIGHTS_PER_CLUSTER; j0 += 32u) {
-                const uint32_t j = j0 + lane;
+        const uint32_t idx = __ldcg(p.unique_clusters + 4u + tile);
+        const Aabb3 box = cluster_volume(p, idx);
+        uint32_t count = 0u;   // hits of this warp's stripe (uncapped)
+        for (uint32_t j0 = j_begin; j0 < j_end; j0 += 128u) {
+            float4 sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {   // four independent 512-byte loads in flight per warp
+                const uint32_t j = j0 + (uint32_t)u * 32u + lane;
+                sv[u] = j < j_end ? __ldg(p.light_view + j) : make_float4(0.f, 0.f, 0.f, -1.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + (uint32_t)u * 32u + lane;
                 bool hit = false;
-                if (j < L) {
-                    const float4 s = __ldg(p.light_view + j);
+                if (j < j_end) {
+                    const float4 s = sv[u];
                     float acc = 0.0f;
                     const float c[3] = {s.x, s.y, s.z};
 #pragma unroll
@@ -210,39 +239,36 @@ __global__ void __launch_bounds__(kLcWarps * 32) light_culling_kernel(const __gr
                 const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
                 if (hit) {
                     const uint32_t r = count + __popc(bal & ((1u << lane) - 1u));
-                    if (r < ORBIT_MAX_LIGHTS_PER_CLUSTER) s_list[warp][r] = j;
+                    if (r < ORBIT_MAX_LIGHTS_PER_CLUSTER) my_list[r] = j;
                 }
                 count += __popc(bal);
             }
-            count = min(count, ORBIT_MAX_LIGHTS_PER_CLUSTER);
         }
-        if (lane == 0u) s_warp[warp] = count;
+        if (lane == 0u) s_warp[warp] = min(count, ORBIT_MAX_LIGHTS_PER_CLUSTER);
         __syncthreads();
-        if (warp == 0u) {
-            const uint32_t v = lane < (uint32_t)kLcWarps ? s_warp[lane] : 0u;
-            uint32_t incl = v;
+        // exclusive prefix of the (capped) stripe counts in warp order; everything past 256 is dropped
+        uint32_t before = 0u, total = 0u;
 #pragma unroll
-            for (int d = 1; d < kLcWarps; d <<= 1) {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= (uint32_t)d) incl += t;
-            }
-            const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, incl, kLcWarps - 1);
-            const uint32_t base = lookback_exclusive(p.scan, epoch, tile, tile_total);
-            if (lane < (uint32_t)kLcWarps) s_warp[lane] = base + incl - v;
-            if (lane == 0u && tile == ntiles - 1u) {
-                p.light_index_words[0] = base + tile_total;
-                if ((uint64_t)base + tile_total > p.capacity_indices) *p.overflow_flag = 1u;
+        for (int w = 0; w < kLcWarps; ++w) { const uint32_t v = s_warp[w]; if ((uint32_t)w < warp) before += v; total += v; }
+        total = min(total, ORBIT_MAX_LIGHTS_PER_CLUSTER);
+        if (warp == 0u) {
+            const uint32_t off = lookback_exclusive(p.scan, epoch, tile, total);
+            if (lane == 0u) {
+                s_off = off;
+                p.offset_count_image[2u * (size_t)idx] = off;
+                p.offset_count_image[2u * (size_t)idx + 1u] = total;
+                if (tile == nactive - 1u) {
+                    p.light_index_words[0] = off + total;
+                    if ((uint64_t)off + total > p.capacity_indices) *p.overflow_flag = 1u;
+                }
             }
         }
         __syncthreads();
-        if (a < nactive) {
-            const uint32_t off = s_warp[warp];
-            for (uint32_t k = lane; k < count; k += 32u)
-                if ((uint64_t)off + k < p.capacity_indices) p.light_index_words[1u + off + k] = s_list[warp][k];
-            if (lane == 0u) {
-                p.offset_count_image[2u * (size_t)idx] = off;
-                p.offset_count_image[2u * (size_t)idx + 1u] = count;
-            }
+        const uint32_t off = s_off;
+        const uint32_t mine = min(count, ORBIT_MAX_LIGHTS_PER_CLUSTER);
+        for (uint32_t k = lane; k < mine; k += 32u) {
+            const uint32_t r = before + k;
+            if (r < ORBIT_MAX_LIGHTS_PER_CLUSTER && (uint64_t)off + r < p.capacity_indices) p.light_index_words[1u + off + r] = my_list[k];
         }
     }
     if (tid == 0) scan_cta_exit(p.scan, epoch);
@@ -264,7 +290,14 @@ cudaError_t launch_light_view(const ClusterParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t launch_light_culling(const ClusterParams& p, int grid, cudaStream_t s) {
-    light_culling_kernel<<<grid, kLcWarps * 32, 0, s>>>(p);
+    const size_t smem = (size_t)kLcWarps * ORBIT_MAX_LIGHTS_PER_CLUSTER * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(light_culling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    light_culling_kernel<<<grid, kLcWarps * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 

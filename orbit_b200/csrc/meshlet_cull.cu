@@ -34,6 +34,10 @@ namespace orbit {
 constexpr int kMcWarps = 8;
 constexpr int kMcThreads = kMcWarps * 32;
 constexpr int kMvStride = 20;   // 16 matrix entries + scale, padded
+#ifndef ORBIT_DIRECT_MIN_CTAS
+#define ORBIT_DIRECT_MIN_CTAS 3
+#endif
+constexpr int kDirectMinCtas = ORBIT_DIRECT_MIN_CTAS;
 
 // ---- TMA bulk copy + mbarrier plumbing (PTX; SASS: UBLKCP / SYNCS) --------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -189,7 +193,7 @@ __device__ __forceinline__ void tile_model_view(const MeshletCullParams& p, floa
 // Direct mode: pass 0, pass 2, and pass 1 without a meshlet visibility buffer — every lane of every record is
 // tested. kPass2 = (occlusion_pass == 2 && meshlet occlusion culling on); kProj as in test_item.
 template <int R, bool kPass2, int kProj>
-__global__ void __launch_bounds__(kMcThreads, 3) meshlet_test_direct_kernel(const __grid_constant__ MeshletCullParams p) {
+__global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direct_kernel(const __grid_constant__ MeshletCullParams p) {
     static_assert(R == 2 || R == 4 || R == 8, "records per warp tile");
     extern __shared__ __align__(128) unsigned char s_raw[];
     WarpSmem<R>* const all = reinterpret_cast<WarpSmem<R>*>(s_raw);

@@ -23,6 +23,14 @@ def time_frame(ctx, copies, reps=7, per_graph=8):
     stages = {"entity_early": lambda pf, s: pf.entity(False, s), "meshlet_early": lambda pf, s: pf.meshlet(False, s),
               "hiz": lambda pf, s: pf.hiz(s), "entity_late": lambda pf, s: pf.entity(True, s),
               "meshlet_late": lambda pf, s: pf.meshlet(True, s)}
+    # pass 0 (frustum + cone only, no Hi-Z) over every meshlet the frustum keeps: the HBM-heaviest use of the stage
+    from orbit_b200.passes import OcclusionCullInfo, create_meshlet_dispatch_command, create_meshlet_draw_commands
+    p0 = []
+    for i, pf in enumerate(copies):
+        ci = frame.cull_info_for(pf.view, OcclusionCullInfo("none"))
+        _, disp = create_meshlet_dispatch_command(ctx, "p0_%d" % i, pf.dscene.assets, pf.dscene.scene, ci)
+        p0.append((ci, disp))
+    stages["meshlet_pass0"] = lambda pf, s: create_meshlet_draw_commands(ctx, "p0_%d" % copies.index(pf), pf.dscene.assets, pf.dscene.scene, p0[copies.index(pf)][0], p0[copies.index(pf)][1])
     out = {}
     for name, fn in stages.items():
         for pf in copies:          # consistent steady-state inputs for every stage
@@ -63,6 +71,13 @@ def main():
             copies.append(pf)
         torch.cuda.synchronize()
         t = time_frame(ctx, copies)
+        hdr, recs = frame.read_dispatch(copies[0].context._transients["p0_0_meshlet_dispatch_buffer"])
+        n0, _ = frame.read_draws(copies[0].context._transients["p0_0_meshlet_draw_command_buffer"], capacity=0)
+        lanes0 = int(recs["meshlet_count"].sum())
+        bytes0 = 32 * lanes0 + 16 * len(recs) + 64 * len(np.unique(recs["entity_index"])) + 28 * n0
+        t["pass0_GBs"] = (bytes0 / (t["meshlet_pass0"][0] * 1e-6) / 1e9, 0)
+        t["pass0_lanes_M"] = (lanes0 / 1e6, 0)
+        t["pass0_survivors_M"] = (n0 / 1e6, 0)
         print(json.dumps({"recs_per_warp": rpw, "ctas_per_sm": cps, **{k: round(v[0], 2) for k, v in t.items()},
                           "min_meshlet_late": round(t["meshlet_late"][1], 2)}), flush=True)
         del copies
