@@ -39,7 +39,7 @@ struct orbit_ctx {
     OrbitStatus* status_dev = nullptr;
     uint32_t* chunk_counts = nullptr; // 2 x 2048 per-chunk survivor counts
     // meshlet stage scratch: one draw mask per dispatch record
-    uint32_t* draw_masks = nullptr;
+    uint4* draw_masks = nullptr;
     size_t draw_mask_capacity = 0;
     // light scratch
     float4* light_view = nullptr;
@@ -286,7 +286,7 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     if (max_records > c->draw_mask_capacity) {
         if (c->draw_masks) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->draw_masks)); c->draw_masks = nullptr; c->draw_mask_capacity = 0; }
         size_t cap = 65536; while (cap < max_records) cap *= 2;
-        CK(cudaMalloc(&c->draw_masks, cap * sizeof(uint32_t)));
+        CK(cudaMalloc(&c->draw_masks, cap * sizeof(uint4)));
         c->draw_mask_capacity = cap;
     }
     MeshletCullParams p{};
@@ -300,9 +300,8 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     p.task_payloads = (uint32_t*)task_payloads;
     p.overflow_flag = &c->status_dev->draw_overflow;
     p.draw_masks = c->draw_masks;
-    p.draw_total = c->counters + 4;
-    p.chunk_parity = c->counters + 5;
-    p.emit_done = c->counters + 6;
+    p.draw_total = c->counters + 4;     // [4],[5]
+    p.chunk_parity = c->counters + 6;   // [6] word A, [7] word B
     p.chunk_counts = c->chunk_counts;
     p.capacity_records = max_records;
     p.capacity_draws = capacity_draws;

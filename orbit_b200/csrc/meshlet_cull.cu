@@ -207,7 +207,13 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
     uint32_t nrec = __ldcg(p.dispatch_words);  // workgroup_count_x written by the entity stage
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
     const uint32_t chunk_rec = chunk_records(nrec);
-    uint32_t* const chunk_counts = p.chunk_counts + (__ldcg(p.chunk_parity) & 1u) * kMaxChunks;
+    // Scratch is double-buffered by a parity that lives in device memory (CUDA-graph replays must see fresh state).
+    // Word A is read by test kernels and written by emit kernels; word B the other way round: a kernel never writes
+    // a word that CTAs of the same launch read, so the stream order of the launches is the only synchronisation.
+    const uint32_t half = __ldcg(p.chunk_parity) & 1u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.chunk_parity[1] = half;
+    uint32_t* const chunk_counts = p.chunk_counts + half * kMaxChunks;
+    uint32_t* const draw_total = p.draw_total + half;
     // cyclic tile assignment over all warps of the grid: balances hot and cold regions of the record list
     const uint32_t tiles_total = (nrec + R - 1) / R;
     const uint32_t w_stride = gridDim.x * kMcWarps;
@@ -335,13 +341,18 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
             const uint32_t dm = __ballot_sync(0xFFFFFFFFu, sd);
             if (lane == (uint32_t)r) my_draw_mask = dm;
         }
-        // one draw mask per record, kept L2-resident for the emit kernel; survivors counted per chunk
-        if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = my_draw_mask;
+        // one {draw mask, entity, meshlet offset} per record, kept L2-resident for the emit kernel (so it needs one
+        // load per record and never touches the dispatch buffer); survivors counted per chunk
+        {
+            const uint32_t ent = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 0u) & 31u);
+            const uint32_t mof = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 1u) & 31u);
+            if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(my_draw_mask, ent, mof, 0u);
+        }
         const uint32_t tile_total = __reduce_add_sync(0xFFFFFFFFu, __popc(my_draw_mask));
         if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + rec0 / chunk_rec, tile_total);
         warp_total += tile_total;
     }
-    if (lane == 0u && warp_total != 0u) atomicAdd(p.draw_total, warp_total);
+    if (lane == 0u && warp_total != 0u) atomicAdd(draw_total, warp_total);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -368,7 +379,10 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
     uint32_t nrec = __ldcg(p.dispatch_words);
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
     const uint32_t chunk_rec = chunk_records(nrec);
-    uint32_t* const chunk_counts = p.chunk_counts + (__ldcg(p.chunk_parity) & 1u) * kMaxChunks;
+    const uint32_t half = __ldcg(p.chunk_parity) & 1u;   // see meshlet_test_direct_kernel
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.chunk_parity[1] = half;
+    uint32_t* const chunk_counts = p.chunk_counts + half * kMaxChunks;
+    uint32_t* const draw_total = p.draw_total + half;
     const uint32_t tiles_total = (nrec + R - 1) / R;
     const uint32_t w_stride = gridDim.x * kMcWarps;
     const uint32_t vrow_i = lane & 3u;
@@ -410,12 +424,16 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
         uint32_t my_draw_mask = 0u;
         if (lane < (uint32_t)R) my_draw_mask = ws.mask[lane];
         __syncwarp();
-        if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = my_draw_mask;
+        {
+            const uint32_t ent = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 0u) & 31u);
+            const uint32_t mof = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 1u) & 31u);
+            if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(my_draw_mask, ent, mof, 0u);
+        }
         const uint32_t tile_total = __reduce_add_sync(0xFFFFFFFFu, __popc(my_draw_mask));
         if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + rec0 / chunk_rec, tile_total);
         warp_total += tile_total;
     }
-    if (lane == 0u && warp_total != 0u) atomicAdd(p.draw_total, warp_total);
+    if (lane == 0u && warp_total != 0u) atomicAdd(draw_total, warp_total);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -427,7 +445,8 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
 //      its first output, walks that chunk's draw masks 32 records at a time, and writes its outputs. Survivors
 //      cluster in the visible part of the scene, so splitting by RECORDS leaves a few CTAs with 10-16x the average
 //      work; splitting by OUTPUTS gives every warp the same number.
-//   3. the counts of the OTHER parity are zeroed for the next call; the last CTA flips the parity.
+//   3. the counts of the OTHER parity are zeroed for the next call and the parity word the next test kernel reads is
+//      flipped — no done-counter, fence or atomic on the way out (that exit chain was ~1/3 of this kernel's samples).
 constexpr int kEmitWarps = 8;
 __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __grid_constant__ MeshletCullParams p) {
     __shared__ uint32_t s_prefix[kMaxChunks];            // inclusive survivor count up to chunk c
@@ -437,13 +456,23 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
     const bool want_payload = p.task_payloads != nullptr;
     pdl_launch_dependents();
     pdl_wait();
-    const uint32_t parity = __ldcg(p.chunk_parity) & 1u;
-    const uint32_t grand_total = __ldcg(p.draw_total);
+    // both halves of the chunk counts are requested before the parity is known: one round trip instead of two
+    uint32_t v0[8], v1[8];
+    {
+        const uint4* c0 = reinterpret_cast<const uint4*>(p.chunk_counts) + tid * 2u;
+        const uint4* c1 = reinterpret_cast<const uint4*>(p.chunk_counts + kMaxChunks) + tid * 2u;
+        const uint4 a0 = __ldcg(c0), a1 = __ldcg(c0 + 1), b0 = __ldcg(c1), b1 = __ldcg(c1 + 1);
+        v0[0] = a0.x; v0[1] = a0.y; v0[2] = a0.z; v0[3] = a0.w; v0[4] = a1.x; v0[5] = a1.y; v0[6] = a1.z; v0[7] = a1.w;
+        v1[0] = b0.x; v1[1] = b0.y; v1[2] = b0.z; v1[3] = b0.w; v1[4] = b1.x; v1[5] = b1.y; v1[6] = b1.z; v1[7] = b1.w;
+    }
+    const uint32_t t0 = __ldcg(p.draw_total), t1 = __ldcg(p.draw_total + 1);
     uint32_t nrec = __ldcg(p.dispatch_words);
+    const uint32_t parity = __ldcg(p.chunk_parity + 1) & 1u;   // word B: the half the test kernel of this call used
+    const uint32_t grand_total = parity ? t1 : t0;
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
-    const uint32_t* const counts = p.chunk_counts + parity * kMaxChunks;
     // zero the other parity's counters for the next call (it runs after this kernel in stream order)
     for (uint32_t i = blockIdx.x * blockDim.x + tid; i < kMaxChunks; i += gridDim.x * blockDim.x) p.chunk_counts[(parity ^ 1u) * kMaxChunks + i] = 0u;
+    if (blockIdx.x == 0 && tid == 0) { p.draw_total[parity ^ 1u] = 0u; p.chunk_parity[0] = parity ^ 1u; }   // word A for the next call
     const uint32_t gw = blockIdx.x * kEmitWarps + warp, GW = gridDim.x * kEmitWarps;
     if (grand_total != 0u) {
         const uint32_t chunk_rec = chunk_records(nrec);
@@ -451,11 +480,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
         // ---- 1. chunk counts -> inclusive prefix in shared memory (8 consecutive chunks per thread)
         uint32_t v[8], local = 0u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t i = tid * 8u + (uint32_t)k;
-            v[k] = i < nchunks ? __ldcg(counts + i) : 0u;
-            local += v[k];
-        }
+        for (int k = 0; k < 8; ++k) { v[k] = parity ? v1[k] : v0[k]; local += v[k]; }
         uint32_t incl = local;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -490,8 +515,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
             uint32_t rec = lo * chunk_rec;
             while (running < o_end && rec < nrec) {
                 const uint32_t my = rec + lane;
-                uint32_t dm = 0u, entity = 0u, moff = 0u;
-                if (my < nrec) dm = __ldcg(p.draw_masks + my);
+                uint4 e = make_uint4(0u, 0u, 0u, 0u);
+                if (my < nrec) e = __ldcg(p.draw_masks + my);
+                const uint32_t dm = e.x, entity = e.y, moff = e.z;
                 const uint32_t pc = __popc(dm);
                 uint32_t inc = pc;
 #pragma unroll
@@ -501,10 +527,6 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
                 }
                 const uint32_t step_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
                 if (running + step_total > o_begin) {
-                    if (dm != 0u) {
-                        entity = __ldcg(p.dispatch_words + 3u + (size_t)my * 4u + 0u);
-                        moff = __ldcg(p.dispatch_words + 3u + (size_t)my * 4u + 1u);
-                    }
                     __syncwarp();
                     sr[lane] = inc; sr[32 + lane] = dm; sr[64 + lane] = entity; sr[96 + lane] = moff;
                     __syncwarp();
@@ -539,7 +561,8 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
         // MeshTaskPayload + emitted task count per record (record-parallel; indices ascending by lane — the task
         // shader's atomicAdd order is arbitrary): one warp per record, lane q packs index bytes 4q..4q+3
         for (uint32_t r = gw; r < nrec; r += GW) {
-            const uint32_t rdm = __ldcg(p.draw_masks + r);
+            const uint4 e = __ldcg(p.draw_masks + r);
+            const uint32_t rdm = e.x;
             uint32_t* tp = p.task_payloads + (size_t)r * 11u;
             if (lane < 8u) {
                 uint32_t packed_idx = 0u, m = rdm;
@@ -548,16 +571,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
                 tp[3u + lane] = packed_idx;
             }
             if (lane == 8u) tp[0] = __popc(rdm);
-            if (lane == 9u) tp[1] = __ldcg(p.dispatch_words + 3u + (size_t)r * 4u + 0u);
-            if (lane == 10u) tp[2] = __ldcg(p.dispatch_words + 3u + (size_t)r * 4u + 1u);
+            if (lane == 9u) tp[1] = e.y;
+            if (lane == 10u) tp[2] = e.z;
         }
-    }
-    // ---- 3. last CTA out: re-arm the survivor total and flip the parity
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned int prev = atomicAdd(p.emit_done, 1u);
-        if (prev + 1u == gridDim.x) { *p.emit_done = 0u; *p.draw_total = 0u; *p.chunk_parity = parity ^ 1u; }
     }
 }
 

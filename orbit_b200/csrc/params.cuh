@@ -31,11 +31,10 @@ struct MeshletCullParams {
     uint32_t* draw_words;             // MeshletDrawCommandBuffer as u32[]: count then 7 words per command
     uint32_t* task_payloads;          // nullable, 11 words per record
     uint32_t* overflow_flag;          // host-mapped status word
-    uint32_t* draw_masks;             // scratch: one draw mask per dispatch record (test kernel -> emit kernel)
-    uint32_t* draw_total;             // scratch: survivors counted by the test kernel (re-zeroed by the emit kernel)
+    uint4* draw_masks;                // scratch: {draw mask, entity, meshlet offset, 0} per dispatch record (test -> emit kernel)
+    uint32_t* draw_total;             // scratch[2]: survivors counted by the test kernel, per parity (re-zeroed by the emit kernel)
     uint32_t* chunk_counts;           // scratch: 2 x 2048 per-chunk survivor counts (double-buffered by parity)
-    uint32_t* chunk_parity;           // scratch: which half the current call uses (flipped by the emit kernel)
-    uint32_t* emit_done;              // scratch: CTAs of the emit kernel that have finished
+    uint32_t* chunk_parity;           // scratch[2]: word A (read by test, written by emit), word B (written by test, read by emit)
     uint64_t capacity_records;
     uint64_t capacity_draws;
     ScanState scan;
