@@ -156,6 +156,18 @@ int orbit_light_cluster(orbit_ctx* ctx, const OrbitClusterParams* params, const 
 int orbit_draws_scatter(orbit_ctx* ctx, const void* src_draw_buffer, void* dst_draw_buffer,
                         uint32_t dst_first, uint32_t total_count, uint64_t dst_capacity_draws, void* stream);
 
+/* Peer-visible device memory for that assembly: one process per GPU, so a rank's output buffer is shared with the
+ * other ranks through CUDA IPC. `orbit_peer_alloc` returns cudaMalloc'd memory plus its 64-byte IPC handle;
+ * `orbit_peer_open` maps another rank's buffer into this process (NVLink peer access); stores through the mapped
+ * pointer go over NVLink. `orbit_device_copy` is an asynchronous device-to-device copy (reading results back into
+ * caller-owned tensors). */
+#define ORBIT_IPC_HANDLE_BYTES 64
+int  orbit_peer_alloc(orbit_ctx* ctx, uint64_t bytes, void** out_ptr, void* out_handle /* 64 bytes */);
+int  orbit_peer_open(orbit_ctx* ctx, const void* handle /* 64 bytes */, void** out_ptr);
+int  orbit_peer_close(orbit_ctx* ctx, void* mapped_ptr);
+void orbit_peer_free(orbit_ctx* ctx, void* ptr);
+int  orbit_device_copy(void* dst, const void* src, uint64_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -378,8 +378,51 @@ int orbit_draws_scatter(orbit_ctx* c, const void* src, void* dst, uint32_t dst_f
                         uint64_t dst_capacity_draws, void* stream) {
     if (!c || !src || !dst) return ORBIT_ERR_INVALID_ARGUMENT;
     CK(launch_draws_scatter((const uint32_t*)src, (uint32_t*)dst, dst_first, total_count, dst_capacity_draws,
-                            c->sm_count * 4, (cudaStream_t)stream));
+                            c->sm_count * 16, (cudaStream_t)stream));
     c->launches += 1;
+    return ORBIT_OK;
+}
+
+int orbit_peer_alloc(orbit_ctx* c, uint64_t bytes, void** out_ptr, void* out_handle) {
+    if (!c || !out_ptr || !out_handle || bytes == 0) return ORBIT_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return e == cudaErrorMemoryAllocation ? ORBIT_ERR_OUT_OF_MEMORY : ORBIT_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; cudaFree(p); return ORBIT_ERR_CUDA; }
+    static_assert(sizeof(h) == ORBIT_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(out_handle, &h, sizeof(h));
+    *out_ptr = p;
+    return ORBIT_OK;
+}
+
+int orbit_peer_open(orbit_ctx* c, const void* handle, void** out_ptr) {
+    if (!c || !handle || !out_ptr) return ORBIT_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CK(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return ORBIT_OK;
+}
+
+int orbit_peer_close(orbit_ctx* c, void* mapped_ptr) {
+    if (!c || !mapped_ptr) return ORBIT_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    CK(cudaIpcCloseMemHandle(mapped_ptr));
+    return ORBIT_OK;
+}
+
+void orbit_peer_free(orbit_ctx* c, void* ptr) {
+    if (!c || !ptr) return;
+    cudaSetDevice(c->device);
+    cudaFree(ptr);
+}
+
+int orbit_device_copy(void* dst, const void* src, uint64_t bytes, void* stream) {
+    if (!dst || !src) return ORBIT_ERR_INVALID_ARGUMENT;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return ORBIT_OK;
 }
 
@@ -395,7 +438,15 @@ __global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __re
     const uint64_t words = m * 7u;
     const uint32_t* s = src + 1;
     uint32_t* d = dst + 1u + (uint64_t)dst_first * 7u;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) d[i] = __ldcg(s + i);
+    // 4 independent words per thread per round (the 28-byte commands start 4 bytes into both buffers, so 16-byte
+    // vectors would need a shifted pipeline; with enough loads in flight 4-byte accesses still fill NVLink)
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3u * stride < words; i += 4u * stride) {
+        const uint32_t a = __ldcg(s + i), b = __ldcg(s + i + stride), c = __ldcg(s + i + 2u * stride), e = __ldcg(s + i + 3u * stride);
+        d[i] = a; d[i + stride] = b; d[i + 2u * stride] = c; d[i + 3u * stride] = e;
+    }
+    for (; i < words; i += stride) d[i] = __ldcg(s + i);
     if (blockIdx.x == 0 && threadIdx.x == 0 && total_count != 0xFFFFFFFFu) dst[0] = total_count;
 }
 cudaError_t launch_draws_scatter(const uint32_t* src, uint32_t* dst, uint32_t dst_first, uint32_t total_count,

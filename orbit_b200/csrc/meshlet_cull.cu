@@ -157,7 +157,8 @@ struct __align__(128) WarpSmem {
     float mv[R][kMvStride];        // view*model + scale per record
     float q[6][64];                // ring buffer of Hi-Z candidates: x, y, z, r, r_model, scale
     uint32_t qid[64];              //   (record << 5) | lane
-    uint32_t mask[R];              // per-record visible / draw masks under construction
+    uint32_t mask[R];              // per-record visible masks under construction
+    uint32_t aok[R], nsk[R];       // per-record "alpha mode passes the filter" / "alpha mode is noskip" lane masks
     unsigned long long bar;        // mbarrier of the TMA copies
 };
 
@@ -268,34 +269,39 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
         if (kPass2 && lane < (uint32_t)R && my_cnt != 0u) vw = __ldcg(p.meshlet_visibility + my_vo);
         tile_model_view<R>(p, mv_base, my_word, lane, v0, v1, v2, v3);
 
-        uint32_t vis_mask[R], packed[R];
         uint32_t qn = 0u;
         mbar_wait(bar, parity);
         parity ^= 1u;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, my_word, r * 4 + 2);   // 0 for records past the end
-            vis_mask[r] = 0u; packed[r] = 0u;
-            if (cnt == 0u) continue;   // warp-uniform
-            bool pre = false;
+        // The record loop is deliberately NOT unrolled: four inlined copies of the test (~600 SASS instructions each)
+        // overflowed the instruction cache (9% of issue stalls were "no instruction"); per-record results live in
+        // shared memory as warp-uniform 32-bit masks instead of register arrays.
+#pragma unroll 1
+        for (uint32_t r = 0; r < (uint32_t)R; ++r) {
+            const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, my_word, r * 4u + 2u);   // 0 for records past the end
+            if (cnt == 0u) { if (lane == 0u) { ws.mask[r] = 0u; ws.aok[r] = 0u; ws.nsk[r] = 0u; } continue; }   // warp-uniform
+            bool pre = false, alpha_ok = false, noskip = false;
             ItemTest t;
             if (lane < cnt) {
-                const uint4 a = ws.meshlets[r * 64 + lane * 2];
-                const uint4 b = ws.meshlets[r * 64 + lane * 2 + 1];
-                packed[r] = b.w;
+                const uint4 a = ws.meshlets[r * 64u + lane * 2u];
+                const uint4 b = ws.meshlets[r * 64u + lane * 2u + 1u];
+                const uint32_t alpha = __ldg(reinterpret_cast<const uint32_t*>(
+                    p.materials + (size_t)(b.w & 0xFFFFu) * ORBIT_MATERIAL_STRIDE_BYTES + ORBIT_MATERIAL_ALPHA_MODE_OFFSET));
+                alpha_ok = (shl1(alpha) & ci.alpha_mode_flags) != 0u;
+                noskip = (shl1(alpha) & ci.noskip_alpha_mode) != 0u;
                 t = test_item<kProj>(ci, mv_base + r * kMvStride, a, b.x);
                 pre = t.pre_visible;
             }
             const uint32_t pre_mask = __ballot_sync(0xFFFFFFFFu, pre);
-            vis_mask[r] = pre_mask;
+            const uint32_t aok_mask = __ballot_sync(0xFFFFFFFFu, alpha_ok);
+            const uint32_t nsk_mask = kPass2 ? __ballot_sync(0xFFFFFFFFu, noskip) : 0u;
+            if (lane == 0u) { ws.mask[r] = pre_mask; ws.aok[r] = aok_mask; ws.nsk[r] = nsk_mask; }
             if (kPass2) {
                 // queue the survivors for the Hi-Z test; run it whenever a full warp of them is waiting
-                if (lane == 0u) ws.mask[r] = pre_mask;
                 if (pre) {
                     const uint32_t slot = (qhead + qn + __popc(pre_mask & lt)) & 63u;
                     ws.q[0][slot] = t.s.x; ws.q[1][slot] = t.s.y; ws.q[2][slot] = t.s.z;
                     ws.q[3][slot] = t.s.r; ws.q[4][slot] = t.s.r_model; ws.q[5][slot] = t.s.s;
-                    ws.qid[slot] = ((uint32_t)r << 5) | lane;
+                    ws.qid[slot] = (r << 5) | lane;
                 }
                 qn += __popc(pre_mask);
                 __syncwarp();
@@ -326,21 +332,21 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
             }
             qhead = (qhead + qn) & 63u;
             __syncwarp();
-            if (lane < (uint32_t)R && my_cnt != 0u) p.meshlet_visibility[my_vo] = ws.mask[lane];   // ballot(visible), meshlet_cull.comp:235-242
-#pragma unroll
-            for (int r = 0; r < R; ++r) vis_mask[r] = ws.mask[r] & vis_mask[r];
-            __syncwarp();
         }
-        uint32_t my_draw_mask = 0u;   // lane r keeps the draw mask of record r
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const uint32_t vword = __shfl_sync(0xFFFFFFFFu, vw, r);   // all ones when visibility is not in use
-            const bool visible = ((vis_mask[r] >> lane) & 1u) != 0u;
-            const bool vib = ((vword >> lane) & 1u) != 0u;
-            const bool sd = draw_rule(ci, p, visible, vib, kPass2, packed[r]);
-            const uint32_t dm = __ballot_sync(0xFFFFFFFFu, sd);
-            if (lane == (uint32_t)r) my_draw_mask = dm;
+        // lane r < R finishes record r with warp-uniform bit logic (meshlet_cull.comp:207-213):
+        //   should_draw = visible && alpha passes the filter; in pass 2, unless the alpha mode is "noskip",
+        //   should_draw = visible && !visible_last_frame (this overrides the alpha filter)
+        uint32_t my_draw_mask = 0u;
+        if (lane < (uint32_t)R) {
+            const uint32_t vis = ws.mask[lane], aok = ws.aok[lane], nsk = ws.nsk[lane];
+            if (kPass2) {
+                if (my_cnt != 0u) p.meshlet_visibility[my_vo] = vis;   // ballot(visible), meshlet_cull.comp:235-242
+                my_draw_mask = vis & ((nsk & aok) | (~nsk & ~vw));
+            } else {
+                my_draw_mask = vis & aok;
+            }
         }
+        __syncwarp();
         // one {draw mask, entity, meshlet offset} per record, kept L2-resident for the emit kernel (so it needs one
         // load per record and never touches the dispatch buffer); survivors counted per chunk
         {

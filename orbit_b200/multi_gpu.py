@@ -78,6 +78,68 @@ def exchange_survivors(local_draw_buffer: torch.Tensor, out_buffer: torch.Tensor
     return out_buffer[:4 + DRAW_BYTES * total], counts_h
 
 
+class PeerExchange:
+    """Survivor exchange over NVLink peer stores instead of a padded NCCL all-gather.
+
+    Every rank owns one output MeshletDrawCommandBuffer in cudaMalloc'd memory shared through CUDA IPC
+    (orbit_peer_alloc / orbit_peer_open). After the per-rank counts are all-gathered (4 bytes each, the only
+    collective), each rank's `orbit_draws_scatter` kernel stores its commands straight into EVERY rank's output
+    buffer at command index sum(counts[:rank]) — remote stores travel over NVLink — so every rank ends up with the
+    full rank-major list without staging or padding. A barrier closes the step."""
+
+    def __init__(self, context, capacity_draws, group=None):
+        import ctypes as C
+        from . import _lib
+        self.C, self.lib, self.context, self.group = C, _lib.lib(), context, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.capacity = int(capacity_draws)
+        self.bytes = 4 + DRAW_BYTES * self.capacity
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(self.lib.orbit_peer_alloc(context._h, self.bytes, C.byref(ptr), handle), "orbit_peer_alloc")
+        self.local_ptr = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.peer_ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.peer_ptrs.append(self.local_ptr)
+            else:
+                q = C.c_void_p()
+                _lib.check(self.lib.orbit_peer_open(context._h, handles[r], C.byref(q)), "orbit_peer_open")
+                self.peer_ptrs.append(q.value)
+        self.counts = torch.zeros(self.world, dtype=torch.int32, device=context.device)
+        dist.barrier(group=group)
+
+    def exchange(self, local_draw_buffer):
+        """Returns (total count, per-rank counts); the assembled list is in self.local_ptr (see read())."""
+        C = self.C
+        dist.all_gather_into_tensor(self.counts, local_draw_buffer[:4].view(torch.int32), group=self.group)
+        counts = [int(v) for v in self.counts.cpu().tolist()]
+        total, first = sum(counts), sum(counts[:self.rank])
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for r in range(self.world):
+            rc = self.lib.orbit_draws_scatter(self.context._h, C.c_void_p(local_draw_buffer.data_ptr()), C.c_void_p(self.peer_ptrs[r]),
+                                              first, total, self.capacity, stream)
+            if rc:
+                raise RuntimeError("orbit_draws_scatter: %d" % rc)
+        dist.barrier(group=self.group)   # every rank's stores into my buffer are complete and visible
+        return total, counts
+
+    def read(self, total):
+        """Copies the assembled MeshletDrawCommandBuffer (count + total commands) into a torch tensor."""
+        out = torch.empty(4 + DRAW_BYTES * total, dtype=torch.uint8, device=self.context.device)
+        self.lib.orbit_device_copy(self.C.c_void_p(out.data_ptr()), self.C.c_void_p(self.local_ptr), out.numel(),
+                                   self.C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def close(self):
+        for r, q in enumerate(self.peer_ptrs):
+            if r != self.rank:
+                self.lib.orbit_peer_close(self.context._h, self.C.c_void_p(q))
+        self.lib.orbit_peer_free(self.context._h, self.C.c_void_p(self.local_ptr))
+
+
 class ShardedView:
     """One huge view culled by `world` GPUs (BASELINE config C3). Rank 0 owns the depth buffer and builds the
     pyramid; every rank culls its entity-draw range with the CUDA passes; survivors are all-gathered."""
@@ -98,6 +160,11 @@ class ShardedView:
             (view.height, view.width), dtype=torch.float32, device=context.device)
         self.prepared = frame.PreparedFrame(context, self.dscene, self.vstate, view, self.depth)
 
+    def enable_peer_exchange(self, capacity_draws):
+        """Use NVLink peer stores (PeerExchange) for the survivor exchange instead of the padded NCCL all-gather."""
+        self.peer_early = PeerExchange(self.context, capacity_draws)
+        self.peer_late = PeerExchange(self.context, capacity_draws)
+
     def step(self, exchange=True):
         """One two-pass frame: early cull (local range) -> Hi-Z on rank 0 + broadcast -> late cull -> gather."""
         pf = self.prepared
@@ -112,6 +179,10 @@ class ShardedView:
             pf.early_draws[:4].zero_(); pf.late_draws[:4].zero_()
         if not exchange:
             return None
+        if exchange == "peer":
+            n_e, _ = self.peer_early.exchange(pf.early_draws)
+            n_l, _ = self.peer_late.exchange(pf.late_draws)
+            return n_e, n_l
         early, _ = exchange_survivors(pf.early_draws)
         late, _ = exchange_survivors(pf.late_draws)
         return early, late

@@ -100,15 +100,26 @@ def run_c3(args, rank, world, ctx):
     t_full = event_time(lambda: sv.step(exchange=True))[0]
     early, late = sv.step(exchange=True)
     torch.cuda.synchronize()
+    t_peer, peer_ok = None, None
     if world > 1:
-        t = torch.tensor([t_compute, t_full], device=ctx.device, dtype=torch.float64)
+        sv.enable_peer_exchange(scene.n_meshlet_instances)
+        sv.step(exchange="peer")
+        t_peer = event_time(lambda: sv.step(exchange="peer"))[0]
+        n_e, n_l = sv.step(exchange="peer")
+        torch.cuda.synchronize()
+        pe, pl = sv.peer_early.read(n_e), sv.peer_late.read(n_l)
+        torch.cuda.synchronize()
+        peer_ok = bool(torch.equal(pe, early) and torch.equal(pl, late))
+        t = torch.tensor([t_compute, t_full, t_peer], device=ctx.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_compute, t_full = float(t[0]), float(t[1])
+        t_compute, t_full, t_peer = float(t[0]), float(t[1]), float(t[2])
     res = {"config": "C3", "n_gpus": world, "entities": scene.n_entities, "meshlet_instances": scene.n_meshlet_instances,
            "ranges": sv.ranges, "us_compute": t_compute, "us_with_exchange": t_full,
            "gmeshlets_per_s_compute": scene.n_meshlet_instances / t_compute / 1e3,
            "gmeshlets_per_s_with_exchange": scene.n_meshlet_instances / t_full / 1e3,
-           "pyramid_bytes": int(sv.vstate.depth_pyramid.texels.numel() * 4)}
+           "pyramid_bytes": int(sv.vstate.depth_pyramid.texels.numel() * 4),
+           "us_with_peer_exchange": t_peer, "peer_exchange_equals_allgather": peer_ok,
+           "gmeshlets_per_s_with_peer_exchange": (scene.n_meshlet_instances / t_peer / 1e3) if t_peer else None}
     if rank == 0:
         n_early = int(early[:4].view(torch.int32).item()); n_late = int(late[:4].view(torch.int32).item())
         res["survivors_early"], res["survivors_late"] = n_early, n_late
