@@ -91,6 +91,15 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_final_meshlet_test_ncu.json")) as f:
+            return int(json.load(f)["dram_traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def late_meshlet_algorithmic_bytes(records, n_draws, n_materials=16, passes_vis=2):
     """SURVEY §8(d) meshlet-stage formula, pass 2, WITHOUT the pyramid term (conservative: sampled texels are not
     counted): 32*L + 16*R + 12 + 64*E + 400 + 80*mats + 4*R (visibility read) + 4*R (visibility write) + 4 + 28*S."""
@@ -313,7 +322,8 @@ def run_ours(args, rank, world, local_rank):
                            N_COPIES, sum(scene.bytes_summary().values()) // 2 ** 20),
                        "launch": "one CUDA graph replay per step (7 kernels: 2x entity_cull, 2x meshlet_test+meshlet_emit, hiz_build)", "views": "every rank culls its own instance of the C2 view on a replicated scene; no data-path collective"},
             "roofline": {"bound": "hbm", "kernel": "meshlet_test_direct_kernel<4,pass2,persp> + meshlet_emit_kernel (late pass, occlusion_pass=2)", "achieved": achieved,
-                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                         "traffic_source": "profiles/r1_final_meshlet_test_ncu.json (ncu --set full, per launch, bytes)",
                          "algorithmic_bytes_per_launch": late_bytes, "launch_us_median": late_us, "launch_us_min": k_times["meshlet_late"][1],
                          "lanes": late_lanes, "records": late_R, "entities": late_E, "survivors": n_late_draws,
                          "stage_gmeshlets_per_s": late_lanes / (late_us * 1e-6) / 1e9,

@@ -40,8 +40,16 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
     }
     const uint32_t ntiles = gridDim.x;
 
-    const uint32_t count = min(__ldg(p.entity_draw_words), p.draw_end);
+    // The draw words are requested before the device-side count is known (gid < draw_end <= the host's
+    // entity_draw_count, which sized the buffer): one dependent round trip less on a latency-bound kernel.
     const uint32_t gid = p.draw_begin + tile * kEcThreads + tid;
+    uint32_t entity_index = 0u, mesh_index = 0u, vis_offset = 0u;
+    if (gid < p.draw_end) {
+        entity_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 0u);
+        mesh_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 1u);
+        vis_offset = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 2u);
+    }
+    const uint32_t count = min(__ldg(p.entity_draw_words), p.draw_end);
     const uint32_t pass = ci.occlusion_pass;
     const bool mocc = ci.meshlet_visibility_buffer != ORBIT_NO_BUFFER;
 
@@ -49,9 +57,6 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
     bool visible = false;
     const bool in_range = gid < count;
     if (in_range) {
-        const uint32_t entity_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 0u);
-        const uint32_t mesh_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 1u);
-        const uint32_t vis_offset = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 2u);
         const uint8_t* mi = p.mesh_infos + (size_t)mesh_index * 128u;
         const float4 sph = __ldg(reinterpret_cast<const float4*>(mi));
         const uint4 mi_hdr = __ldg(reinterpret_cast<const uint4*>(mi + 48));      // vertex_offset, data_offset, lod_count, pad

@@ -111,8 +111,9 @@ __device__ __forceinline__ unsigned int gather_lower_aggregates(const ScanState&
 }
 
 // Every CTA calls this once on exit (one thread). The last CTA re-arms the ticket for the next launch.
+// No fence is needed: the control words touched here do not depend on the visibility of the kernel's data writes
+// (the kernel boundary publishes those), and a fence would add a full store-drain round trip to every CTA's exit.
 __device__ __forceinline__ void scan_cta_exit(const ScanState& st, unsigned int epoch, unsigned int* also_zero = nullptr) {
-    __threadfence();
     unsigned int prev = atomicAdd(st.done, 1u);
     if (prev + 1u == gridDim.x) {
         *st.ticket = 0u;
@@ -120,7 +121,6 @@ __device__ __forceinline__ void scan_cta_exit(const ScanState& st, unsigned int 
         if (also_zero) *also_zero = 0u;
         unsigned int next = (epoch + 1u) & 0x3FFFFFFFu;
         *st.epoch = next ? next : 1u;
-        __threadfence();
     }
 }
 
