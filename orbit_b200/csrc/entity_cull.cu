@@ -29,7 +29,6 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const OrbitCullInfo& ci = p.cull;
-    pdl_launch_dependents();
     pdl_wait();
     const unsigned int epoch = scan_epoch(p.scan);
     uint32_t tile = blockIdx.x;
@@ -144,6 +143,7 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
         }
     }
     __syncthreads();
+    pdl_launch_dependents();
     // ---- load-balanced emission: record j of the tile's span
     const uint64_t base = s_base;
     for (uint32_t j = tid; j < tile_total; j += kEcThreads) {

@@ -78,7 +78,6 @@ __device__ void hiz_tail_smem(const HizBuildParams& p, uint32_t first, float* s_
 }
 
 __global__ void __launch_bounds__(256) hiz_small_kernel(const __grid_constant__ HizBuildParams p) {
-    pdl_launch_dependents();
     pdl_wait();
     hiz_tail(p, 0u);
 }
@@ -90,7 +89,6 @@ __global__ void __launch_bounds__(256) hiz_build_kernel(const __grid_constant__ 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tiles_x = p.width >> 6;
     const uint32_t tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    pdl_launch_dependents();
     pdl_wait();
 
     // ---- level 0: lane owns columns 2*lane, 2*lane+1 of rows warp*8 .. warp*8+7 of the tile
@@ -164,6 +162,7 @@ __global__ void __launch_bounds__(256) hiz_build_kernel(const __grid_constant__ 
         v6 = fminf(v6, __shfl_xor_sync(0xFFFFFFFFu, v6, 8));
         if (lane == 0u) p.texels[p.level_offset[6] + (size_t)ty * (p.width >> 6) + tx] = v6;
     }
+    pdl_launch_dependents();
     if (p.levels <= 7u) return;
     // ---- remaining small levels: last CTA to arrive
     __threadfence();

@@ -203,7 +203,6 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
     const uint32_t lt = (1u << lane) - 1u;
     WarpSmem<R>& ws = all[warp];
     const OrbitCullInfo& ci = p.cull;
-    pdl_launch_dependents();
     pdl_wait();
     uint32_t nrec = __ldcg(p.dispatch_words);  // workgroup_count_x written by the entity stage
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
@@ -358,6 +357,7 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
         if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + rec0 / chunk_rec, tile_total);
         warp_total += tile_total;
     }
+    pdl_launch_dependents();
     if (lane == 0u && warp_total != 0u) atomicAdd(draw_total, warp_total);
 }
 
@@ -380,7 +380,6 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
     const uint32_t lt = (1u << lane) - 1u;
     PackedSmem<R>& ws = s_all[warp];
     const OrbitCullInfo& ci = p.cull;
-    pdl_launch_dependents();
     pdl_wait();
     uint32_t nrec = __ldcg(p.dispatch_words);
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
@@ -439,6 +438,7 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
         if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + rec0 / chunk_rec, tile_total);
         warp_total += tile_total;
     }
+    pdl_launch_dependents();
     if (lane == 0u && warp_total != 0u) atomicAdd(draw_total, warp_total);
 }
 
@@ -460,7 +460,6 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
     __shared__ uint32_t s_rec[kEmitWarps][4][32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const bool want_payload = p.task_payloads != nullptr;
-    pdl_launch_dependents();
     pdl_wait();
     // both halves of the chunk counts are requested before the parity is known: one round trip instead of two
     uint32_t v0[8], v1[8];
@@ -506,6 +505,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
             p.draw_words[0] = total;   // exact count even when it exceeds capacity
             if ((uint64_t)total > p.capacity_draws) *p.overflow_flag = 1u;
         }
+        pdl_launch_dependents();
         // ---- 2. my share of the outputs
         const uint32_t o_begin = (uint32_t)(((uint64_t)total * gw) / GW);
         const uint32_t o_end = (uint32_t)(((uint64_t)total * (gw + 1u)) / GW);

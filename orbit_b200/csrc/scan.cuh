@@ -12,10 +12,10 @@
 
 namespace orbit {
 
-// Programmatic dependent launch (PDL): every kernel of the pipeline lets its successor be scheduled early
-// (`launch_dependents` at entry) and waits for its predecessor's results right before its first global access
-// (`wait`), so the ~2 us launch ramp of each of the 7 small dependent kernels of a frame overlaps the previous
-// kernel instead of adding to it. Both are no-ops when a kernel is launched without the PDL attribute.
+// Programmatic dependent launch (PDL): every kernel of the pipeline waits for its predecessor's results before its
+// first global access (`wait`) and lets its successor be scheduled once its own main work is done
+// (`launch_dependents` near the end), so the launch ramp of each of the 7 small dependent kernels of a frame
+// overlaps the tail of the previous one. Both are no-ops when a kernel is launched without the PDL attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
