@@ -13,10 +13,10 @@ using namespace orbit;
 
 namespace orbit {
 bool pdl_enabled() {
-    // measured on B200 (profiles/r1_pdl.txt): with the trigger at kernel ENTRY the frame got ~10% slower (early-resident
-    // dependents take SM slots from the persistent kernels); with the trigger at the END of each kernel's main work
-    // it is ~2% faster (the successor's launch ramp overlaps the tail). Default on; ORBIT_NO_PDL=1 disables it.
-    static const bool on = std::getenv("ORBIT_NO_PDL") == nullptr;
+    // measured on B200 (profiles/r1_pdl.txt): trigger at kernel ENTRY: frame ~10% slower; trigger at the END of each
+    // kernel's main work: steady-state C2 frame 1.3% faster, but a pass-0 sweep with 1.2M survivors 15% slower.
+    // Not a clear win -> opt-in: ORBIT_PDL=1.
+    static const bool on = std::getenv("ORBIT_PDL") != nullptr;
     return on;
 }
 }  // namespace orbit

@@ -6,7 +6,7 @@
 
 namespace orbit {
 
-// Launch helper; adds programmatic stream serialization (PDL) unless ORBIT_NO_PDL is set (see api.cu).
+// Launch helper; adds programmatic stream serialization (PDL) when ORBIT_PDL is set (opt-in, see api.cu).
 bool pdl_enabled();
 template <typename P>
 inline cudaError_t launch_kernel(void (*kernel)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const P& params) {
