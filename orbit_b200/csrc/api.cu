@@ -430,7 +430,10 @@ int orbit_device_copy(void* dst, const void* src, uint64_t bytes, void* stream) 
 }  // extern "C"
 
 namespace orbit {
-// Copies src's commands into dst at command index dst_first (peer-mapped dst allowed): plain coalesced words.
+// Copies src's commands into dst at command index dst_first (peer-mapped dst allowed). The 28-byte commands start
+// 4 bytes into both buffers and dst_first shifts the destination further, so source and destination are not
+// mutually 16-byte aligned: the body issues ALIGNED 16-byte stores to the destination (what matters over NVLink),
+// each assembled from four 4-byte loads of the local source; up to 3 head and 3 tail words go out as 4-byte stores.
 __global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
                                                             uint32_t dst_first, uint32_t total_count, uint64_t dst_capacity) {
     const uint32_t n = __ldcg(src);
@@ -439,15 +442,20 @@ __global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __re
     const uint64_t words = m * 7u;
     const uint32_t* s = src + 1;
     uint32_t* d = dst + 1u + (uint64_t)dst_first * 7u;
-    // 4 independent words per thread per round (the 28-byte commands start 4 bytes into both buffers, so 16-byte
-    // vectors would need a shifted pipeline; with enough loads in flight 4-byte accesses still fill NVLink)
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3u * stride < words; i += 4u * stride) {
-        const uint32_t a = __ldcg(s + i), b = __ldcg(s + i + stride), c = __ldcg(s + i + 2u * stride), e = __ldcg(s + i + 3u * stride);
-        d[i] = a; d[i + stride] = b; d[i + 2u * stride] = c; d[i + 3u * stride] = e;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (uint64_t)gridDim.x * blockDim.x;
+    // head: words until d + head is 16-byte aligned
+    uint64_t head = ((16u - ((uintptr_t)d & 15u)) & 15u) >> 2;
+    if (head > words) head = words;
+    const uint64_t body4 = (words - head) >> 2;           // number of aligned uint4 stores
+    if (gtid < head) d[gtid] = __ldcg(s + gtid);
+    uint4* d4 = reinterpret_cast<uint4*>(d + head);
+    const uint32_t* sb = s + head;
+    for (uint64_t i = gtid; i < body4; i += gsize) {
+        const uint32_t a = __ldcg(sb + 4u * i), b = __ldcg(sb + 4u * i + 1u), c = __ldcg(sb + 4u * i + 2u), e = __ldcg(sb + 4u * i + 3u);
+        d4[i] = make_uint4(a, b, c, e);
     }
-    for (; i < words; i += stride) d[i] = __ldcg(s + i);
+    const uint64_t done = head + 4u * body4;
+    if (gtid < words - done) d[done + gtid] = __ldcg(s + done + gtid);
     if (blockIdx.x == 0 && threadIdx.x == 0 && total_count != 0xFFFFFFFFu) dst[0] = total_count;
 }
 cudaError_t launch_draws_scatter(const uint32_t* src, uint32_t* dst, uint32_t dst_first, uint32_t total_count,

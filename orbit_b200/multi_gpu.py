@@ -118,7 +118,8 @@ class PeerExchange:
         counts = [int(v) for v in self.counts.cpu().tolist()]
         total, first = sum(counts), sum(counts[:self.rank])
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for r in range(self.world):
+        for k in range(self.world):
+            r = (self.rank + k) % self.world       # staggered destinations: no rank is everybody's first target
             rc = self.lib.orbit_draws_scatter(self.context._h, C.c_void_p(local_draw_buffer.data_ptr()), C.c_void_p(self.peer_ptrs[r]),
                                               first, total, self.capacity, stream)
             if rc:
