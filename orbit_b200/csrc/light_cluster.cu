@@ -7,7 +7,8 @@
 //
 // B200 design:
 //   * mark_active: 2-3 global atomics per PIXEL in the reference; here lanes of a warp that hit the same
-//     cluster are merged with match.any + redux (max / or) so one lane per distinct cluster issues the atomics.
+//     cluster are merged with a ballot loop over the distinct keys + full-mask redux (max / or), so one lane per
+//     distinct cluster issues the atomics.
 //     atomicMax / atomicOr are order-independent, so the result is deterministic; an L2 read first skips the
 //     atomic when the stored value already covers ours (same-address atomics serialise, reads do not).
 //   * compaction: ballot + CTA scan + decoupled look-back instead of atomicAdd: cluster ids come out ascending.
@@ -23,55 +24,100 @@ namespace orbit {
 
 
 // ---------------------------------------------------------------------------------------------------------
+// Merge, inside one warp, the lanes that hit the same key, with one REDUX per distinct key instead of match.any +
+// partial-mask redux (ncu: the partial-mask `__reduce_or_sync` is a ~32-instruction software loop and was the top
+// line of this kernel). Lanes with key == kNoKey take no part. fn(leader_lane_is_me, same_mask) is called by the
+// lanes of one key at a time.
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+
 __global__ void __launch_bounds__(256) mark_active_kernel(const __grid_constant__ ClusterParams p) {
     const OrbitClusterCullInfo& ci = p.info;
     const uint32_t W = ci.screen_size[0], H = ci.screen_size[1];
     const uint32_t cx = ci.cluster_count[0], cy = ci.cluster_count[1], cz = ci.cluster_count[2];
+    const uint32_t tile_px = ci.tile_size_px;
     // a warp covers 32 consecutive pixels of kRows consecutive rows per step (kRows independent loads in flight)
     constexpr uint32_t kRows = 4u;
     const uint32_t warps_per_row = (W + 31u) / 32u;
     const uint32_t row_groups = (H + kRows - 1u) / kRows;
-    const uint64_t total_warps = (uint64_t)warps_per_row * row_groups;
+    const uint32_t total_warps = warps_per_row * row_groups;   // < 2^32: screen sizes are bounded by the API
     const uint32_t lane = threadIdx.x & 31u;
-    for (uint64_t wi = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < total_warps;
-         wi += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
-        const uint32_t y0 = (uint32_t)(wi / warps_per_row) * kRows;
-        const uint32_t x = (uint32_t)(wi % warps_per_row) * 32u + lane;
+    for (uint32_t wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < total_warps; wi += gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t row_group = wi / warps_per_row;           // 32-bit: a 64-bit division here cost ~100 instructions per step
+        const uint32_t y0 = row_group * kRows;
+        const uint32_t x0 = (wi - row_group * warps_per_row) * 32u;
+        const uint32_t x = x0 + lane;
         float dv[kRows];
 #pragma unroll
         for (uint32_t k = 0; k < kRows; ++k) dv[k] = (x < W && y0 + k < H) ? __ldg(p.depth + (size_t)(y0 + k) * W + x) : 0.0f;
+        // tile column of this lane: one (warp-uniform) integer division per step instead of one per pixel
+        uint32_t tx = x0 / tile_px;
+        {
+            uint32_t t = x0 - tx * tile_px + lane;
+            if (tile_px >= 8u) { while (t >= tile_px) { t -= tile_px; ++tx; } } else { tx += t / tile_px; }
+        }
+        const uint32_t ty0 = y0 / tile_px;
+        uint32_t ry = y0 - ty0 * tile_px;   // row offset inside the tile row, advanced per k
+        uint32_t ty = ty0;
+        // ---- per-lane math for the kRows pixels of this lane's column (no warp-level operations yet)
+        uint32_t cl[kRows], tl[kRows], mk[kRows], bn[kRows], bx[kRows];
 #pragma unroll
         for (uint32_t k = 0; k < kRows; ++k) {
             const uint32_t y = y0 + k;
-            uint32_t cluster = 0xFFFFFFFFu, tile = 0xFFFFFFFFu, mask = 0u, bmin = 0u, bmax = 0u;
+            cl[k] = kNoKey; tl[k] = kNoKey; mk[k] = 0u; bn[k] = 0u; bx[k] = 0u;
             if (x < W && y < H) {
                 const float d = dv[k];
-                const uint32_t tx = x / ci.tile_size_px, ty = y / ci.tile_size_px;
-                const float z = fdiv(ci.z_near, d);
+                // sky pixels (d == +0, the clear value of the reverse-Z buffer) would send the IEEE division into its
+                // ~50-instruction slow path for the whole warp; z_near / +0 is +inf exactly when z_near > 0
+                const float z = (__float_as_uint(d) == 0u && ci.z_near > 0.0f) ? __uint_as_float(0x7F800000u) : fdiv(ci.z_near, d);
                 const uint32_t slice = f2u(fma_(orbit_log2f(z), p.z_scale, p.z_bias));
-                mask = shl1(slice);
-                if (mask != 0u) tile = tx + ty * cx;
+                mk[k] = shl1(slice);
+                if (mk[k] != 0u) tl[k] = tx + ty * cx;
                 if (slice < cz) {
-                    cluster = tx + ty * cx + slice * cx * cy;
-                    bmin = __float_as_uint(sub(1.0f, d));
-                    bmax = __float_as_uint(d);
+                    cl[k] = tx + ty * cx + slice * cx * cy;
+                    bn[k] = __float_as_uint(sub(1.0f, d));
+                    bx[k] = __float_as_uint(d);
                 }
             }
-            // merge lanes hitting the same cluster / tile
-            const uint32_t peers_c = __match_any_sync(0xFFFFFFFFu, cluster);
-            const uint32_t mn = __reduce_max_sync(peers_c, bmin);
-            const uint32_t mx = __reduce_max_sync(peers_c, bmax);
-            if (cluster != 0xFFFFFFFFu && lane == (uint32_t)(__ffs((int)peers_c) - 1)) {
-                // values only grow: a (possibly stale) read that is already >= ours makes the atomic a no-op, and
-                // plain L2 reads of one address are not serialised the way same-address atomics are
-                uint32_t* b = p.depth_bounds + 2u * (size_t)cluster;
-                if (__ldcg(b) < mn) atomicMax(b, mn);
-                if (__ldcg(b + 1) < mx) atomicMax(b + 1, mx);
+            if (++ry == tile_px) { ry = 0u; ++ty; }
+        }
+        // ---- lane-local merge: vertically adjacent pixels mostly fall into the same cluster / tile, so rows 1..3 are
+        //      folded into the first row with the same key and the warp-level merge below usually runs once, not kRows times
+#pragma unroll
+        for (uint32_t k = 1; k < kRows; ++k) {
+#pragma unroll
+            for (uint32_t j = 0; j < k; ++j) {
+                if (cl[k] != kNoKey && cl[k] == cl[j]) { bn[j] = max(bn[j], bn[k]); bx[j] = max(bx[j], bx[k]); cl[k] = kNoKey; }
+                if (tl[k] != kNoKey && tl[k] == tl[j]) { mk[j] |= mk[k]; tl[k] = kNoKey; }
             }
-            const uint32_t peers_t = __match_any_sync(0xFFFFFFFFu, tile);
-            const uint32_t orm = __reduce_or_sync(peers_t, mask);
-            if (tile != 0xFFFFFFFFu && lane == (uint32_t)(__ffs((int)peers_t) - 1) && (__ldcg(p.tile_masks + tile) & orm) != orm)
-                atomicOr(p.tile_masks + tile, orm);
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < kRows; ++k) {
+            // ---- cluster depth bounds: one pair of atomics per distinct cluster of the warp
+            uint32_t todo = __ballot_sync(0xFFFFFFFFu, cl[k] != kNoKey);
+            while (todo) {
+                const uint32_t key = __shfl_sync(0xFFFFFFFFu, cl[k], __ffs((int)todo) - 1);
+                const bool mine = cl[k] == key;
+                const uint32_t same = __ballot_sync(0xFFFFFFFFu, mine);
+                const uint32_t mn = __reduce_max_sync(0xFFFFFFFFu, mine ? bn[k] : 0u);
+                const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, mine ? bx[k] : 0u);
+                if (lane == (uint32_t)(__ffs((int)same) - 1)) {
+                    // values only grow: a (possibly stale) read that is already >= ours makes the atomic a no-op
+                    uint32_t* b = p.depth_bounds + 2u * (size_t)key;
+                    if (__ldcg(b) < mn) atomicMax(b, mn);
+                    if (__ldcg(b + 1) < mx) atomicMax(b + 1, mx);
+                }
+                todo &= ~same;
+            }
+            // ---- tile slice masks: one atomicOr per distinct tile of the warp
+            todo = __ballot_sync(0xFFFFFFFFu, tl[k] != kNoKey);
+            while (todo) {
+                const uint32_t key = __shfl_sync(0xFFFFFFFFu, tl[k], __ffs((int)todo) - 1);
+                const bool mine = tl[k] == key;
+                const uint32_t same = __ballot_sync(0xFFFFFFFFu, mine);
+                const uint32_t orm = __reduce_or_sync(0xFFFFFFFFu, mine ? mk[k] : 0u);
+                if (lane == (uint32_t)(__ffs((int)same) - 1) && (__ldcg(p.tile_masks + key) & orm) != orm) atomicOr(p.tile_masks + key, orm);
+                todo &= ~same;
+            }
         }
     }
 }
@@ -230,9 +276,11 @@ __global__ void __launch_bounds__(kLcWarps * 32) light_culling_kernel(const __gr
                     const float c[3] = {s.x, s.y, s.z};
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
+                        // lo <= hi, so at most one of the reference's two branches adds a term; d is that term's
+                        // base (or 0, and fma(0,0,acc) == acc): same value, no divergence
                         const float v = c[k];
-                        if (v < box.lo[k]) { const float t = sub(box.lo[k], v); acc = fma_(t, t, acc); }
-                        if (v > box.hi[k]) { const float t = sub(v, box.hi[k]); acc = fma_(t, t, acc); }
+                        const float d = fmaxf(fmaxf(sub(box.lo[k], v), sub(v, box.hi[k])), 0.0f);
+                        acc = fma_(d, d, acc);
                     }
                     hit = acc <= mul(s.w, s.w);
                 }
