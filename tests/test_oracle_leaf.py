@@ -112,3 +112,71 @@ def test_cone_cull_matches_float64(oracle):
         n_checked += 1
         assert bool(lib.oracle_cone_cull(*[C.c_float(v) for v in (*c, r, *a, cut)])) == (lhs >= rhs)
     assert n_checked > 3000
+
+
+def _rust_twin_project_sphere_clip_space(c, r, znear, p00, p11):
+    """numpy float32 restatement of the reference's OWN CPU twin of the shader math, math::project_sphere_clip_space
+    (src/math.rs:170-199; Rust f32 arithmetic is unfused). Returns None or the clip-space aabb (minx, miny, maxx, maxy)."""
+    f = np.float32
+    cx_, cy_, cz_ = f(c[0]), f(c[1]), f(c[2]); r = f(r)
+    if cz_ < f(r + f(znear)):
+        return None
+    def axis(a):
+        c0, c1 = f(-a), f(-cz_)
+        v0 = f(np.sqrt(f(f(f(c0 * c0) + f(c1 * c1)) - f(r * r)))); v1 = r
+        mn = (f(f(v0 * c0) + f(f(-v1) * c1)), f(f(v1 * c0) + f(v0 * c1)))
+        mx = (f(f(v0 * c0) + f(v1 * c1)), f(f(f(-v1) * c0) + f(v0 * c1)))
+        return mn, mx
+    (minx, maxx), (miny, maxy) = axis(cx_), axis(cy_)
+    return (f(f(minx[0] / minx[1]) * f(p00)), f(f(miny[0] / miny[1]) * f(p11)), f(f(maxx[0] / maxx[1]) * f(p00)), f(f(maxy[0] / maxy[1]) * f(p11)))
+
+
+def test_project_sphere_against_reference_cpu_twin(oracle):
+    """The only independent restatement of the projection inside the reference: agree within the north star's 1e-5
+    (the shader path has Fma where the Rust twin has separate ops, so not bit-for-bit)."""
+    lib = oracle.lib()
+    lib.oracle_project_sphere.argtypes = [C.c_float] * 8 + [C.POINTER(C.c_float)]
+    rng = np.random.default_rng(21)
+    out = (C.c_float * 6)()
+    n_some = n_none = 0
+    for _ in range(3000):
+        c = rng.uniform([-30, -30, 0.05], [30, 30, 200]); r = rng.uniform(0.05, 3.0)
+        twin = _rust_twin_project_sphere_clip_space(c, r, 0.01, 0.5625, 1.0)
+        # the shader negates view-space z before calling project_sphere: pass z_view = -c.z
+        lib.oracle_project_sphere(C.c_float(c[0]), C.c_float(c[1]), C.c_float(-c[2]), C.c_float(r), C.c_float(1.0), C.c_float(0.01),
+                                  C.c_float(0.5625), C.c_float(1.0), out)
+        margin = abs(c[2] - (r + 0.01))
+        if margin > 1e-4 * max(c[2], 1.0):
+            assert (twin is not None) == (out[5] == 1.0)
+        if twin is None:
+            n_none += 1
+            continue
+        n_some += 1
+        uv = np.array([twin[0] * 0.5 + 0.5, twin[3] * -0.5 + 0.5, twin[2] * 0.5 + 0.5, twin[1] * -0.5 + 0.5], np.float64)
+        got = np.array(list(out)[:4], np.float64)
+        assert np.allclose(got, uv, rtol=1e-5, atol=1e-5), (c, r, got, uv)
+    assert n_some > 1000 and n_none > 10
+
+
+def test_orthographic_box_against_shadow_renderer_twin(oracle):
+    """shadow_renderer.rs:593-604 restates the ortho screen box + depth on the CPU (with width AND height recip,
+    where the shader uses p00 for both — entity_cull.comp:166; equal for the square cascades the reference renders)."""
+    from orbit_b200 import layouts as L
+    import oracle_ref
+    f = np.float32
+    rng = np.random.default_rng(5)
+    sc, _ = scenes.config_c1(scale=0.1)
+    view = scenes.orthographic_view((0, 50, 0), (0.3, -1.0, 0.2), 2048, 2048, half_width=40.0, near=-20.0, far=150.0)
+    g = oracle_ref.gpu_cull_info(view, "write")
+    wr2 = f(g.p00_or_width_recip_x2)
+    assert abs(wr2 - 2.0 / 80.0) < 1e-7 and g.p11_or_height_recip_x2 == g.p00_or_width_recip_x2
+    for _ in range(200):
+        cx, cy, cz, r = rng.uniform(-60, 60), rng.uniform(-60, 60), rng.uniform(-140, 10), rng.uniform(0.1, 5)
+        centre = (f(wr2 * f(cx)), f(wr2 * f(cy))); box = f(f(r) * wr2)
+        aabb = np.clip([centre[0] - box, centre[1] - box, centre[0] + box, centre[1] + box], -1, 1)
+        rr = f(1.0) / f(f(g.z_far) - f(g.z_near))
+        depth_twin = f(f(f(cz) + f(r)) * rr) + f(rr * f(g.z_far))
+        # oracle formula (SPIR-V): k * (fma(r_model, s, z) + z_far), s = 1
+        depth_oracle = rr * f(f(np.float64(r) * 1.0 + np.float64(cz)) + f(g.z_far))
+        assert abs(float(depth_twin) - float(depth_oracle)) <= 1e-5 * max(abs(float(depth_twin)), 1e-3)
+        assert np.all(aabb >= -1) and np.all(aabb <= 1)
