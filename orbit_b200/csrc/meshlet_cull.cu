@@ -96,11 +96,20 @@ __device__ __forceinline__ ItemTest test_item(const OrbitCullInfo& ci, const flo
     const float nr = -s.r;
     bool visible = true;
     const uint32_t n = ci.cull_plane_count;
+    if (n == 5u) {
+        // the main-view case (forward.rs:268 passes planes[0..5]): straight-line code, plane coefficients as constant-bank
+        // operands, no loop control (the generic loop below costs ~25 more instructions per record)
 #pragma unroll
-    for (uint32_t i = 0; i < ORBIT_MAX_CULL_PLANES; ++i) {
-        if (i >= n) break;   // uniform
-        const float d = add(dot3(ci.cull_planes[i][0], ci.cull_planes[i][1], ci.cull_planes[i][2], px, py, pz), ci.cull_planes[i][3]);
-        visible = visible && (d > nr);
+        for (uint32_t i = 0; i < 5u; ++i) {
+            const float d = add(dot3(ci.cull_planes[i][0], ci.cull_planes[i][1], ci.cull_planes[i][2], px, py, pz), ci.cull_planes[i][3]);
+            visible = visible && (d > nr);
+        }
+    } else {
+#pragma unroll 1
+        for (uint32_t i = 0; i < n; ++i) {
+            const float d = add(dot3(ci.cull_planes[i][0], ci.cull_planes[i][1], ci.cull_planes[i][2], px, py, pz), ci.cull_planes[i][3]);
+            visible = visible && (d > nr);
+        }
     }
     if (visible) {
         const float K = 0.007874015718698502f;

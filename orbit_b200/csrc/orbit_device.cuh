@@ -16,12 +16,23 @@ namespace orbit {
 
 #define ORBIT_DEV __device__ __forceinline__
 
+#ifndef ORBIT_EXPERIMENT_FAST_MATH
 ORBIT_DEV float mul(float a, float b) { return __fmul_rn(a, b); }
 ORBIT_DEV float add(float a, float b) { return __fadd_rn(a, b); }
 ORBIT_DEV float sub(float a, float b) { return __fsub_rn(a, b); }
 ORBIT_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 ORBIT_DEV float fsqrt(float a) { return __fsqrt_rn(a); }
 ORBIT_DEV float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
+// EXPERIMENT ONLY (never shipped, results are NOT bit-exact): contraction allowed, approximate division and square
+// root — used once to measure what the pinned arithmetic contract costs (profiles/r1_contract_cost.txt).
+ORBIT_DEV float mul(float a, float b) { return a * b; }
+ORBIT_DEV float add(float a, float b) { return a + b; }
+ORBIT_DEV float sub(float a, float b) { return a - b; }
+ORBIT_DEV float fdiv(float a, float b) { return __fdividef(a, b); }
+ORBIT_DEV float fsqrt(float a) { return __frsqrt_rn(a) * a; }
+ORBIT_DEV float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
 
 ORBIT_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz) {
     return add(add(mul(ax, bx), mul(ay, by)), mul(az, bz));
