@@ -24,6 +24,10 @@
  *     commands by (dispatch record index, lane), compacted clusters and light indices ascending.  The
  *     reference appends with atomicAdd (entity_cull.comp:211, meshlet_cull.comp:228), i.e. in arbitrary
  *     order; any order is valid for its consumers, so a fixed one is a drop-in.
+ *   - scratch grows on the first call that needs more than the context has seen so far (larger capacity_records,
+ *     more clusters, more lights); growing synchronises the device once, so warm a context up with its real
+ *     capacities before capturing calls into a CUDA graph. Captured calls are replay-safe: scan epochs, tickets and
+ *     scratch parities live in device memory, never in kernel parameters.
  *   - there is no CPU fallback: without a CUDA device every entry point that needs one fails.
  */
 #ifndef ORBIT_CUDA_H
