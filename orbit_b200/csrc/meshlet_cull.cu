@@ -213,6 +213,15 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
     WarpSmem<R>& ws = all[warp];
     const OrbitCullInfo& ci = p.cull;
     pdl_wait();
+    // The record words of this warp's first two tiles are requested BEFORE the record count is known (bounded by the
+    // dispatch buffer's capacity, masked by the count afterwards): one dependent round trip less in the prologue.
+    uint32_t spec_word0 = 0u, spec_word1 = 0u;
+    {
+        const uint32_t t0 = blockIdx.x * kMcWarps + warp, t1 = t0 + gridDim.x * kMcWarps;
+        const uint64_t ra = (uint64_t)t0 * R + (lane >> 2), rb = (uint64_t)t1 * R + (lane >> 2);
+        if (lane < 4u * R && ra < p.capacity_records) spec_word0 = __ldcg(p.dispatch_words + 3u + (size_t)t0 * R * 4u + lane);
+        if (lane < 4u * R && rb < p.capacity_records) spec_word1 = __ldcg(p.dispatch_words + 3u + (size_t)t1 * R * 4u + lane);
+    }
     uint32_t nrec = __ldcg(p.dispatch_words);  // workgroup_count_x written by the entity stage
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
     const uint32_t chunk_rec = chunk_records(nrec);
@@ -261,8 +270,12 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
     };
 
     uint32_t warp_total = 0u;   // survivors found by this warp (lets the emit kernel skip everything when zero)
-    uint32_t cur_word = load_words(w_t0);
-    uint32_t next_word = load_words(w_t0 + w_stride);
+    uint32_t cur_word = spec_word0, next_word = spec_word1;
+    {   // the two speculative loads were bounded by the buffer capacity; now apply the real record count
+        const uint32_t rec_a = w_t0 * R + (lane >> 2), rec_b = (w_t0 + w_stride) * R + (lane >> 2);
+        if (!(lane < 4u * R && rec_a < nrec)) cur_word = 0u;
+        if (!(lane < 4u * R && rec_b < nrec)) next_word = 0u;
+    }
     if (w_t0 < w_t1) issue_tma(cur_word);
     uint32_t qhead = 0u;   // ring-buffer read position (entries [qhead, qhead+qn) mod 64 are pending)
     for (uint32_t tile = w_t0; tile < w_t1; tile += w_stride) {
