@@ -31,6 +31,10 @@ def time_frame(ctx, copies, reps=7, per_graph=8):
         _, disp = create_meshlet_dispatch_command(ctx, "p0_%d" % i, pf.dscene.assets, pf.dscene.scene, ci)
         p0.append((ci, disp))
     stages["meshlet_pass0"] = lambda pf, s: create_meshlet_draw_commands(ctx, "p0_%d" % copies.index(pf), pf.dscene.assets, pf.dscene.scene, p0[copies.index(pf)][0], p0[copies.index(pf)][1])
+    # the same sweep with the mesh-shading output as well (forward_depth_prepass.task:224-256): 44 B per record
+    tp = [torch.zeros(44 * int(pf.dscene.scene.record_capacity), dtype=torch.uint8, device=ctx.device) for pf in copies]
+    stages["meshlet_pass0_task_payloads"] = lambda pf, s: create_meshlet_draw_commands(
+        ctx, "p0_%d" % copies.index(pf), pf.dscene.assets, pf.dscene.scene, p0[copies.index(pf)][0], p0[copies.index(pf)][1], tp[copies.index(pf)])
     out = {}
     for name, fn in stages.items():
         for pf in copies:          # consistent steady-state inputs for every stage
