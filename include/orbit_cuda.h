@@ -59,7 +59,8 @@ typedef struct OrbitStatus {
     uint32_t dispatch_overflow;   /* entity stage produced more records than capacity_records (extra dropped) */
     uint32_t draw_overflow;       /* meshlet stage produced more draws than capacity_draws (extra dropped)    */
     uint32_t light_index_overflow;/* light lists exceeded capacity_indices (extra dropped)                    */
-    uint32_t reserved;
+    uint32_t visibility_overflow; /* scene update needed more visibility words than the buffer holds (the reference
+                                     panics here: scene.rs:427 `.unwrap()`)                                   */
 } OrbitStatus;
 
 /* Device pointers to the long-lived scene / asset arrays the culling path reads.
@@ -151,6 +152,28 @@ int orbit_light_cluster(orbit_ctx* ctx, const OrbitClusterParams* params, const 
                         const void* lights, void* tile_masks, void* depth_bounds, void* unique_clusters,
                         void* offset_count_image, void* light_index_list, uint64_t capacity_indices,
                         void* stream);
+
+/* ---- SceneData::update_scene (scene.rs:404-492), the per-frame producer of the entity buffers the culling path
+ *      reads. For every entity with a mesh, in entity order: instance_index = running count,
+ *      GpuEntityData {model_matrix = Mat4::from_scale_rotation_translation(scale, orientation, position),
+ *      normal_matrix = Mat4::from_mat3(Mat3::from_mat4(model.inverse().transpose()))} (scene.rs:69-76),
+ *      GpuEntityDraw {instance_index, mesh.slot(), visibility_offset}; an entity without a visibility range gets
+ *      ceil(lod0 meshlet_count / 32) words from the allocator (scene.rs:422-431). The reference's
+ *      FreeListAllocator hands out consecutive ranges as long as nothing was freed (collections/freelist_alloc.rs:
+ *      40-72), which is what this entry point implements: an exclusive prefix sum over the entities that need a
+ *      range, starting at *visibility_cursor. Lights and deallocation stay host bookkeeping. ---------------------- */
+typedef struct OrbitSceneUpdate {
+    const OrbitTransform* transforms;        /* [n_entities] device                                              */
+    const uint32_t* mesh_slots;              /* [n_entities] device; ORBIT_NO_MESH = no mesh                     */
+    uint32_t*       visibility_offsets;      /* [n_entities] device, in/out; ORBIT_NO_VISIBILITY_RANGE = none yet */
+    const void*     mesh_infos;              /* OrbitMeshInfo[] device                                           */
+    uint32_t*       visibility_cursor;       /* device word, in/out: first unallocated visibility word           */
+    uint32_t        n_entities;
+    uint32_t        visibility_capacity_words; /* MESHLET_VISIBILITY_BUFFER_CHUNK_COUNT (scene.rs:392)           */
+    void*           entity_data;             /* out: OrbitEntityData[>= n_entities] device                       */
+    void*           entity_draws;            /* out: EntityDrawBuffer (u32 count @0, OrbitEntityDraw[] @4)       */
+} OrbitSceneUpdate;
+int orbit_scene_update(orbit_ctx* ctx, const OrbitSceneUpdate* update, void* stream);
 
 /* ---- multi-GPU helper (no reference counterpart) --------------------------------------------- */
 /* Appends `count` draw commands read from src (a MeshletDrawCommandBuffer, device-side count honoured) into

@@ -101,6 +101,20 @@ typedef struct OrbitEntityData {
 } OrbitEntityData;
 ORBIT_STATIC_ASSERT(sizeof(OrbitEntityData) == 128, "GpuEntityData is 128 bytes");
 
+/* Transform (src/scene.rs:18-23: position Vec3, orientation Quat, scale Vec3). The reference's struct is a plain
+ * Rust struct without a defined byte layout; this is the layout the scene-update entry point reads: three 16-byte
+ * rows so that one entity is three aligned vector loads. */
+typedef struct OrbitTransform {
+    float position[3];    /*  0 */
+    float _pad0;
+    float orientation[4]; /* 16  x, y, z, w (glam Quat memory order) */
+    float scale[3];       /* 32 */
+    float _pad1;
+} OrbitTransform;
+ORBIT_STATIC_ASSERT(sizeof(OrbitTransform) == 48, "OrbitTransform is 48 bytes");
+#define ORBIT_NO_MESH 0xFFFFFFFFu        /* EntityData::mesh == None (scene.rs:63) */
+#define ORBIT_NO_VISIBILITY_RANGE 0xFFFFFFFFu /* EntityData::visibility_buffer_range == None (scene.rs:65) */
+
 typedef struct OrbitEntityDraw {
     uint32_t entity_index;
     uint32_t mesh_index;

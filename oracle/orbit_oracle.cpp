@@ -642,4 +642,93 @@ uint64_t oracle_light_culling(const OrbitClusterParams* p, const void* lights_, 
     return total;
 }
 
+// ---- SceneData::update_scene (src/scene.rs:404-492) --------------------------------------------------------
+// glam 0.24 (Cargo.toml:24; NOT vendored in /root/reference — restated from its published source, x86_64/SSE2
+// build, no FMA contraction):
+//   Mat4::from_scale_rotation_translation = quat_to_axes (x2=x+x .. wz=w*z2; x_axis = (1-(yy+zz), xy+wz, xz-wy, 0) ..)
+//     with each axis multiplied by the matching scale component, w_axis = (translation, 1);
+//   Mat4::inverse = the GLM cofactor scheme: 18 2x2 sub-determinants a*b - c*d, inv_k = (v*f - v*f) + v*f with the
+//     checkerboard sign, determinant = dot(x_axis, first row of the adjugate) summed as (x+z)+(y+w) (SSE2 dot4),
+//     rcp = 1/det, every element multiplied by rcp.
+// PARITY UNPINNED: glam itself cannot be run here; the model matrix is plain enough to be safe, the rounding of
+// the normal matrix (never read by the culling path) depends on the summation order assumed above.
+static void glam_from_srt(const float* pos, const float* q, const float* scl, float m[16]) {
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    const float x2 = x + x, y2 = y + y, z2 = z + z;
+    const float xx = x * x2, xy = x * y2, xz = x * z2, yy = y * y2, yz = y * z2, zz = z * z2;
+    const float wx = w * x2, wy = w * y2, wz = w * z2;
+    const float ax[3] = {1.0f - (yy + zz), xy + wz, xz - wy};
+    const float ay[3] = {xy - wz, 1.0f - (xx + zz), yz + wx};
+    const float az[3] = {xz + wy, yz - wx, 1.0f - (xx + yy)};
+    for (int i = 0; i < 3; ++i) { m[i] = ax[i] * scl[0]; m[4 + i] = ay[i] * scl[1]; m[8 + i] = az[i] * scl[2]; m[12 + i] = pos[i]; }
+    m[3] = 0.0f * scl[0]; m[7] = 0.0f * scl[1]; m[11] = 0.0f * scl[2]; m[15] = 1.0f;   // Vec4 * f32 multiplies the 0 lane too
+}
+
+static void glam_inverse(const float m[16], float out[16]) {
+    const float m00 = m[0], m01 = m[1], m02 = m[2], m03 = m[3], m10 = m[4], m11 = m[5], m12 = m[6], m13 = m[7];
+    const float m20 = m[8], m21 = m[9], m22 = m[10], m23 = m[11], m30 = m[12], m31 = m[13], m32 = m[14], m33 = m[15];
+    const float c00 = m22 * m33 - m32 * m23, c02 = m12 * m33 - m32 * m13, c03 = m12 * m23 - m22 * m13;
+    const float c04 = m21 * m33 - m31 * m23, c06 = m11 * m33 - m31 * m13, c07 = m11 * m23 - m21 * m13;
+    const float c08 = m21 * m32 - m31 * m22, c10 = m11 * m32 - m31 * m12, c11 = m11 * m22 - m21 * m12;
+    const float c12 = m20 * m33 - m30 * m23, c14 = m10 * m33 - m30 * m13, c15 = m10 * m23 - m20 * m13;
+    const float c16 = m20 * m32 - m30 * m22, c18 = m10 * m32 - m30 * m12, c19 = m10 * m22 - m20 * m12;
+    const float c20 = m20 * m31 - m30 * m21, c22 = m10 * m31 - m30 * m11, c23 = m10 * m21 - m20 * m11;
+    const float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+    const float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+    const float v0[4] = {m10, m00, m00, m00}, v1[4] = {m11, m01, m01, m01}, v2[4] = {m12, m02, m02, m02}, v3[4] = {m13, m03, m03, m03};
+    float inv[16];
+    for (int k = 0; k < 4; ++k) {
+        const float sa = (k & 1) ? -1.0f : 1.0f, sb = -sa;
+        inv[k]      = ((v1[k] * f0[k] - v2[k] * f1[k]) + v3[k] * f2[k]) * sa;
+        inv[4 + k]  = ((v0[k] * f0[k] - v2[k] * f3[k]) + v3[k] * f4[k]) * sb;
+        inv[8 + k]  = ((v0[k] * f1[k] - v1[k] * f3[k]) + v3[k] * f5[k]) * sa;
+        inv[12 + k] = ((v0[k] * f2[k] - v1[k] * f4[k]) + v2[k] * f5[k]) * sb;
+    }
+    const float d0 = m00 * inv[0], d1 = m01 * inv[4], d2 = m02 * inv[8], d3 = m03 * inv[12];
+    const float det = (d0 + d2) + (d1 + d3);
+    const float rcp = 1.0f / det;
+    for (int i = 0; i < 16; ++i) out[i] = inv[i] * rcp;
+}
+
+// transforms: 12 floats per entity (OrbitTransform). Returns 1 when the visibility buffer overflowed.
+int oracle_scene_update(const float* transforms, const uint32_t* mesh_slots, uint32_t* visibility_offsets, const void* mesh_infos_,
+                        uint32_t* visibility_cursor, uint32_t n_entities, uint32_t visibility_capacity_words,
+                        void* entity_data_, void* entity_draws_) {
+    const OrbitMeshInfo* mesh_infos = (const OrbitMeshInfo*)mesh_infos_;
+    float* entity_data = (float*)entity_data_;
+    uint32_t* draw_words = (uint32_t*)entity_draws_;
+    uint32_t count = 0;
+    uint64_t cursor = *visibility_cursor;
+    int overflow = 0;
+    for (uint32_t e = 0; e < n_entities; ++e) {              // scene.rs:419
+        const uint32_t slot = mesh_slots[e];
+        if (slot == ORBIT_NO_MESH) continue;
+        uint32_t vo = visibility_offsets[e];
+        if (vo == ORBIT_NO_VISIBILITY_RANGE) {               // scene.rs:424-431; allocator without frees = bump pointer
+            const uint32_t mc = mesh_infos[slot].mesh_lods[0].meshlet_count;
+            const uint32_t words = (mc >> 5) + ((mc & 31u) ? 1u : 0u);
+            vo = (uint32_t)cursor;
+            cursor += words;
+            if (cursor > visibility_capacity_words) overflow = 1;
+            visibility_offsets[e] = vo;
+        }
+        const float* t = transforms + (size_t)e * 12;
+        float model[16], inv[16];
+        glam_from_srt(t, t + 4, t + 8, model);
+        glam_inverse(model, inv);
+        float* out = entity_data + (size_t)count * 32;
+        std::memcpy(out, model, 64);
+        float* nm = out + 16;                                // from_mat3(from_mat4(inverse.transpose()))
+        for (int c = 0; c < 3; ++c) { for (int r = 0; r < 3; ++r) nm[c * 4 + r] = inv[r * 4 + c]; nm[c * 4 + 3] = 0.0f; }
+        nm[12] = 0.0f; nm[13] = 0.0f; nm[14] = 0.0f; nm[15] = 1.0f;
+        draw_words[1 + 3 * (size_t)count + 0] = count;       // instance_index
+        draw_words[1 + 3 * (size_t)count + 1] = slot;
+        draw_words[1 + 3 * (size_t)count + 2] = vo;
+        ++count;
+    }
+    draw_words[0] = count;
+    *visibility_cursor = (uint32_t)cursor;
+    return overflow;
+}
+
 }  // extern "C"

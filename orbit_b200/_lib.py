@@ -33,6 +33,7 @@ PROTOTYPES = {
                                      C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "orbit_light_cluster": (C.c_int, [C.c_void_p, C.POINTER(L.ClusterParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "orbit_scene_update": (C.c_int, [C.c_void_p, C.POINTER(L.SceneUpdate), C.c_void_p]),
     "orbit_draws_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
                                       C.c_void_p]),
     "orbit_peer_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liborbit_b200.so")
-SOURCES = ["api.cu", "hiz_build.cu", "entity_cull.cu", "meshlet_cull.cu", "light_cluster.cu"]
+SOURCES = ["api.cu", "hiz_build.cu", "entity_cull.cu", "meshlet_cull.cu", "light_cluster.cu", "scene_update.cu"]
 HEADERS = ["orbit_device.cuh", "scan.cuh", "params.cuh", "../../include/orbit_cuda.h", "../../include/orbit_layouts.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -42,6 +42,9 @@ struct orbit_ctx {
     // meshlet stage scratch: one draw mask per dispatch record
     uint4* draw_masks = nullptr;
     size_t draw_mask_capacity = 0;
+    // scene-update scratch: per-tile sums (kept apart from `status`, whose words carry scan epochs)
+    unsigned long long* tile_sums = nullptr;
+    size_t tile_sums_capacity = 0;
     // light scratch
     float4* light_view = nullptr;
     size_t light_capacity = 0;
@@ -70,6 +73,16 @@ static int ensure_status(orbit_ctx* c, size_t tiles) {
     CK(cudaMalloc(&c->status, cap * sizeof(unsigned long long)));
     CK(cudaMemset(c->status, 0, cap * sizeof(unsigned long long)));
     c->status_capacity = cap;
+    return ORBIT_OK;
+}
+
+static int ensure_tile_sums(orbit_ctx* c, size_t tiles) {
+    if (tiles <= c->tile_sums_capacity) return ORBIT_OK;
+    size_t cap = c->tile_sums_capacity ? c->tile_sums_capacity : 1024;
+    while (cap < tiles) cap *= 2;
+    if (c->tile_sums) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->tile_sums)); c->tile_sums = nullptr; c->tile_sums_capacity = 0; }
+    CK(cudaMalloc(&c->tile_sums, cap * sizeof(unsigned long long)));
+    c->tile_sums_capacity = cap;
     return ORBIT_OK;
 }
 
@@ -141,7 +154,7 @@ void orbit_ctx_destroy(orbit_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->draw_masks); cudaFree(c->chunk_counts);
+    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->draw_masks); cudaFree(c->chunk_counts); cudaFree(c->tile_sums);
     cudaFreeHost(c->status_host);
     delete c;
 }
@@ -150,7 +163,7 @@ int orbit_ctx_poll_status(orbit_ctx* c, OrbitStatus* out) {
     if (!c || !out) return ORBIT_ERR_INVALID_ARGUMENT;
     *out = *c->status_host;
     std::memset(c->status_host, 0, sizeof(OrbitStatus));
-    return (out->dispatch_overflow || out->draw_overflow || out->light_index_overflow) ? ORBIT_ERR_CAPACITY : ORBIT_OK;
+    return (out->dispatch_overflow || out->draw_overflow || out->light_index_overflow || out->visibility_overflow) ? ORBIT_ERR_CAPACITY : ORBIT_OK;
 }
 
 uint64_t orbit_ctx_launch_count(const orbit_ctx* c) { return c ? c->launches.load() : 0; }
@@ -381,6 +394,31 @@ int orbit_draws_scatter(orbit_ctx* c, const void* src, void* dst, uint32_t dst_f
     CK(launch_draws_scatter((const uint32_t*)src, (uint32_t*)dst, dst_first, total_count, dst_capacity_draws,
                             c->sm_count * 16, (cudaStream_t)stream));
     c->launches += 1;
+    return ORBIT_OK;
+}
+
+int orbit_scene_update(orbit_ctx* c, const OrbitSceneUpdate* u, void* stream) {
+    if (!c || !u) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (!u->entity_draws) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (u->n_entities == 0u) {   // empty scene: only the count header is produced
+        CK(cudaMemsetAsync(u->entity_draws, 0, 4, (cudaStream_t)stream));
+        return ORBIT_OK;
+    }
+    if (!u->transforms || !u->mesh_slots || !u->visibility_offsets || !u->mesh_infos || !u->visibility_cursor || !u->entity_data)
+        return ORBIT_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)u->transforms | (uintptr_t)u->entity_data) & 15u) return ORBIT_ERR_INVALID_ARGUMENT;
+    const size_t tiles = ((size_t)u->n_entities + 255u) / 256u;
+    int rc = ensure_tile_sums(c, tiles);
+    if (rc != ORBIT_OK) return rc;
+    SceneUpdateParams p{};
+    p.transforms = (const uint8_t*)u->transforms; p.mesh_slots = u->mesh_slots; p.visibility_offsets = u->visibility_offsets;
+    p.mesh_infos = (const uint8_t*)u->mesh_infos; p.visibility_cursor = u->visibility_cursor;
+    p.cursor_snapshot = c->counters + 8; p.tile_sums = c->tile_sums;
+    p.entity_data = (float4*)u->entity_data; p.entity_draw_words = (uint32_t*)u->entity_draws;
+    p.overflow_flag = &c->status_dev->visibility_overflow;
+    p.n_entities = u->n_entities; p.visibility_capacity_words = u->visibility_capacity_words;
+    CK(launch_scene_update(p, (cudaStream_t)stream));
+    c->launches += 2;
     return ORBIT_OK;
 }
 

@@ -54,6 +54,20 @@ struct EntityCullParams {
     ScanState scan;
 };
 
+struct SceneUpdateParams {
+    const uint8_t* transforms;           // OrbitTransform[], 48 B each
+    const uint32_t* mesh_slots;
+    uint32_t* visibility_offsets;
+    const uint8_t* mesh_infos;           // 128 B each
+    uint32_t* visibility_cursor;
+    uint32_t* cursor_snapshot;           // scratch word: cursor value at the start of the update
+    unsigned long long* tile_sums;       // scratch: per 256-entity tile, meshed count | visibility words << 32
+    float4* entity_data;                 // out, 8 x float4 per instance
+    uint32_t* entity_draw_words;         // out, EntityDrawBuffer as u32[]
+    uint32_t* overflow_flag;             // host-mapped status word
+    uint32_t n_entities, visibility_capacity_words;
+};
+
 struct HizBuildParams {
     const float* depth;
     float* texels;
@@ -87,6 +101,7 @@ int meshlet_cull_tile_records(int recs_per_warp);
 cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t);
 int entity_cull_max_ctas_per_sm();
 cudaError_t launch_hiz_build(const HizBuildParams&, cudaStream_t);
+cudaError_t launch_scene_update(const SceneUpdateParams&, cudaStream_t);
 cudaError_t launch_mark_active(const ClusterParams&, int grid, cudaStream_t);
 cudaError_t launch_compact_clusters(const ClusterParams&, cudaStream_t);
 cudaError_t launch_light_view(const ClusterParams&, cudaStream_t);

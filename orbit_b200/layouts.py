@@ -49,6 +49,12 @@ light_dtype = np.dtype([
     ("light_type", "<u4"), ("shadow_data_index", "<u4"), ("irradiance_map", "<u4"), ("prefiltered_map", "<u4"),
     ("color", "<f4", (3,)), ("intensity", "<f4"), ("position", "<f4", (3,)), ("inner_radius", "<f4"),
     ("direction", "<f4", (3,)), ("outer_radius", "<f4")])
+# Transform (scene.rs:18-23) in the 48-byte layout orbit_scene_update reads (include/orbit_layouts.h OrbitTransform)
+transform_dtype = np.dtype([("position", "<f4", (3,)), ("_pad0", "<f4"), ("orientation", "<f4", (4,)),
+                            ("scale", "<f4", (3,)), ("_pad1", "<f4")])
+NO_MESH = 0xFFFFFFFF
+NO_VISIBILITY_RANGE = 0xFFFFFFFF
+assert transform_dtype.itemsize == 48
 assert meshlet_dtype.itemsize == 32 and mesh_info_dtype.itemsize == 128 and entity_dtype.itemsize == 128
 assert entity_draw_dtype.itemsize == 12 and dispatch_dtype.itemsize == 16 and draw_command_dtype.itemsize == 28
 assert task_payload_dtype.itemsize == 44 and light_dtype.itemsize == 64
@@ -116,8 +122,16 @@ class ClusterParams(C.Structure):
 
 class Status(C.Structure):
     _fields_ = [("dispatch_overflow", C.c_uint32), ("draw_overflow", C.c_uint32), ("light_index_overflow", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("visibility_overflow", C.c_uint32)]
 
 
+class SceneUpdate(C.Structure):
+    """OrbitSceneUpdate (include/orbit_cuda.h): arguments of orbit_scene_update (scene.rs:404-492)."""
+    _fields_ = [("transforms", C.c_void_p), ("mesh_slots", C.c_void_p), ("visibility_offsets", C.c_void_p),
+                ("mesh_infos", C.c_void_p), ("visibility_cursor", C.c_void_p), ("n_entities", C.c_uint32),
+                ("visibility_capacity_words", C.c_uint32), ("entity_data", C.c_void_p), ("entity_draws", C.c_void_p)]
+
+
+assert C.sizeof(SceneUpdate) == 64
 assert C.sizeof(CullInfo) == 400 and C.sizeof(ClusterCullInfo) == 192 and C.sizeof(ClusterParams) == 208
 assert C.sizeof(SceneBuffers) == 72

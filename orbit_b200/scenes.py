@@ -136,6 +136,7 @@ class Scene:
     entity_pos: np.ndarray = field(default=None, repr=False)     # float64 [N,3] world centre of the bounding sphere
     entity_radius: np.ndarray = field(default=None, repr=False)  # float64 [N] world radius
     entity_occluder: np.ndarray = field(default=None, repr=False)  # float64 [N] world radius of the depth-splat disc
+    transforms: np.ndarray = field(default=None, repr=False)     # layouts.transform_dtype [N]: what scene.rs:404-492 starts from
 
     @property
     def draws(self):
@@ -281,6 +282,11 @@ def make_scene(name, seed, n_entities, n_meshes, lod_meshlets, layout="city", gr
     entity_draws[:4] = np.frombuffer(np.uint32(N).tobytes(), np.uint8)
     entity_draws[4:] = draws.view(np.uint8)
 
+    transforms = np.zeros(N, L.transform_dtype)   # the Transform each model matrix came from (input of orbit_scene_update)
+    transforms["position"] = T.astype(np.float32)
+    transforms["orientation"] = q.astype(np.float32)
+    transforms["scale"] = scale.astype(np.float32)[:, None]
+
     centre_local = np.stack([np.zeros(N), centre_y[mesh_index], np.zeros(N)], axis=1)
     entity_pos = np.einsum("nij,nj->ni", model[:, :3, :3], centre_local) + T
     entity_radius = sphere_r[mesh_index] * scale
@@ -290,7 +296,7 @@ def make_scene(name, seed, n_entities, n_meshes, lod_meshlets, layout="city", gr
                  entity_draws=entity_draws, n_entities=N, n_meshlet_instances=N * lod_meshlets[0],
                  n_records_lod0=N * words, n_visibility_words=N * words,
                  aabb_min=entity_pos.min(axis=0) - pad, aabb_max=entity_pos.max(axis=0) + pad,
-                 entity_pos=entity_pos, entity_radius=entity_radius, entity_occluder=occ)
+                 entity_pos=entity_pos, entity_radius=entity_radius, entity_occluder=occ, transforms=transforms)
 
 
 # ------------------------------------------------------------------------------------------------------------

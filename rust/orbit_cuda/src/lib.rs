@@ -86,7 +86,7 @@ pub struct OrbitClusterParams { pub info: OrbitClusterCullInfo, pub z_scale: f32
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
-pub struct OrbitStatus { pub dispatch_overflow: u32, pub draw_overflow: u32, pub light_index_overflow: u32, pub reserved: u32 }
+pub struct OrbitStatus { pub dispatch_overflow: u32, pub draw_overflow: u32, pub light_index_overflow: u32, pub visibility_overflow: u32 }
 
 extern "C" {
     pub fn orbit_abi_version() -> i32;

@@ -57,6 +57,8 @@ def lib():
         h.oracle_compact_clusters.restype = u32; h.oracle_compact_clusters.argtypes = [C.POINTER(L.ClusterParams), vp, vp]
         h.oracle_light_culling.restype = u64
         h.oracle_light_culling.argtypes = [C.POINTER(L.ClusterParams), vp, vp, vp, vp, vp, u64]
+        h.oracle_scene_update.restype = C.c_int
+        h.oracle_scene_update.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp, vp]
         _lib = h
     return _lib
 
@@ -185,3 +187,18 @@ def depth_prepass_culling(hs, view, depth, meshlet_occlusion=True, stats=None):
 
 def main_pass_culling(hs, view, meshlet_occlusion=True, stats=None):
     return cull_pass(hs, gpu_cull_info(view, "read", meshlet_occlusion), stats=stats)
+
+
+def scene_update(transforms, mesh_slots, visibility_offsets, mesh_infos, cursor, capacity_words=1 << 26):
+    """SceneData::update_scene (scene.rs:404-492), mesh part. visibility_offsets (uint32[n]) and cursor (uint32[1]) are
+    updated in place. Returns (entity data array, EntityDrawBuffer bytes, overflow flag)."""
+    n = len(transforms)
+    assert transforms.dtype == L.transform_dtype and visibility_offsets.dtype == np.uint32 and cursor.dtype == np.uint32
+    t = np.ascontiguousarray(transforms)
+    slots = np.ascontiguousarray(mesh_slots, dtype=np.uint32)
+    entity_data = np.zeros(n, L.entity_dtype)
+    draws = np.zeros(4 + 12 * n, np.uint8)
+    ovf = lib().oracle_scene_update(_p(t), _p(slots), _p(visibility_offsets), _p(mesh_infos), _p(cursor), n, capacity_words,
+                                    _p(entity_data), _p(draws))
+    count = int(draws[:4].view(np.uint32)[0])
+    return entity_data[:count], draws[:4 + 12 * count], int(ovf)
