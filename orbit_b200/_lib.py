@@ -72,6 +72,24 @@ def lib():
     return _lib
 
 
+_host = None
+
+
+def host_lib():
+    """Loads liborbit_host.so: the compiled host-side frame driver above the C ABI (orbit_b200/host/frame_driver.cpp)."""
+    global _host
+    if _host is None:
+        lib()   # liborbit_b200.so first: the driver links against it
+        path = os.path.join(os.path.dirname(LIB_PATH), "liborbit_host.so")
+        if not os.path.exists(path):
+            raise ImportError("liborbit_host.so is not built (%s). Run `python -m orbit_b200.build`." % path)
+        h = C.CDLL(path)
+        h.orbit_host_frame_loop.restype = C.c_int
+        h.orbit_host_frame_loop.argtypes = [C.c_void_p, C.POINTER(L.HostFrame), C.c_uint32, C.POINTER(L.HostFrameIO), C.c_uint32, C.c_uint32]
+        _host = h
+    return _host
+
+
 def check(code, what):
     if code != OK:
         raise OrbitError(code, what)

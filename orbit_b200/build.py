@@ -12,6 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liborbit_b200.so")
 SOURCES = ["api.cu", "hiz_build.cu", "entity_cull.cu", "meshlet_cull.cu", "light_cluster.cu", "scene_update.cu"]
+HOST_LIB_PATH = os.path.join(LIB_DIR, "liborbit_host.so")   # compiled host-side frame driver above the C ABI
+HOST_SOURCES = [os.path.join(HERE, "host", "frame_driver.cpp")]
 HEADERS = ["orbit_device.cuh", "scan.cuh", "params.cuh", "../../include/orbit_cuda.h", "../../include/orbit_layouts.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -28,10 +30,10 @@ def _nvcc():
 
 
 def needs_build():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HOST_LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    t = min(os.path.getmtime(LIB_PATH), os.path.getmtime(HOST_LIB_PATH))
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + HOST_SOURCES + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -49,6 +51,12 @@ def build(force=False, verbose=False, extra_flags=()):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
+    # host-side frame driver: plain C++ over the C ABI + cudart (no device code)
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(HERE, "..", "include"),
+           "-o", HOST_LIB_PATH] + HOST_SOURCES + ["-L", LIB_DIR, "-lorbit_b200", "-Xlinker", "-rpath=$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host driver build failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

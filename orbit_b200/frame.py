@@ -151,12 +151,13 @@ class PreparedFrame:
         if rc:
             raise RuntimeError("orbit_entity_cull: %d" % rc)
 
-    def meshlet(self, late, s=None):
+    def meshlet(self, late, s=None, context=None):
+        """`context`: run the stage on another Context's scratch (bench.py times the test kernel alone that way)."""
         C, lib, p = self._C, self._lib, self._ptr
         s = s or self._stream()
         g, sb, disp, out = ((self.g_late, self.sb_late, self.late_dispatch, self.late_draws) if late
                             else (self.g_early, self.sb_early, self.early_dispatch, self.early_draws))
-        rc = lib.orbit_meshlet_cull(self.context._h, C.byref(g), C.byref(sb), self.vstate.depth_pyramid._h if late else None,
+        rc = lib.orbit_meshlet_cull((context or self.context)._h, C.byref(g), C.byref(sb), self.vstate.depth_pyramid._h if late else None,
                                     p(disp), self.rcap, p(out), self.dcap, None, s)
         if rc:
             raise RuntimeError("orbit_meshlet_cull: %d" % rc)
@@ -182,3 +183,30 @@ class PreparedFrame:
 
     def replay(self):
         self.graph.replay()
+
+
+def host_frame_loop(context, prepared, scene_datas, h_transforms, h_depth, h_counts, h_early_draws, h_late_draws, steps, lookahead=2):
+    """End-to-end frame loop with HOST inputs/outputs run by the compiled host driver (orbit_b200/host/frame_driver.cpp):
+    per step, pinned-host Transforms + depth -> device, orbit_scene_update, the five culling-stage calls, both survivor
+    lists -> pinned host; `lookahead` steps in flight ahead of the one being read back, rotating over `prepared`
+    (PreparedFrame) / `scene_datas` (scene.SceneData) copies. Returns the driver's report."""
+    import ctypes as C
+    from . import _lib
+    n = len(prepared)
+    frames = (L.HostFrame * n)()
+    for f, pf, sd in zip(frames, prepared, scene_datas):
+        sd.update_scene(pf.dscene.assets)       # packs sd._packed (and keeps the ranges allocated)
+        f.update = sd._packed
+        f.cull_early, f.cull_late, f.scene_early, f.scene_late = pf.g_early, pf.g_late, pf.sb_early, pf.sb_late
+        f.hiz = pf.vstate.depth_pyramid._h.value
+        f.depth = pf.depth.data_ptr()
+        f.early_dispatch, f.early_draws = pf.early_dispatch.data_ptr(), pf.early_draws.data_ptr()
+        f.late_dispatch, f.late_draws = pf.late_dispatch.data_ptr(), pf.late_draws.data_ptr()
+        f.capacity_records, f.capacity_draws = pf.rcap, pf.dcap
+        f.width, f.height = pf._hw
+    torch.cuda.synchronize()
+    io = L.HostFrameIO()
+    io.h_transforms, io.h_depth, io.h_counts = h_transforms.data_ptr(), h_depth.data_ptr(), h_counts.data_ptr()
+    io.h_early_draws, io.h_late_draws = h_early_draws.data_ptr(), h_late_draws.data_ptr()
+    _lib.check(_lib.host_lib().orbit_host_frame_loop(context._h, frames, n, C.byref(io), int(steps), int(lookahead)), "orbit_host_frame_loop")
+    return {"ms_per_step": io.ms_per_step, "h2d_bytes_per_step": int(io.h2d_bytes_per_step), "d2h_bytes_per_step": int(io.d2h_bytes_last_step)}

@@ -43,13 +43,16 @@ class SceneData:
 
     def update_scene(self, assets):
         """scene.rs:404-492 (mesh part). Asynchronous on the current stream."""
-        u = L.SceneUpdate()
-        u.transforms = self.transforms.data_ptr(); u.mesh_slots = self.mesh_slots.data_ptr()
-        u.visibility_offsets = self.visibility_offsets.data_ptr(); u.mesh_infos = assets.mesh_info_buffer.data_ptr()
-        u.visibility_cursor = self.visibility_cursor.data_ptr()
-        u.n_entities = self.n_entities; u.visibility_capacity_words = self.visibility_capacity_words
-        u.entity_data = self.entity_data_buffer.data_ptr(); u.entity_draws = self.entity_draw_buffer.data_ptr()
-        _lib.check(_lib.lib().orbit_scene_update(self.context._h, C.byref(u), _stream()), "orbit_scene_update")
+        key = (assets.mesh_info_buffer.data_ptr(), self.entity_data_buffer.data_ptr(), self.entity_draw_buffer.data_ptr(), self.n_entities)
+        if getattr(self, "_packed_key", None) != key:      # the argument block only changes when a buffer does
+            u = L.SceneUpdate()
+            u.transforms = self.transforms.data_ptr(); u.mesh_slots = self.mesh_slots.data_ptr()
+            u.visibility_offsets = self.visibility_offsets.data_ptr(); u.mesh_infos = key[0]
+            u.visibility_cursor = self.visibility_cursor.data_ptr()
+            u.n_entities = self.n_entities; u.visibility_capacity_words = self.visibility_capacity_words
+            u.entity_data = key[1]; u.entity_draws = key[2]
+            self._packed, self._packed_key = u, key
+        _lib.check(_lib.lib().orbit_scene_update(self.context._h, C.byref(self._packed), _stream()), "orbit_scene_update")
 
     def import_to_graph(self, meshlet_visibility_buffer=None, record_capacity=0, draw_capacity=0):
         """scene.rs:494-502. entity_draw_count is the host's upper bound (every entity); the culling kernels clamp to the

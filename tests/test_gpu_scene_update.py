@@ -118,3 +118,43 @@ def test_scene_update_feeds_the_culling_passes(gpu_context, oracle):
             gn, gd = frame.read_draws(g[k][1]); on, od = oracle.parse_draws(o[k][1])
             assert gn == on and np.array_equal(gd.view(np.uint32), od.view(np.uint32)), (f, k)
         assert f == 0 or frame.read_draws(g["early"][1])[0] > 0      # frame 1 draws what frame 0's late pass found
+
+
+def test_compiled_host_frame_loop_matches_oracle(gpu_context, oracle):
+    """orbit_b200/host/frame_driver.cpp (the compiled host loop bench.py's e2e number comes from): HOST transforms + depth
+    in, HOST survivor lists out, pipelined over scene copies — the lists of the last step equal the oracle chain's."""
+    import torch
+    from orbit_b200 import frame
+    from orbit_b200.scene import SceneData
+    ctx = gpu_context
+    sc, view = scenes.config_c1(scale=0.5, lods=(100, 40))
+    depth = scenes.make_depth(sc, view)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+    copies, sds = [], []
+    for i in range(4):
+        ds = frame.DeviceScene.upload(ctx, sc)
+        vs = frame.ViewState(ctx, ds, (view.width, view.height), name="hfl%d" % i)
+        pf = frame.PreparedFrame(ctx, ds, vs, view, torch.zeros((view.height, view.width), dtype=torch.float32, device=ctx.device), name="hfl%d" % i)
+        sd = SceneData(ctx, sc.n_entities)
+        sd.set_entities(sc.transforms, sc.draws["mesh_index"])
+        sd.transforms.zero_()                                           # the loop must bring the transforms in itself
+        sd.entity_data_buffer, sd.entity_draw_buffer = ds.scene.entity_buffer, ds.scene.entity_draw_buffer
+        copies.append(pf); sds.append(sd)
+    h_t, h_d = pin(sc.transforms), torch.from_numpy(depth).pin_memory()
+    h_c = torch.zeros(2, dtype=torch.int32).pin_memory()
+    h_e = torch.zeros(28 * sc.n_meshlet_instances, dtype=torch.uint8).pin_memory()
+    h_l = torch.zeros(28 * sc.n_meshlet_instances, dtype=torch.uint8).pin_memory()
+    rep = frame.host_frame_loop(ctx, copies, sds, h_t, h_d, h_c, h_e, h_l, steps=6, lookahead=2)
+    assert rep["h2d_bytes_per_step"] == h_t.numel() + depth.nbytes
+    # step 5 ran on copy 1 and was that copy's second frame
+    vo = np.full(sc.n_entities, L.NO_VISIBILITY_RANGE, np.uint32)
+    o_ed, o_draws, _ = oracle.scene_update(sc.transforms, sc.draws["mesh_index"].copy(), vo, sc.mesh_infos, np.zeros(1, np.uint32))
+    sc.entities, sc.entity_draws = o_ed.copy(), o_draws.copy()
+    hs = oracle.HostScene(sc)
+    oracle.depth_prepass_culling(hs, view, depth)
+    o = oracle.depth_prepass_culling(hs, view, depth)
+    ne, e = oracle.parse_draws(o["early"][1]); nl, l = oracle.parse_draws(o["late"][1])
+    assert (int(h_c[0]), int(h_c[1])) == (ne, nl) and ne > 0
+    assert np.array_equal(h_e.numpy()[:28 * ne], e.view(np.uint8).reshape(-1))
+    assert np.array_equal(h_l.numpy()[:28 * nl], l.view(np.uint8).reshape(-1))
+    assert rep["d2h_bytes_per_step"] == 8 + 28 * (ne + nl)
