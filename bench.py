@@ -211,6 +211,11 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     step_ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()
+    if args.step_only:   # for `ncu` launch lists: the last 7 x steps kernels of the process are exactly the timed region
+        if rank == 0:
+            print(json.dumps({"step_only": True, "ms_per_step": step_ms, "steps": args.steps}), flush=True)
+        ctx.close()
+        return
     gpu_launches = 7 * args.steps  # per step: 2 x entity_cull, 2 x (meshlet_test + meshlet_emit), 1 x hiz_build (graph replays bypass the ABI counter)
 
     # ---- per-stage device times: a CUDA graph of 8 back-to-back launches of ONE stage rotating over the scene copies
@@ -382,6 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--step-only", action="store_true", help="stop after the timed region (profiling aid)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
