@@ -24,6 +24,10 @@
  *     commands by (dispatch record index, lane), compacted clusters and light indices ascending.  The
  *     reference appends with atomicAdd (entity_cull.comp:211, meshlet_cull.comp:228), i.e. in arbitrary
  *     order; any order is valid for its consumers, so a fixed one is a drop-in.
+ *   - latency hiding reads ahead: the meshlet stage may LOAD (and then ignore) dispatch-buffer bytes between the
+ *     device-side record count and `capacity_records`, and the entity stage entity-draw words up to
+ *     `entity_draw_count`; the buffers must be allocated to the stated capacities (contents beyond the counts are
+ *     never used; zero them once if a tool such as compute-sanitizer initcheck is to stay quiet).
  *   - scratch grows on the first call that needs more than the context has seen so far (larger capacity_records,
  *     more clusters, more lights); growing synchronises the device once, so warm a context up with its real
  *     capacities before capturing calls into a CUDA graph. Captured calls are replay-safe: scan epochs, tickets and

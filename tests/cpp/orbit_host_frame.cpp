@@ -61,6 +61,7 @@ int main(int argc, char** argv) {
     void *dispatch = nullptr, *draws = nullptr;
     const size_t dispatch_bytes = 12 + 16 * (size_t)m.record_capacity, draw_bytes = 4 + 28 * (size_t)m.draw_capacity;
     CU(cudaMalloc(&dispatch, dispatch_bytes)); CU(cudaMalloc(&draws, draw_bytes));
+    CU(cudaMemset(dispatch, 0, dispatch_bytes));   // the meshlet stage reads ahead of the record count (orbit_cuda.h, conventions)
     DepthPyramid pyramid(ctx, m.width, m.height);
 
     CullInfo cull;
