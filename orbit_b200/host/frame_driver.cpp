@@ -41,6 +41,10 @@ typedef struct OrbitHostFrameIO {
     double ms_per_step;                 // out: host wall clock over `steps`, everything drained
 } OrbitHostFrameIO;
 
+// sizeof probes for the ctypes mirrors (orbit_b200/layouts.py: HostFrame, HostFrameIO)
+uint32_t orbit_host_sizeof_frame(void) { return (uint32_t)sizeof(OrbitHostFrame); }
+uint32_t orbit_host_sizeof_io(void) { return (uint32_t)sizeof(OrbitHostFrameIO); }
+
 #define CU_OK(x) do { if ((x) != cudaSuccess) return ORBIT_ERR_CUDA; } while (0)
 #define OR_OK(x) do { int rc_ = (x); if (rc_ != ORBIT_OK) return rc_; } while (0)
 

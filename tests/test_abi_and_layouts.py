@@ -58,7 +58,8 @@ def test_layouts_match_c_header(tmp_path):
 int main(void) {
   P(OrbitCullInfo); P(OrbitEntityData); P(OrbitEntityDraw); P(OrbitMeshInfo); P(OrbitMeshlet); P(OrbitMeshletDispatch);
   P(OrbitMeshletDrawCommand); P(OrbitMeshTaskPayload); P(OrbitLightData); P(OrbitClusterCullInfo); P(OrbitClusterParams);
-  P(OrbitSceneBuffers); P(OrbitHizInfo); P(OrbitStatus);
+  P(OrbitSceneBuffers); P(OrbitHizInfo); P(OrbitStatus); P(OrbitTransform); P(OrbitSceneUpdate);
+  O(OrbitTransform, orientation); O(OrbitTransform, scale); O(OrbitSceneUpdate, n_entities); O(OrbitSceneUpdate, entity_data); O(OrbitStatus, visibility_overflow);
   O(OrbitCullInfo, cull_planes); O(OrbitCullInfo, occlusion_pass); O(OrbitCullInfo, p00_or_width_recip_x2); O(OrbitCullInfo, lod_base);
   O(OrbitCullInfo, lod_target_pos_view_space); O(OrbitCullInfo, max_mesh_lod);
   O(OrbitClusterCullInfo, tile_size_px); O(OrbitClusterCullInfo, z_near); O(OrbitClusterCullInfo, global_light_count);
@@ -73,7 +74,8 @@ int main(void) {
                 "OrbitMeshInfo": L.mesh_info_dtype.itemsize, "OrbitMeshlet": L.meshlet_dtype.itemsize, "OrbitMeshletDispatch": L.dispatch_dtype.itemsize,
                 "OrbitMeshletDrawCommand": L.draw_command_dtype.itemsize, "OrbitMeshTaskPayload": 40, "OrbitLightData": L.light_dtype.itemsize,
                 "OrbitClusterCullInfo": C.sizeof(L.ClusterCullInfo), "OrbitClusterParams": C.sizeof(L.ClusterParams),
-                "OrbitSceneBuffers": C.sizeof(L.SceneBuffers), "OrbitHizInfo": C.sizeof(L.HizInfo), "OrbitStatus": C.sizeof(L.Status)}
+                "OrbitSceneBuffers": C.sizeof(L.SceneBuffers), "OrbitHizInfo": C.sizeof(L.HizInfo), "OrbitStatus": C.sizeof(L.Status),
+                "OrbitTransform": L.transform_dtype.itemsize, "OrbitSceneUpdate": C.sizeof(L.SceneUpdate)}
     for k, v in py_sizes.items():
         assert got[k] == v, (k, got[k], v)
     offs = {"OrbitCullInfo.cull_planes": L.CullInfo.cull_planes.offset, "OrbitCullInfo.occlusion_pass": L.CullInfo.occlusion_pass.offset,
@@ -83,6 +85,9 @@ int main(void) {
             "OrbitClusterCullInfo.global_light_count": L.ClusterCullInfo.global_light_count.offset, "OrbitClusterParams.z_scale": L.ClusterParams.z_scale.offset,
             "OrbitSceneBuffers.entity_draw_count": L.SceneBuffers.entity_draw_count.offset, "OrbitHizInfo.level_offset": L.HizInfo.level_offset.offset,
             "OrbitHizInfo.texels": L.HizInfo.texels.offset,
+            "OrbitTransform.orientation": L.transform_dtype.fields["orientation"][1], "OrbitTransform.scale": L.transform_dtype.fields["scale"][1],
+            "OrbitSceneUpdate.n_entities": L.SceneUpdate.n_entities.offset, "OrbitSceneUpdate.entity_data": L.SceneUpdate.entity_data.offset,
+            "OrbitStatus.visibility_overflow": L.Status.visibility_overflow.offset,
             "OrbitMeshlet.cone_axis": L.meshlet_dtype.fields["cone_axis"][1], "OrbitMeshlet.material_index": L.meshlet_dtype.fields["material_index"][1],
             "OrbitMeshInfo.mesh_lods": L.mesh_info_dtype.fields["mesh_lods"][1], "OrbitLightData.outer_radius": L.light_dtype.fields["outer_radius"][1]}
     for k, v in offs.items():
@@ -113,3 +118,12 @@ def test_argument_errors_without_gpu():
     assert lib.orbit_entity_cull(None, None, None, None, None, 0, None) == _lib.ERR_INVALID_ARGUMENT
     assert lib.orbit_meshlet_cull(None, None, None, None, None, 0, None, 0, None, None) == _lib.ERR_INVALID_ARGUMENT
     assert lib.orbit_hiz_build(None, None, None, 1, 1, None) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.orbit_scene_update(None, None, None) == _lib.ERR_INVALID_ARGUMENT
+
+
+def test_host_driver_library_loads():
+    """liborbit_host.so (compiled host frame loop above the C ABI) loads, resolves against liborbit_b200.so, and its
+    struct mirrors have the sizes the C++ side sees."""
+    h = _lib.host_lib()
+    assert h.orbit_host_frame_loop(None, None, 0, None, 0, 0) == _lib.ERR_INVALID_ARGUMENT
+    assert h.orbit_host_sizeof_frame() == C.sizeof(L.HostFrame) and h.orbit_host_sizeof_io() == C.sizeof(L.HostFrameIO)
