@@ -326,7 +326,7 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     int per_sm = c->mc_ctas_per_sm;
     if (per_sm <= 0) per_sm = occ > 0 ? occ : 1;
     const uint64_t grid = (uint64_t)c->sm_count * (uint64_t)per_sm;
-    // emit kernel: CTAs wait on lower CTAs' aggregates -> never more CTAs than are co-resident
+    // emit kernel: two CTAs per SM (every CTA repeats the 2048-entry chunk scan; more CTAs only add to that)
     if (c->emit_occupancy <= 0) c->emit_occupancy = meshlet_emit_max_ctas_per_sm();
     int emit_per_sm = c->emit_occupancy < 2 ? (c->emit_occupancy > 0 ? c->emit_occupancy : 1) : 2;
     const uint64_t emit_grid = (uint64_t)c->sm_count * (uint64_t)emit_per_sm;

@@ -56,21 +56,27 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
     bool visible = false;
     const bool in_range = gid < count;
     if (in_range) {
+        // every load that depends only on the draw words, issued back to back (ordered loads, orbit_device.cuh): what
+        // is needed last goes first, the model matrix — consumed by the very next instructions — last
         const uint8_t* mi = p.mesh_infos + (size_t)mesh_index * 128u;
-        const float4 sph = __ldg(reinterpret_cast<const float4*>(mi));
-        const uint4 mi_hdr = __ldg(reinterpret_cast<const uint4*>(mi + 48));      // vertex_offset, data_offset, lod_count, pad
         uint4 lods[4];                                                            // 8 x (meshlet_offset, meshlet_count)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) lods[k] = __ldg(reinterpret_cast<const uint4*>(mi + 64) + k);
-        bool vib = true;
-        if (pass == 1u || pass == 2u) vib = ((__ldcg(p.entity_visibility + (gid >> 5)) >> (gid & 31u)) & 1u) != 0u;
+        for (int k = 0; k < 4; ++k) lods[k] = ld_v4_ordered(mi + 64 + 16 * k);
+        const uint4 mi_hdr = ld_v4_ordered(mi + 48);                              // vertex_offset, data_offset, lod_count, pad
+        uint32_t vword = 0xFFFFFFFFu;
+        if (pass == 1u || pass == 2u) vword = ld_u32_ordered(p.entity_visibility + (gid >> 5));
+        const float4 sph = as_float4(ld_v4_ordered(mi));
+        float4 mcol[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mcol[k] = as_float4(ld_v4_ordered(p.entities + (size_t)entity_index * 8u + k));
+        const bool vib = ((vword >> (gid & 31u)) & 1u) != 0u;
         visible = (pass == 1u) ? vib : true;
 
         // view * model (entity_cull.comp:131-133)
         ModelView mv;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float4 b = __ldg(p.entities + (size_t)entity_index * 8u + k);
+            const float4 b = mcol[k];
 #pragma unroll
             for (int row = 0; row < 4; ++row)
                 mv.m[k * 4 + row] = add(add(add(mul(ci.view_matrix.m[0][row], b.x), mul(ci.view_matrix.m[1][row], b.y)),

@@ -507,7 +507,10 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
         v0[0] = a0.x; v0[1] = a0.y; v0[2] = a0.z; v0[3] = a0.w; v0[4] = a1.x; v0[5] = a1.y; v0[6] = a1.z; v0[7] = a1.w;
         v1[0] = b0.x; v1[1] = b0.y; v1[2] = b0.z; v1[3] = b0.w; v1[4] = b1.x; v1[5] = b1.y; v1[6] = b1.z; v1[7] = b1.w;
     }
-    const uint32_t t0 = __ldcg(p.draw_total), t1 = __ldcg(p.draw_total + 1);
+    // both parities' totals in ONE 8-byte load (two 4-byte loads get the second one predicated on the parity by ptxas,
+    // even as volatile asm: a dependent round trip in a kernel that is only a handful of round trips long)
+    const uint2 t01 = __ldcg(reinterpret_cast<const uint2*>(p.draw_total));
+    const uint32_t t0 = t01.x, t1 = t01.y;
     uint32_t nrec = __ldcg(p.dispatch_words);
     const uint32_t parity = __ldcg(p.chunk_parity + 1) & 1u;   // word B: the half the test kernel of this call used
     const uint32_t grand_total = parity ? t1 : t0;

@@ -187,6 +187,23 @@ ORBIT_DEV bool occlusion_test(const OrbitCullInfo& ci, Sphere& s, const HizDevic
     return depth >= sampled;
 }
 
+// Loads that are issued where they are written. In the latency-bound kernels the order of the independent loads is
+// the schedule: left alone, nvcc AND ptxas sink a prefetch below arithmetic that waits on an earlier load (register
+// pressure heuristic), turning two overlapped round trips into two dependent ones. PTX `ld.volatile` operations keep
+// their program order among themselves, so a chain "prefetches first, the load the next instruction needs last" pins
+// all of them before the first use. (Volatile loads are served by L2, which is where this single-use data lives.)
+ORBIT_DEV uint4 ld_v4_ordered(const void* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+ORBIT_DEV uint32_t ld_u32_ordered(const void* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+ORBIT_DEV float4 as_float4(uint4 v) { return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)); }
+
 // ConvertFToU pinned: NaN/negative -> 0, >= 2^32 -> 0xFFFFFFFF (cvt.rzi.u32.f32 saturates exactly like this).
 ORBIT_DEV uint32_t f2u(float f) { return __float2uint_rz(f); }
 ORBIT_DEV uint32_t shl1(uint32_t s) { return s >= 32u ? 0u : (1u << s); }

@@ -67,7 +67,7 @@ def main():
             os.environ["ORBIT_MC_CTAS_PER_SM"] = str(cps)
         ctx = Context(0)
         copies = []
-        for i in range(4):
+        for i in range(int(os.environ.get("KBENCH_COPIES", "4"))):   # 1 = everything L2-resident (latency floor of each stage)
             ds = frame.DeviceScene.upload(ctx, scene)
             vs = frame.ViewState(ctx, ds, (view.width, view.height), name="v%d" % i)
             pf = frame.PreparedFrame(ctx, ds, vs, view, torch.from_numpy(depth_np).to(ctx.device), name="c%d" % i)
