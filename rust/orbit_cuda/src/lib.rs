@@ -41,6 +41,26 @@ pub struct OrbitCullInfo {
 }
 const _: () = assert!(std::mem::size_of::<OrbitCullInfo>() == 400);
 
+/// Transform in the 48-byte row layout orbit_scene_update reads (include/orbit_layouts.h; scene.rs:18-23).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct OrbitTransform { pub position: [f32; 3], pub _pad0: f32, pub orientation: [f32; 4], pub scale: [f32; 3], pub _pad1: f32 }
+
+/// Arguments of orbit_scene_update (SceneData::update_scene, scene.rs:404-492). Device pointers.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct OrbitSceneUpdate {
+    pub transforms: *const OrbitTransform,
+    pub mesh_slots: *const u32,
+    pub visibility_offsets: *mut u32,
+    pub mesh_infos: *const c_void,
+    pub visibility_cursor: *mut u32,
+    pub n_entities: u32,
+    pub visibility_capacity_words: u32,
+    pub entity_data: *mut c_void,
+    pub entity_draws: *mut c_void,
+}
+
 #[repr(C)]
 #[derive(Clone, Copy)]
 pub struct OrbitSceneBuffers {
@@ -110,6 +130,7 @@ extern "C" {
     pub fn orbit_light_cluster(ctx: *mut orbit_ctx, params: *const OrbitClusterParams, depth: *const f32, lights: *const c_void,
                                tile_masks: *mut c_void, depth_bounds: *mut c_void, unique_clusters: *mut c_void,
                                offset_count_image: *mut c_void, light_index_list: *mut c_void, capacity_indices: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_scene_update(ctx: *mut orbit_ctx, update: *const OrbitSceneUpdate, stream: *mut c_void) -> i32;
     pub fn orbit_draws_scatter(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, dst_draw_buffer: *mut c_void, dst_first: u32,
                                total_count: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
 }

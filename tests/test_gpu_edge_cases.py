@@ -157,3 +157,59 @@ def test_graph_replay_is_stateless(gpu_context, oracle):
     _cmp(oracle, (pf.early_dispatch, pf.early_draws), o["early"])
     _cmp(oracle, (pf.late_dispatch, pf.late_draws), o["late"])
     assert np.array_equal(vs.meshlet_visibility.cpu().numpy().view(np.uint32), hs.meshlet_visibility)
+
+
+def test_contexts_are_independent_across_threads(oracle):
+    """SURVEY §8b threading: pass recording runs on worker threads (context.rs:1392-1423), so the library must be callable
+    from any thread with an explicit context + stream and no thread-local state. Three host threads, each with its own
+    context, stream and scene, run three frames concurrently; every thread's outputs equal the oracle's."""
+    import threading
+    from orbit_b200 import frame
+    from orbit_b200.passes import Context
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cases = []
+    for k, scale in enumerate((0.3, 0.45, 0.6)):
+        sc, view = scenes.config_c1(scale=scale, lods=(100, 40) if k % 2 else (100,))
+        cases.append((sc, view, scenes.make_depth(sc, view)))
+    results, errors = [None] * len(cases), []
+
+    def worker(k):
+        try:
+            sc, view, depth = cases[k]
+            torch.cuda.set_device(0)
+            ctx = Context(0)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                ds = frame.DeviceScene.upload(ctx, sc)
+                vs = frame.ViewState(ctx, ds, (view.width, view.height), name="thr%d" % k)
+                d_depth = torch.from_numpy(depth).to(ctx.device)
+                out = []
+                for f in range(3):
+                    g = frame.depth_prepass_culling(ctx, ds, vs, view, d_depth, name="thr%d" % k)
+                    stream.synchronize()
+                    out.append({s: (g[s][0].cpu().numpy().copy(), g[s][1][:4 + 28 * frame.read_draws(g[s][1], capacity=0)[0]].cpu().numpy().copy())
+                                for s in ("early", "late")})
+                results[k] = (out, vs.meshlet_visibility.cpu().numpy().view(np.uint32).copy())
+            ctx.close()
+        except Exception as e:   # surfaced in the main thread
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(cases))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k, (sc, view, depth) in enumerate(cases):
+        hs = oracle.HostScene(sc)
+        out, mvis = results[k]
+        for f in range(3):
+            o = oracle.depth_prepass_culling(hs, view, depth)
+            for s in ("early", "late"):
+                ohdr, orecs = oracle.parse_dispatch(o[s][0]); on, od = oracle.parse_draws(o[s][1])
+                gd, gdraw = out[f][s]
+                assert gd[:12].view(np.uint32).tolist() == ohdr.tolist(), (k, f, s)
+                assert np.array_equal(gd[12:12 + 16 * int(ohdr[0])], orecs.view(np.uint8).reshape(-1)), (k, f, s)
+                assert int(gdraw[:4].view(np.uint32)[0]) == on and np.array_equal(gdraw[4:], od.view(np.uint8).reshape(-1)), (k, f, s)
+        assert np.array_equal(mvis, hs.meshlet_visibility), k
