@@ -111,8 +111,10 @@ class PeerExchange:
         self.counts = torch.zeros(self.world, dtype=torch.int32, device=context.device)
         dist.barrier(group=group)
 
-    def exchange(self, local_draw_buffer):
-        """Returns (total count, per-rank counts); the assembled list is in self.local_ptr (see read())."""
+    def exchange(self, local_draw_buffer, root=None):
+        """Returns (total count, per-rank counts); the assembled list is in self.local_ptr (see read()).
+        root=None: every rank receives the full list (all-gather). root=r: only rank r does (gather) — what a frame
+        whose draws are submitted by one GPU needs; each rank then stores its commands once instead of world times."""
         C = self.C
         dist.all_gather_into_tensor(self.counts, local_draw_buffer[:4].view(torch.int32), group=self.group)
         counts = [int(v) for v in self.counts.cpu().tolist()]
@@ -120,6 +122,8 @@ class PeerExchange:
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for k in range(self.world):
             r = (self.rank + k) % self.world       # staggered destinations: no rank is everybody's first target
+            if root is not None and r != root:
+                continue
             rc = self.lib.orbit_draws_scatter(self.context._h, C.c_void_p(local_draw_buffer.data_ptr()), C.c_void_p(self.peer_ptrs[r]),
                                               first, total, self.capacity, stream)
             if rc:
@@ -133,6 +137,13 @@ class PeerExchange:
         self.lib.orbit_device_copy(self.C.c_void_p(out.data_ptr()), self.C.c_void_p(self.local_ptr), out.numel(),
                                    self.C.c_void_p(torch.cuda.current_stream().cuda_stream))
         return out
+
+    def clear(self):
+        """Zeroes this rank's assembled list (tests: proves that a following exchange really delivers it)."""
+        z = torch.zeros(self.bytes, dtype=torch.uint8, device=self.context.device)
+        self.lib.orbit_device_copy(self.C.c_void_p(self.local_ptr), self.C.c_void_p(z.data_ptr()), z.numel(),
+                                   self.C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
 
     def close(self):
         for r, q in enumerate(self.peer_ptrs):
@@ -167,7 +178,9 @@ class ShardedView:
         self.peer_late = PeerExchange(self.context, capacity_draws)
 
     def step(self, exchange=True):
-        """One two-pass frame: early cull (local range) -> Hi-Z on rank 0 + broadcast -> late cull -> gather."""
+        """One two-pass frame: early cull (local range) -> Hi-Z on rank 0 + broadcast -> late cull -> survivor exchange:
+        True = padded NCCL all-gather, "peer" = NVLink peer stores to every rank, "gather" = peer stores to rank 0 only,
+        False = none."""
         pf = self.prepared
         if not self.empty:
             pf.entity(False); pf.meshlet(False)
@@ -180,9 +193,10 @@ class ShardedView:
             pf.early_draws[:4].zero_(); pf.late_draws[:4].zero_()
         if not exchange:
             return None
-        if exchange == "peer":
-            n_e, _ = self.peer_early.exchange(pf.early_draws)
-            n_l, _ = self.peer_late.exchange(pf.late_draws)
+        if exchange in ("peer", "gather"):
+            root = 0 if exchange == "gather" else None
+            n_e, _ = self.peer_early.exchange(pf.early_draws, root)
+            n_l, _ = self.peer_late.exchange(pf.late_draws, root)
             return n_e, n_l
         early, _ = exchange_survivors(pf.early_draws)
         late, _ = exchange_survivors(pf.late_draws)

@@ -110,9 +110,19 @@ def run_c3(args, rank, world, ctx):
         pe, pl = sv.peer_early.read(n_e), sv.peer_late.read(n_l)
         torch.cuda.synchronize()
         peer_ok = bool(torch.equal(pe, early) and torch.equal(pl, late))
-        t = torch.tensor([t_compute, t_full, t_peer], device=ctx.device, dtype=torch.float64)
+        # gather: only rank 0 (the GPU that submits the draws) receives the list
+        sv.step(exchange="gather")
+        t_gather = event_time(lambda: sv.step(exchange="gather"))[0]
+        sv.peer_early.clear(); sv.peer_late.clear()
+        dist.barrier()
+        n_e, n_l = sv.step(exchange="gather")
+        torch.cuda.synchronize()
+        gather_ok = True
+        if rank == 0:
+            gather_ok = bool(torch.equal(sv.peer_early.read(n_e), early) and torch.equal(sv.peer_late.read(n_l), late))
+        t = torch.tensor([t_compute, t_full, t_peer, t_gather], device=ctx.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_compute, t_full, t_peer = float(t[0]), float(t[1]), float(t[2])
+        t_compute, t_full, t_peer, t_gather = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     res = {"config": "C3", "n_gpus": world, "entities": scene.n_entities, "meshlet_instances": scene.n_meshlet_instances,
            "ranges": sv.ranges, "us_compute": t_compute, "us_with_exchange": t_full,
            "gmeshlets_per_s_compute": scene.n_meshlet_instances / t_compute / 1e3,
@@ -120,6 +130,10 @@ def run_c3(args, rank, world, ctx):
            "pyramid_bytes": int(sv.vstate.depth_pyramid.texels.numel() * 4),
            "us_with_peer_exchange": t_peer, "peer_exchange_equals_allgather": peer_ok,
            "gmeshlets_per_s_with_peer_exchange": (scene.n_meshlet_instances / t_peer / 1e3) if t_peer else None}
+    if world > 1:
+        res["us_with_gather_to_rank0"] = t_gather
+        res["gather_equals_allgather_on_rank0"] = gather_ok
+        res["gmeshlets_per_s_with_gather"] = scene.n_meshlet_instances / t_gather / 1e3
     if rank == 0:
         n_early = int(early[:4].view(torch.int32).item()); n_late = int(late[:4].view(torch.int32).item())
         res["survivors_early"], res["survivors_late"] = n_early, n_late
