@@ -186,6 +186,12 @@ int orbit_scene_update(orbit_ctx* ctx, const OrbitSceneUpdate* update, void* str
  * rank-major survivor list of a meshlet-range-sharded view through NVLink peer stores. */
 int orbit_draws_scatter(orbit_ctx* ctx, const void* src_draw_buffer, void* dst_draw_buffer,
                         uint32_t dst_first, uint32_t total_count, uint64_t dst_capacity_draws, void* stream);
+/* Same, with the placement taken from the DEVICE: rank_counts[world] = every rank's survivor count (e.g. the result
+ * of an all-gather enqueued on the same stream); dst_first = sum of rank_counts[0..rank), header = their total.
+ * Nothing is read back to the host, so a whole sharded frame stays asynchronous. */
+int orbit_draws_scatter_ranked(orbit_ctx* ctx, const void* src_draw_buffer, void* dst_draw_buffer,
+                               const uint32_t* rank_counts, uint32_t rank, uint32_t world,
+                               uint64_t dst_capacity_draws, void* stream);
 
 /* Peer-visible device memory for that assembly: one process per GPU, so a rank's output buffer is shared with the
  * other ranks through CUDA IPC. `orbit_peer_alloc` returns cudaMalloc'd memory plus its 64-byte IPC handle;

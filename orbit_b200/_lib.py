@@ -36,6 +36,8 @@ PROTOTYPES = {
     "orbit_scene_update": (C.c_int, [C.c_void_p, C.POINTER(L.SceneUpdate), C.c_void_p]),
     "orbit_draws_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
                                       C.c_void_p]),
+    "orbit_draws_scatter_ranked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
+                                             C.c_void_p]),
     "orbit_peer_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]),
     "orbit_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "orbit_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),

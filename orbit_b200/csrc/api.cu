@@ -392,7 +392,16 @@ int orbit_draws_scatter(orbit_ctx* c, const void* src, void* dst, uint32_t dst_f
                         uint64_t dst_capacity_draws, void* stream) {
     if (!c || !src || !dst) return ORBIT_ERR_INVALID_ARGUMENT;
     CK(launch_draws_scatter((const uint32_t*)src, (uint32_t*)dst, dst_first, total_count, dst_capacity_draws,
-                            c->sm_count * 16, (cudaStream_t)stream));
+                            c->sm_count * 16, (cudaStream_t)stream, nullptr, 0u, 0u));
+    c->launches += 1;
+    return ORBIT_OK;
+}
+
+int orbit_draws_scatter_ranked(orbit_ctx* c, const void* src, void* dst, const uint32_t* rank_counts, uint32_t rank, uint32_t world,
+                               uint64_t dst_capacity_draws, void* stream) {
+    if (!c || !src || !dst || !rank_counts || world == 0u || rank >= world) return ORBIT_ERR_INVALID_ARGUMENT;
+    CK(launch_draws_scatter((const uint32_t*)src, (uint32_t*)dst, 0u, 0u, dst_capacity_draws, c->sm_count * 16, (cudaStream_t)stream,
+                            rank_counts, rank, world));
     c->launches += 1;
     return ORBIT_OK;
 }
@@ -472,8 +481,16 @@ namespace orbit {
 // 4 bytes into both buffers and dst_first shifts the destination further, so source and destination are not
 // mutually 16-byte aligned: the body issues ALIGNED 16-byte stores to the destination (what matters over NVLink),
 // each assembled from four 4-byte loads of the local source; up to 3 head and 3 tail words go out as 4-byte stores.
+// rank_counts != nullptr: dst_first and total_count come from the device (the all-gathered per-rank survivor counts):
+// dst_first = sum of the counts of ranks below `rank`, total = sum over all `world` ranks — no host round trip.
 __global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
-                                                            uint32_t dst_first, uint32_t total_count, uint64_t dst_capacity) {
+                                                            uint32_t dst_first, uint32_t total_count, uint64_t dst_capacity,
+                                                            const uint32_t* __restrict__ rank_counts, uint32_t rank, uint32_t world) {
+    if (rank_counts) {
+        uint32_t first = 0u, total = 0u;
+        for (uint32_t r = 0; r < world; ++r) { const uint32_t c = __ldcg(rank_counts + r); if (r < rank) first += c; total += c; }
+        dst_first = first; total_count = total;
+    }
     const uint32_t n = __ldcg(src);
     uint64_t m = n;
     if ((uint64_t)dst_first >= dst_capacity) m = 0; else if ((uint64_t)dst_first + m > dst_capacity) m = dst_capacity - dst_first;
@@ -497,8 +514,8 @@ __global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __re
     if (blockIdx.x == 0 && threadIdx.x == 0 && total_count != 0xFFFFFFFFu) dst[0] = total_count;
 }
 cudaError_t launch_draws_scatter(const uint32_t* src, uint32_t* dst, uint32_t dst_first, uint32_t total_count,
-                                 uint64_t dst_capacity, int grid, cudaStream_t s) {
-    draws_scatter_kernel<<<grid, 256, 0, s>>>(src, dst, dst_first, total_count, dst_capacity);
+                                 uint64_t dst_capacity, int grid, cudaStream_t s, const uint32_t* rank_counts, uint32_t rank, uint32_t world) {
+    draws_scatter_kernel<<<grid, 256, 0, s>>>(src, dst, dst_first, total_count, dst_capacity, rank_counts, rank, world);
     return cudaGetLastError();
 }
 }  // namespace orbit

@@ -107,6 +107,6 @@ cudaError_t launch_compact_clusters(const ClusterParams&, cudaStream_t);
 cudaError_t launch_light_view(const ClusterParams&, cudaStream_t);
 cudaError_t launch_light_culling(const ClusterParams&, int grid, cudaStream_t);
 cudaError_t launch_draws_scatter(const uint32_t* src, uint32_t* dst, uint32_t dst_first, uint32_t total_count,
-                                 uint64_t dst_capacity, int grid, cudaStream_t);
+                                 uint64_t dst_capacity, int grid, cudaStream_t s, const uint32_t* rank_counts, uint32_t rank, uint32_t world);
 
 }  // namespace orbit

@@ -131,6 +131,27 @@ class PeerExchange:
         dist.barrier(group=self.group)   # every rank's stores into my buffer are complete and visible
         return total, counts
 
+    def exchange_async(self, local_draw_buffer, root=None):
+        """Same exchange without any host round trip: the all-gathered counts stay on the device and
+        `orbit_draws_scatter_ranked` derives each rank's offset from them; a 4-byte all-reduce enqueued behind the
+        stores is the closing barrier. Everything is stream-ordered, so a sharded frame can be enqueued back to back.
+        Returns the device tensor of per-rank counts (read it after synchronising to learn the total)."""
+        C = self.C
+        dist.all_gather_into_tensor(self.counts, local_draw_buffer[:4].view(torch.int32), group=self.group)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for k in range(self.world):
+            r = (self.rank + k) % self.world
+            if root is not None and r != root:
+                continue
+            rc = self.lib.orbit_draws_scatter_ranked(self.context._h, C.c_void_p(local_draw_buffer.data_ptr()), C.c_void_p(self.peer_ptrs[r]),
+                                                     C.c_void_p(self.counts.data_ptr()), self.rank, self.world, self.capacity, stream)
+            if rc:
+                raise RuntimeError("orbit_draws_scatter_ranked: %d" % rc)
+        if not hasattr(self, "_fence"):
+            self._fence = torch.zeros(1, dtype=torch.int32, device=self.context.device)
+        dist.all_reduce(self._fence, group=self.group)   # completes on a rank only after every rank's stores were issued and flushed
+        return self.counts
+
     def read(self, total):
         """Copies the assembled MeshletDrawCommandBuffer (count + total commands) into a torch tensor."""
         out = torch.empty(4 + DRAW_BYTES * total, dtype=torch.uint8, device=self.context.device)
@@ -193,6 +214,9 @@ class ShardedView:
             pf.early_draws[:4].zero_(); pf.late_draws[:4].zero_()
         if not exchange:
             return None
+        if exchange in ("peer_async", "gather_async"):
+            root = 0 if exchange == "gather_async" else None
+            return self.peer_early.exchange_async(pf.early_draws, root), self.peer_late.exchange_async(pf.late_draws, root)
         if exchange in ("peer", "gather"):
             root = 0 if exchange == "gather" else None
             n_e, _ = self.peer_early.exchange(pf.early_draws, root)

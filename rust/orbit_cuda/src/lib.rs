@@ -130,6 +130,8 @@ extern "C" {
     pub fn orbit_light_cluster(ctx: *mut orbit_ctx, params: *const OrbitClusterParams, depth: *const f32, lights: *const c_void,
                                tile_masks: *mut c_void, depth_bounds: *mut c_void, unique_clusters: *mut c_void,
                                offset_count_image: *mut c_void, light_index_list: *mut c_void, capacity_indices: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_draws_scatter_ranked(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, dst_draw_buffer: *mut c_void, rank_counts: *const u32,
+                                      rank: u32, world: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
     pub fn orbit_scene_update(ctx: *mut orbit_ctx, update: *const OrbitSceneUpdate, stream: *mut c_void) -> i32;
     pub fn orbit_draws_scatter(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, dst_draw_buffer: *mut c_void, dst_first: u32,
                                total_count: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;

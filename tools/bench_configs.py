@@ -120,9 +120,22 @@ def run_c3(args, rank, world, ctx):
         gather_ok = True
         if rank == 0:
             gather_ok = bool(torch.equal(sv.peer_early.read(n_e), early) and torch.equal(sv.peer_late.read(n_l), late))
-        t = torch.tensor([t_compute, t_full, t_peer, t_gather], device=ctx.device, dtype=torch.float64)
+        # the same two exchanges with the counts kept on the device (no host round trip inside the frame)
+        t_async = {}
+        for mode in ("peer_async", "gather_async"):
+            sv.step(exchange=mode)
+            t_async[mode] = event_time(lambda: sv.step(exchange=mode))[0]
+            sv.peer_early.clear(); sv.peer_late.clear()
+            dist.barrier()
+            c_e, c_l = sv.step(exchange=mode)
+            torch.cuda.synchronize()
+            if rank == 0 or mode == "peer_async":
+                ok = bool(torch.equal(sv.peer_early.read(int(c_e.sum())), early) and torch.equal(sv.peer_late.read(int(c_l.sum())), late))
+                t_async[mode + "_ok"] = ok
+        t = torch.tensor([t_compute, t_full, t_peer, t_gather, t_async["peer_async"], t_async["gather_async"]], device=ctx.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_compute, t_full, t_peer, t_gather = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        t_async["peer_async"], t_async["gather_async"] = float(t[4]), float(t[5])
     res = {"config": "C3", "n_gpus": world, "entities": scene.n_entities, "meshlet_instances": scene.n_meshlet_instances,
            "ranges": sv.ranges, "us_compute": t_compute, "us_with_exchange": t_full,
            "gmeshlets_per_s_compute": scene.n_meshlet_instances / t_compute / 1e3,
@@ -134,6 +147,10 @@ def run_c3(args, rank, world, ctx):
         res["us_with_gather_to_rank0"] = t_gather
         res["gather_equals_allgather_on_rank0"] = gather_ok
         res["gmeshlets_per_s_with_gather"] = scene.n_meshlet_instances / t_gather / 1e3
+        res["device_side_counts"] = {"us_with_peer_exchange": t_async["peer_async"], "us_with_gather_to_rank0": t_async["gather_async"],
+                                     "peer_ok": t_async.get("peer_async_ok"), "gather_ok_on_rank0": t_async.get("gather_async_ok"),
+                                     "gmeshlets_per_s_with_gather": scene.n_meshlet_instances / t_async["gather_async"] / 1e3,
+                                     "gmeshlets_per_s_with_peer_exchange": scene.n_meshlet_instances / t_async["peer_async"] / 1e3}
     if rank == 0:
         n_early = int(early[:4].view(torch.int32).item()); n_late = int(late[:4].view(torch.int32).item())
         res["survivors_early"], res["survivors_late"] = n_early, n_late
