@@ -505,9 +505,21 @@ __global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __re
     if (gtid < head) d[gtid] = __ldcg(s + gtid);
     uint4* d4 = reinterpret_cast<uint4*>(d + head);
     const uint32_t* sb = s + head;
-    for (uint64_t i = gtid; i < body4; i += gsize) {
+    // four independent 16-byte stores per thread and iteration: remote (NVLink) stores need many of them in flight
+    uint64_t i = gtid;
+    for (; i + 3u * gsize < body4; i += 4u * gsize) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t* q = sb + 4u * (i + (uint64_t)k * gsize);
+            v[k] = make_uint4(__ldcg(q), __ldcg(q + 1), __ldcg(q + 2), __ldcg(q + 3));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) __stcg(d4 + i + (uint64_t)k * gsize, v[k]);
+    }
+    for (; i < body4; i += gsize) {
         const uint32_t a = __ldcg(sb + 4u * i), b = __ldcg(sb + 4u * i + 1u), c = __ldcg(sb + 4u * i + 2u), e = __ldcg(sb + 4u * i + 3u);
-        d4[i] = make_uint4(a, b, c, e);
+        __stcg(d4 + i, make_uint4(a, b, c, e));
     }
     const uint64_t done = head + 4u * body4;
     if (gtid < words - done) d[done + gtid] = __ldcg(s + done + gtid);
