@@ -558,10 +558,28 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
             }
             uint32_t running = lo ? s_prefix[lo - 1u] : 0u;               // outputs before record `rec`
             uint32_t rec = lo * chunk_rec;
+            // At a chunk boundary the prefix tells whether the chunk holds any survivor: empty chunks are stepped over
+            // without touching memory (a warp whose share of the outputs straddles an invisible stretch of the record
+            // list would otherwise pay one dependent load per 32 records of it), and the masks of the next group are
+            // requested before the current group is processed.
+            uint32_t cur_chunk = lo, in_chunk = 0u;                        // rec == cur_chunk * chunk_rec + in_chunk
+            auto advance = [&]() -> uint32_t {                               // next group of 32 records worth loading
+                in_chunk += 32u;
+                if (in_chunk >= chunk_rec) {
+                    in_chunk = 0u;
+                    ++cur_chunk;
+                    while (cur_chunk < nchunks && s_prefix[cur_chunk] == s_prefix[cur_chunk - 1u]) ++cur_chunk;
+                }
+                return cur_chunk < nchunks ? cur_chunk * chunk_rec + in_chunk : nrec;
+            };
+            auto load_masks = [&](uint32_t r) -> uint4 {
+                const uint32_t my = r + lane;
+                return my < nrec ? __ldcg(p.draw_masks + my) : make_uint4(0u, 0u, 0u, 0u);
+            };
+            uint4 e = load_masks(rec);
             while (running < o_end && rec < nrec) {
-                const uint32_t my = rec + lane;
-                uint4 e = make_uint4(0u, 0u, 0u, 0u);
-                if (my < nrec) e = __ldcg(p.draw_masks + my);
+                const uint32_t rec_next = advance();
+                const uint4 e_next = load_masks(rec_next);                // speculative: unused when this group ends the share
                 const uint32_t dm = e.x, entity = e.y, moff = e.z;
                 const uint32_t pc = __popc(dm);
                 uint32_t inc = pc;
@@ -594,7 +612,8 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
                     }
                 }
                 running += step_total;
-                rec += 32u;
+                rec = rec_next;
+                e = e_next;
             }
         }
     } else if (blockIdx.x == 0 && tid == 0) {

@@ -213,3 +213,35 @@ def test_contexts_are_independent_across_threads(oracle):
                 assert np.array_equal(gd[12:12 + 16 * int(ohdr[0])], orecs.view(np.uint8).reshape(-1)), (k, f, s)
                 assert int(gdraw[:4].view(np.uint32)[0]) == on and np.array_equal(gdraw[4:], od.view(np.uint8).reshape(-1)), (k, f, s)
         assert np.array_equal(mvis, hs.meshlet_visibility), k
+
+
+@pytest.mark.parametrize("pattern", ["two_ends", "single_record", "every_97th"])
+def test_sparse_survivors_with_long_empty_stretches(gpu_context, oracle, pattern):
+    """Survivors only in a few places of a long record list (pass 1 with hand-set visibility words): the emit kernel's
+    output-balanced split then hands warps shares that straddle thousands of empty records, which it steps over chunk
+    by chunk from the prefix instead of loading them."""
+    from orbit_b200 import frame
+    ctx = gpu_context
+    sc, view = scenes.config_c2(scale=0.25)
+    # a camera high above the middle of the city looking straight down: every entity is inside the frustum
+    mid = (sc.aabb_min + sc.aabb_max) / 2
+    view = scenes.perspective_view((mid[0], 2500.0, mid[2]), (0.0, -1.0, 0.001), 640, 360)
+    ds = frame.DeviceScene.upload(ctx, sc)
+    vs = frame.ViewState(ctx, ds, (view.width, view.height), name="sparse_" + pattern)
+    hs = oracle.HostScene(sc)
+    hs.entity_visibility[:] = 0xFFFFFFFF
+    words = hs.meshlet_visibility
+    words[:] = 0
+    if pattern == "two_ends":
+        words[:40] = 0xFFFFFFFF; words[-40:] = 0xFFFFFFFF
+    elif pattern == "single_record":
+        words[len(words) // 2] = 0x80000001
+    else:
+        words[::97] = 0x00010001
+    vs.entity_visibility.copy_(torch.from_numpy(hs.entity_visibility.view(np.int32)).to(ctx.device).view(vs.entity_visibility.dtype))
+    vs.meshlet_visibility.copy_(torch.from_numpy(words.view(np.int32)).to(ctx.device).view(vs.meshlet_visibility.dtype))
+    g = frame.main_pass_culling(ctx, ds, vs, view)
+    torch.cuda.synchronize()
+    o = oracle.main_pass_culling(hs, view)
+    nrec, ndraw = _cmp(oracle, g, o)
+    assert nrec > 3000 and 0 < ndraw < nrec            # long list, few survivors
