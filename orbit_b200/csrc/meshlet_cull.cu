@@ -390,10 +390,51 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
 // that many warps are resident, and the visibility words and model matrices are fetched in parallel.
 template <int R>
 struct __align__(16) PackedSmem {
-    float mv[R][kMvStride];
+    float mv[2][R][kMvStride];     // double-buffered: the next tile's matrices are built while this tile is tested
     uint32_t items[R * 32];
     uint32_t mask[R];
 };
+
+// Loads of one tile that depend only on its record words, kept in registers until the tile's turn comes:
+// model-matrix rows (16 lanes per record, two records per step) and last frame's visibility word (lane r < R).
+template <int R>
+struct PackedPrefetch {
+    float4 b[R / 2];
+    uint32_t vw;
+};
+
+template <int R>
+__device__ __forceinline__ PackedPrefetch<R> packed_issue_loads(const MeshletCullParams& p, uint32_t words, uint32_t lane) {
+    PackedPrefetch<R> f;
+    const uint32_t my_cnt = __shfl_sync(0xFFFFFFFFu, words, (lane * 4u + 2u) & 31u);
+    const uint32_t my_vo = __shfl_sync(0xFFFFFFFFu, words, (lane * 4u + 3u) & 31u);
+    f.vw = 0u;
+    if (lane < (uint32_t)R && my_cnt != 0u) f.vw = __ldcg(p.meshlet_visibility + my_vo) & (my_cnt >= 32u ? 0xFFFFFFFFu : ((1u << my_cnt) - 1u));
+#pragma unroll
+    for (int st = 0; st < R / 2; ++st) {
+        const uint32_t half = lane >> 4, e = lane & 15u;
+        const uint32_t ent = __shfl_sync(0xFFFFFFFFu, words, (2 * st + half) * 4 + 0);
+        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, words, (2 * st + half) * 4 + 2);
+        f.b[st] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cnt != 0u) f.b[st] = __ldg(p.entities + (size_t)ent * 8u + (e >> 2));
+    }
+    return f;
+}
+
+// view * model (+ largest column scale) of the tile's records from the prefetched rows (same arithmetic as tile_model_view)
+template <int R>
+__device__ __forceinline__ void packed_finish_model_view(const PackedPrefetch<R>& f, float* mv_base, uint32_t lane,
+                                                         float v0, float v1, float v2, float v3) {
+#pragma unroll
+    for (int st = 0; st < R / 2; ++st) {
+        const uint32_t half = lane >> 4, e = lane & 15u;
+        const float4 b = f.b[st];
+        mv_base[(2 * st + half) * kMvStride + e] = add(add(add(mul(v0, b.x), mul(v1, b.y)), mul(v2, b.z)), mul(v3, b.w));
+    }
+    __syncwarp();
+    if (lane < (uint32_t)R) mv_base[lane * kMvStride + 16] = largest_scale(mv_base + lane * kMvStride);
+    __syncwarp();
+}
 
 template <int R>
 __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(const __grid_constant__ MeshletCullParams p) {
@@ -403,6 +444,17 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
     PackedSmem<R>& ws = s_all[warp];
     const OrbitCullInfo& ci = p.cull;
     pdl_wait();
+    const uint32_t w_stride = gridDim.x * kMcWarps;
+    const uint32_t tile0 = blockIdx.x * kMcWarps + warp;
+    // Latency-bound kernel (a warp sees one or two tiles, each a chain of dependent loads: record words -> visibility
+    // word + model matrices -> meshlets -> material): the chain of tile t+1 is started before tile t is tested, and
+    // the first two tiles' record words are requested before the record count is known (bounded by the buffer's
+    // capacity, masked afterwards).
+    auto spec_words = [&](uint32_t tile) -> uint32_t {
+        const uint64_t rec = (uint64_t)tile * R + (lane >> 2);
+        return (lane < 4u * R && rec < p.capacity_records) ? __ldcg(p.dispatch_words + 3u + (size_t)tile * R * 4u + lane) : 0u;
+    };
+    uint32_t cur_word = spec_words(tile0), next_word = spec_words(tile0 + w_stride);
     uint32_t nrec = __ldcg(p.dispatch_words);
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
     const uint32_t chunk_rec = chunk_records(nrec);
@@ -411,46 +463,58 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
     uint32_t* const chunk_counts = p.chunk_counts + half * kMaxChunks;
     uint32_t* const draw_total = p.draw_total + half;
     const uint32_t tiles_total = (nrec + R - 1) / R;
-    const uint32_t w_stride = gridDim.x * kMcWarps;
+    if (!(lane < 4u * R && (uint64_t)tile0 * R + (lane >> 2) < nrec)) cur_word = 0u;
+    if (!(lane < 4u * R && (uint64_t)(tile0 + w_stride) * R + (lane >> 2) < nrec)) next_word = 0u;
     const uint32_t vrow_i = lane & 3u;
     const float v0 = ci.view_matrix.m[0][vrow_i], v1 = ci.view_matrix.m[1][vrow_i];
     const float v2 = ci.view_matrix.m[2][vrow_i], v3 = ci.view_matrix.m[3][vrow_i];
-    float* const mv_base = &ws.mv[0][0];
-    uint32_t warp_total = 0u;
-    for (uint32_t tile = blockIdx.x * kMcWarps + warp; tile < tiles_total; tile += w_stride) {
+    uint32_t warp_total = 0u, buf = 0u;
+    PackedPrefetch<R> cur = packed_issue_loads<R>(p, cur_word, lane);
+    // A tile none of whose records had a visible meshlet last frame (most of the list: occluded entities) needs neither
+    // matrices nor packing — that arithmetic, not memory, was what the kernel spent its issue slots on.
+    if (tile0 < tiles_total && __ballot_sync(0xFFFFFFFFu, cur.vw != 0u) != 0u)
+        packed_finish_model_view<R>(cur, &ws.mv[0][0][0], lane, v0, v1, v2, v3);
+    for (uint32_t tile = tile0; tile < tiles_total; tile += w_stride) {
         const uint32_t rec0 = tile * R;
-        uint32_t my_word = 0u;
-        if (lane < 4u * R && rec0 + (lane >> 2) < nrec) my_word = __ldcg(p.dispatch_words + 3u + (size_t)rec0 * 4u + lane);
-        const uint32_t my_cnt = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 2u) & 31u);
-        const uint32_t my_vo = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 3u) & 31u);
-        uint32_t vw = 0u;
-        if (lane < (uint32_t)R && my_cnt != 0u) vw = __ldcg(p.meshlet_visibility + my_vo) & (my_cnt >= 32u ? 0xFFFFFFFFu : ((1u << my_cnt) - 1u));
-        tile_model_view<R>(p, mv_base, my_word, lane, v0, v1, v2, v3);   // issued before vw is consumed: the loads overlap
-        uint32_t n_items = 0u;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const uint32_t m = __shfl_sync(0xFFFFFFFFu, vw, r);
-            if ((m >> lane) & 1u) ws.items[n_items + __popc(m & lt)] = ((uint32_t)r << 5) | lane;
-            n_items += __popc(m);
+        const uint32_t my_word = cur_word;
+        float* const mv_base = &ws.mv[buf][0][0];
+        const uint32_t vw = cur.vw;
+        // ---- start the next tile's chain (its words arrived while the previous tile was tested)
+        const bool has_next = tile + w_stride < tiles_total;
+        PackedPrefetch<R> nxt = packed_issue_loads<R>(p, next_word, lane);
+        uint32_t next2_word = 0u;
+        {
+            const uint32_t t2 = tile + 2u * w_stride;
+            if (t2 < tiles_total && lane < 4u * R && t2 * R + (lane >> 2) < nrec) next2_word = __ldcg(p.dispatch_words + 3u + (size_t)t2 * R * 4u + lane);
         }
-        if (lane < (uint32_t)R) ws.mask[lane] = 0u;
-        __syncwarp();
-        for (uint32_t k = 0; k * 32u < n_items; ++k) {
-            const uint32_t i = k * 32u + lane;
-            const uint32_t id = i < n_items ? ws.items[i] : 0u;
-            const uint32_t moff = __shfl_sync(0xFFFFFFFFu, my_word, (id >> 5) * 4u + 1u);
-            if (i < n_items) {
-                const uint32_t r = id >> 5, j = id & 31u;
-                const uint4* m = p.meshlets + 2u * ((size_t)moff + j);
-                const uint4 a = __ldg(m), b = __ldg(m + 1);
-                const ItemTest t = test_item<-1>(ci, mv_base + r * kMvStride, a, b.x);
-                if (draw_rule(ci, p, t.pre_visible, true, false, b.w)) atomicOr(&ws.mask[r], 1u << j);
-            }
-        }
-        __syncwarp();
+        // ---- this tile: pack the lanes whose visibility bit is set, test them
         uint32_t my_draw_mask = 0u;
-        if (lane < (uint32_t)R) my_draw_mask = ws.mask[lane];
-        __syncwarp();
+        if (__ballot_sync(0xFFFFFFFFu, vw != 0u) != 0u) {      // warp-uniform
+            uint32_t n_items = 0u;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t m = __shfl_sync(0xFFFFFFFFu, vw, r);
+                if ((m >> lane) & 1u) ws.items[n_items + __popc(m & lt)] = ((uint32_t)r << 5) | lane;
+                n_items += __popc(m);
+            }
+            if (lane < (uint32_t)R) ws.mask[lane] = 0u;
+            __syncwarp();
+            for (uint32_t k = 0; k * 32u < n_items; ++k) {
+                const uint32_t i = k * 32u + lane;
+                const uint32_t id = i < n_items ? ws.items[i] : 0u;
+                const uint32_t moff = __shfl_sync(0xFFFFFFFFu, my_word, (id >> 5) * 4u + 1u);
+                if (i < n_items) {
+                    const uint32_t r = id >> 5, j = id & 31u;
+                    const uint4* m = p.meshlets + 2u * ((size_t)moff + j);
+                    const uint4 a = __ldg(m), b = __ldg(m + 1);
+                    const ItemTest t = test_item<-1>(ci, mv_base + r * kMvStride, a, b.x);
+                    if (draw_rule(ci, p, t.pre_visible, true, false, b.w)) atomicOr(&ws.mask[r], 1u << j);
+                }
+            }
+            __syncwarp();
+            if (lane < (uint32_t)R) my_draw_mask = ws.mask[lane];
+            __syncwarp();
+        }
         {
             const uint32_t ent = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 0u) & 31u);
             const uint32_t mof = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 1u) & 31u);
@@ -459,6 +523,12 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
         const uint32_t tile_total = __reduce_add_sync(0xFFFFFFFFu, __popc(my_draw_mask));
         if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + rec0 / chunk_rec, tile_total);
         warp_total += tile_total;
+        // ---- the next tile's matrices into the other buffer; rotate
+        if (has_next && __ballot_sync(0xFFFFFFFFu, nxt.vw != 0u) != 0u) packed_finish_model_view<R>(nxt, &ws.mv[buf ^ 1u][0][0], lane, v0, v1, v2, v3);
+        buf ^= 1u;
+        cur = nxt;
+        cur_word = next_word;
+        next_word = next2_word;
     }
     pdl_launch_dependents();
     if (lane == 0u && warp_total != 0u) atomicAdd(draw_total, warp_total);
@@ -682,8 +752,11 @@ template <int R>
 static cudaError_t launch_test(const MeshletCullParams& p, int grid, cudaStream_t stream, int* occupancy) {
     const TestVariant v = variant_of(p.cull);
     if (v.packed) {
-        if (occupancy) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_packed_kernel<R>, kMcThreads, 0); return cudaSuccess; }
-        return launch_kernel(meshlet_test_packed_kernel<R>, dim3(grid), dim3(kMcThreads), 0, stream, p);
+        // the packed kernel fills its 32-lane test batches from a whole tile: with the default R = 4 a batch is 44 % full
+        // on C2, so it takes 8-record tiles instead (measured 8.9 -> 8.4 us); ORBIT_MC_RECS_PER_WARP=2 or 8 are taken as given
+        constexpr int RP = R == 4 ? 8 : R;
+        if (occupancy) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_packed_kernel<RP>, kMcThreads, 0); return cudaSuccess; }
+        return launch_kernel(meshlet_test_packed_kernel<RP>, dim3(grid), dim3(kMcThreads), 0, stream, p);
     }
     if (v.pass2) {
         if (v.proj == 0) return launch_direct<R, true, 0>(p, grid, stream, occupancy);
