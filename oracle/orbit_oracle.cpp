@@ -4,10 +4,16 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
 // library, and only as the checker / CPU baseline.  liborbit_b200.so never links, loads or calls it.
 //
-// PARITY STATUS: *unpinned by the reference*.  Thefefe/orbit has no test, golden vector or fixture for this
-// path, and neither a Vulkan implementation nor a Rust toolchain exists in the build
-// image, so the reference cannot be run here.  This file therefore restates the shaders line by line and
-// pins ONE arithmetic contract (below); the committed fixtures under tests/golden/ are outputs of THIS oracle.
+// PARITY STATUS.  Thefefe/orbit has no test, golden vector or fixture for this path, and neither a
+// Vulkan implementation nor a Rust toolchain exists in the build image, so the reference BINARY cannot be run here.
+// What can be run are its shipped GPU programs: oracle/spirv_vm interprets shaders/{depth_reduce,entity_cull,
+// meshlet_cull}.comp.spv and shaders/light_cluster/*.comp.spv, dispatched as draw_gen.rs / cluster.rs dispatch them, and
+// tests/golden/spirv_reference.json holds their outputs (tests/golden/make_spirv_golden.py). This oracle is PINNED to
+// those fixtures (tests/test_spirv_golden.py: Hi-Z texels and visibility words byte for byte, records / commands /
+// light lists as sorted sets). It stays UNPINNED with respect to a real Vulkan driver in the three places SPIR-V leaves
+// to the implementation (summation order of OpDot / OpMatrixTimes*, Log2, the sampler's texel footprint), where the
+// interpreter makes the same choices as the contract below, and for the task-shader payload and the scene update
+// (glam), which have no executable reference here. tests/golden/c1_and_clusters.json are outputs of THIS oracle.
 //
 // What each function follows (paths relative to the reference tree):
 //   hiz_build           shaders/depth_reduce.comp:14-19, loop src/passes/draw_gen.rs:538-564,
