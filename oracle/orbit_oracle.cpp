@@ -12,8 +12,8 @@
 // those fixtures (tests/test_spirv_golden.py: Hi-Z texels and visibility words byte for byte, records / commands /
 // light lists as sorted sets). It stays UNPINNED with respect to a real Vulkan driver in the three places SPIR-V leaves
 // to the implementation (summation order of OpDot / OpMatrixTimes*, Log2, the sampler's texel footprint), where the
-// interpreter makes the same choices as the contract below, and for the task-shader payload and the scene update
-// (glam), which have no executable reference here. tests/golden/c1_and_clusters.json are outputs of THIS oracle.
+// interpreter makes the same choices as the contract below, and for the scene update (glam), which has no executable
+// reference here. (The three shipped task shaders are interpreted as well and pin the payload output.) tests/golden/c1_and_clusters.json are outputs of THIS oracle.
 //
 // What each function follows (paths relative to the reference tree):
 //   hiz_build           shaders/depth_reduce.comp:14-19, loop src/passes/draw_gen.rs:538-564,

@@ -125,3 +125,39 @@ def light_cluster(params, depth, lights, log2f):
     vm.dispatch((gx, gy, gz), (256, 1, 1))
     return {"masks": masks.data.view(np.uint32).copy(), "bounds": bounds.data.view(np.uint32).copy(), "unique": unique.data.view(np.uint32).copy(),
             "image": image.levels[0].reshape(-1).copy(), "index": index.data.view(np.uint32).copy()}
+
+
+def task_shader(scene, cull_info, entity_vis, meshlet_vis, pyramid_levels, dispatch, log2f, shader="forward/forward_depth_prepass.task.spv"):
+    """The mesh-shading path's task stage (context.rs:1093-1099: vkCmdDrawMeshTasksIndirectEXT over the dispatch buffer):
+    one 32-lane workgroup per dispatch record. Returns [(record index, emitted task count, payload)] with payload =
+    [entity_index, meshlet_offset, [32 x u8 meshlet indices]] as the shader left it."""
+    vm = VM(os.path.join(SHADERS, shader), spec={0: 32}, log2f=log2f)
+    bufs = _bind_cull(vm, scene, cull_info, entity_vis, meshlet_vis, pyramid_levels)
+    bufs[D["dispatch"]] = Buffer(dispatch)
+    # push constants by member name (the three task shaders lay the block out differently); matrices stay identity,
+    # they are only read by the mesh stage
+    values = {"draw_command_buffer": D["dispatch"], "cull_info_buffer": D["cull_info"], "meshlet_buffer": D["meshlets"],
+              "entity_buffer": D["entities"], "materials_buffer": D["materials"]}
+    push = bytearray(256)
+    m = vm.m
+    for vid, inst in vm.globals.items():
+        pt = vm.types[inst.words[0]]
+        if pt[1] != 9:
+            continue
+        for i, mt in enumerate(vm.types[pt[2]][1]):
+            name, off = m.member_names.get((pt[2], i)), m.member_decor[(pt[2], i)][35][0]
+            if name in values:
+                push[off:off + 4] = struct.pack("<I", values[name])
+            elif vm.types[mt][0] == "mat":
+                push[off:off + 64] = np.eye(4, dtype=np.float32).tobytes()
+    vm.push = Buffer(bytes(push))
+    gx, gy, gz = struct.unpack("<3I", bytes(dispatch[:12]))
+    vm.dispatch((gx, gy, gz), (32, 1, 1))
+    meshlet_vis[:] = bufs[D["meshlet_vis"]].data.view(meshlet_vis.dtype)
+    out = []
+    for (g, emitted) in vm.emitted:
+        assert len(emitted) >= 1, "workgroup %s emitted nothing" % (g,)
+        counts, payload = emitted[0]
+        assert all(e[0] == counts for e in emitted)
+        out.append((g[0], counts[0], payload))
+    return out

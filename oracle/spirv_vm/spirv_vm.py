@@ -98,6 +98,7 @@ class VM:
         self.resources = {}            # (set, binding) -> {index: Buffer | Image | Sampler}
         self.push = Buffer(b"\0" * 256)
         self.trace = False
+        self.emitted = []              # task shaders: (workgroup id, [(group counts, payload)]) per workgroup
         self.blocks, self.block_order = {}, []
         self._decode()
 
@@ -246,13 +247,17 @@ class VM:
             for gy in range(groups[1]):
                 for gx in range(groups[0]):
                     invs = []
+                    shared = {}
+                    emitted = []
+                    self.emitted.append(((gx, gy, gz), emitted))
                     for z in range(lz):
                         for y in range(ly):
                             for x in range(lx):
                                 li = x + lx * (y + ly * z)
                                 b = {"local": [x, y, z], "group": [gx, gy, gz], "global": [gx * lx + x, gy * ly + y, gz * lz + z],
                                      "num_groups": list(groups), "local_index": li, "subgroup_size": subgroup,
-                                     "subgroup_inv": li % subgroup, "subgroup_id": li // subgroup, "wg_size": [lx, ly, lz]}
+                                     "subgroup_inv": li % subgroup, "subgroup_id": li // subgroup, "wg_size": [lx, ly, lz],
+                                     "shared": shared, "emit": (lambda counts, payload, e=emitted: e.append((counts, payload)))}
                                 invs.append(self._run(b))
                     self._schedule(invs, subgroup)
 
@@ -282,6 +287,17 @@ class VM:
                 key = min(by_inst)
                 group = by_inst[key]
                 kind = state[group[0]][0]
+                if kind == "barrier":
+                    # workgroup barrier: released when every live invocation of the workgroup stands at it
+                    everyone = [i for i in range(len(invs)) if alive[i]]
+                    if all(state[i][0] == "barrier" and state[i][1] == key for i in everyone):
+                        for i in everyone: advance(i)
+                        progressed = True
+                    elif any(state[i][0] != "barrier" for i in everyone):
+                        continue
+                    else:
+                        raise RuntimeError("invocations wait at different barriers")
+                    continue
                 if kind == "ballot":
                     mask = 0
                     for i in group:
@@ -321,6 +337,11 @@ class VM:
                 return Ptr("mem", self.push, 0, pt[2])
             if sc in (12, 2, 0):   # StorageBuffer / Uniform / UniformConstant: descriptor (array)
                 return Ptr("desc", (dec[34][0], dec[33][0]), 0, pt[2])
+            if sc in (4, 5402):   # Workgroup / TaskPayloadWorkgroupEXT: one instance per workgroup
+                shared = builtins["shared"]
+                if vid not in shared:
+                    shared[vid] = [self._null(pt[2])]
+                return Ptr("var", shared[vid], 0, pt[2], path=[0])
             if sc in (6, 7):  # Private / Function (module-scope private)
                 if vid not in mem_vars:
                     mem_vars[vid] = [self._null(pt[2])]
@@ -532,9 +553,9 @@ class VM:
                         store(p, new)
                         vals[a[1]] = old
                     elif op == 339:
-                        vals[a[1]] = yield ("ballot", id(inst), bool(V(a[3])))
+                        vals[a[1]] = yield ("ballot", inst.index, bool(V(a[3])))
                     elif op == 333:
-                        vals[a[1]] = yield ("elect", id(inst), None)
+                        vals[a[1]] = yield ("elect", inst.index, None)
                     elif op == 86: vals[a[1]] = (V(a[2]), V(a[3]))
                     elif op == 100: vals[a[1]] = V(a[2])[0]
                     elif op == 88:
@@ -568,7 +589,11 @@ class VM:
                         break
                     elif op == 253: return
                     elif op == 255: raise RuntimeError("OpUnreachable executed")
-                    elif op == 224: pass    # ControlBarrier: no shared memory in these shaders
+                    elif op == 224:
+                        yield ("barrier", inst.index, None)
+                    elif op == 5294:        # EmitMeshTasksEXT: ends the invocation; the group's task count + payload are recorded
+                        builtins["emit"]((V(a[0]), V(a[1]), V(a[2])), self._copy(load(a[3])) if len(a) > 3 else None)
+                        return
                     elif op == 225: pass    # MemoryBarrier
                     else:
                         raise NotImplementedError("opcode %d (line %d)" % (op, inst.line))

@@ -3,10 +3,10 @@ import struct
 
 
 class Inst:
-    __slots__ = ("op", "words", "result", "rtype", "line")
+    __slots__ = ("op", "words", "result", "rtype", "line", "index")
 
-    def __init__(self, op, words, line):
-        self.op, self.words, self.line = op, words, line
+    def __init__(self, op, words, line, index=0):
+        self.op, self.words, self.line, self.index = op, words, line, index
         self.result = self.rtype = None
 
     def __repr__(self):
@@ -49,7 +49,7 @@ class Module:
                 line = a[1]
             elif op == 317:
                 line = 0
-            inst = Inst(op, a, line)
+            inst = Inst(op, a, line, len(self.insts))
             if op in HAS_TYPE_AND_RESULT:
                 inst.rtype, inst.result = a[0], a[1]
             elif op in HAS_RESULT_ONLY:

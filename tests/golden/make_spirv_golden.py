@@ -55,6 +55,35 @@ def main():
                               "entity_visibility": S.pack(ev), "meshlet_visibility": S.pack(mv)})
                 print("cull", name, f, label, "records", hdr[0], "draws", n, "%.0fs" % (time.time() - t0), flush=True)
         out["cull"][name] = {"steps": steps, "hiz": S.pack(np.concatenate([l.reshape(-1) for l in levels])) if levels is not None else None}
+    # ---- mesh-shading path: the three shipped task shaders (payload = what orbit_meshlet_cull's task_payloads output restates)
+    out["task"] = {}
+    cases = S.cull_cases()
+    for name, kind in (("ortho_pass0", "none"), ("ortho_pass2", "write"), ("persp_two_pass_entity_occlusion_only", "write")):
+        sc, view, depth, mocc, _, _ = cases[name]
+        ev = np.zeros((sc.n_entities + 31) // 32 + 1, np.uint32)
+        mv = np.zeros(max(sc.n_visibility_words, 1), np.uint32)
+        levels = R.hiz_build(depth, O.hiz_geometry(view.width, view.height), log2f) if kind == "write" else None
+        g = O.gpu_cull_info(view, kind, mocc)
+        disp = R.entity_cull(sc, g, ev, mv, levels, sc.n_records_lod0, log2f)
+        recs = S.canon_records(disp)[1]
+        out["task"][name] = {}
+        for shader in (S.TASK_SHADERS if kind == "none" else S.TASK_SHADERS[:1]):
+            mv_t = mv.copy()
+            res = R.task_shader(sc, g, ev.copy(), mv_t, levels, disp, log2f, shader)
+            pl = S.canon_payloads([(c, p[0], p[1], p[2]) for (_, c, p) in res])
+            entry = {"payloads": S.pack(pl), "tasks": int(pl["task_count"].sum())}
+            if kind == "write" and mocc:
+                # the task shaders leave `visible` = true for lanes >= meshlet_count, so the words they store have the unused
+                # high bits set; the compute shader's words have them clear. The bits are never read.
+                mv_c = mv.copy()
+                R.meshlet_cull(sc, g, ev.copy(), mv_c, levels, disp, sc.n_meshlet_instances, log2f)
+                for r in recs:
+                    cnt = int(r["meshlet_count"]); used = 0xFFFFFFFF if cnt >= 32 else (1 << cnt) - 1
+                    wt, wc = int(mv_t[r["visibility_offset"]]), int(mv_c[r["visibility_offset"]])
+                    assert wt & used == wc & used and wt | used == 0xFFFFFFFF and wc & ~used & 0xFFFFFFFF == 0
+                entry["meshlet_visibility_comp_semantics"] = S.pack(mv_c)
+            out["task"][name][shader] = entry
+            print("task", name, shader, "records", len(pl), "tasks", entry["tasks"], "%.0fs" % (time.time() - t0), flush=True)
     for name, (p, depth, lights) in S.cluster_cases().items():
         c = S.canon_clusters(R.light_cluster(p, depth, lights, log2f))
         out["clusters"][name] = {"header": c["header"], "total": c["total"], "masks": S.pack(c["masks"]), "bounds": S.pack(c["bounds"]),

@@ -115,3 +115,21 @@ def canon_clusters(res):
     counts = np.array([len(x) for x in lists], np.uint32)
     return {"header": [int(x) for x in res["unique"][:4]], "masks": np.asarray(res["masks"], np.uint32), "bounds": np.asarray(res["bounds"], np.uint32),
             "active": active, "counts": counts, "lists": flat, "total": int(res["index"][0])}
+
+
+TASK_SHADERS = ("forward/forward_depth_prepass.task.spv", "forward/forward.task.spv", "shadow/shadow.task.spv")
+
+
+def canon_payloads(entries):
+    """entries: iterable of (task_count, entity_index, meshlet_offset, indices) -> task_payload_dtype array sorted by
+    (entity_index, meshlet_offset), index bytes beyond the count zeroed (the shader leaves them undefined)."""
+    out = np.zeros(len(entries), L.task_payload_dtype)
+    for i, (c, e, o, idx) in enumerate(entries):
+        out[i]["task_count"], out[i]["entity_index"], out[i]["meshlet_offset"] = c, e, o
+        out[i]["meshlet_indices"][:c] = np.asarray(idx[:c], np.uint8)
+    return np.sort(out, order=["entity_index", "meshlet_offset"])
+
+
+def canon_payload_buffer(buf, nrec):
+    tp = np.frombuffer(bytes(buf), L.task_payload_dtype)[:nrec]
+    return canon_payloads([(int(t["task_count"]), int(t["entity_index"]), int(t["meshlet_offset"]), t["meshlet_indices"].tolist()) for t in tp])

@@ -91,3 +91,30 @@ def test_cuda_clusters_match_shipped_light_cluster_shaders(gpu_context, golden):
         assert c["header"] == g["header"] and c["total"] == g["total"], name
         for k in ("masks", "bounds", "active", "counts", "lists"):
             assert S.matches(g[k], c[k]), (name, k)
+
+
+def test_cuda_task_payloads_match_shipped_task_shaders(gpu_context, golden):
+    import torch
+    from orbit_b200 import frame
+    from orbit_b200.passes import OcclusionCullInfo
+    ctx = gpu_context
+    cases = S.cull_cases()
+    for name, kind in (("ortho_pass0", "none"), ("ortho_pass2", "write"), ("persp_two_pass_entity_occlusion_only", "write")):
+        sc, view, depth, mocc, _, _ = cases[name]
+        ds = frame.DeviceScene.upload(ctx, sc)
+        vs = frame.ViewState(ctx, ds, (view.width, view.height), name="spvt_" + name)
+        mvis = vs.meshlet_visibility if mocc else None
+        if kind == "write":
+            vs.depth_pyramid.update(torch.from_numpy(depth).to(ctx.device))
+            oc = OcclusionCullInfo("write", vs.entity_visibility, mvis, vs.depth_pyramid, noskip_alphamode=0, aspect_ratio=view.aspect)
+        else:
+            oc = OcclusionCullInfo("none")
+        payloads = torch.zeros(L.TASK_PAYLOAD_STRIDE * sc.n_records_lod0, dtype=torch.uint8, device=ctx.device)
+        disp, _ = frame.cull_pass(ctx, "spvt_" + name, ds, frame.cull_info_for(view, oc), task_payloads=payloads)
+        torch.cuda.synchronize()
+        nrec = int(disp[:4].cpu().numpy().view(np.uint32)[0])
+        pl = S.canon_payload_buffer(payloads.cpu().numpy(), nrec)
+        for shader, entry in golden["task"][name].items():
+            assert S.matches(entry["payloads"], pl), (name, shader)
+            if "meshlet_visibility_comp_semantics" in entry:
+                assert S.matches(entry["meshlet_visibility_comp_semantics"], vs.meshlet_visibility.cpu().numpy().view(np.uint32)), (name, shader)

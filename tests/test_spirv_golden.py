@@ -79,3 +79,21 @@ def test_interpreter_reproduces_a_fixture_entry(oracle, golden):
     draws = R.meshlet_cull(sc, g, ev, mv, None, disp, sc.n_meshlet_instances, log2f)
     step = golden["cull"]["ortho_pass0"]["steps"][0]
     assert S.matches(step["records"], S.canon_records(disp)[1]) and S.matches(step["draws"], S.canon_draws(draws)[1])
+
+
+def test_task_payloads_match_shipped_task_shaders(oracle, golden):
+    """forward_depth_prepass.task / forward.task / shadow.task (shipped SPIR-V, interpreted) vs the oracle's payload output."""
+    cases = S.cull_cases()
+    for name, kind in (("ortho_pass0", "none"), ("ortho_pass2", "write"), ("persp_two_pass_entity_occlusion_only", "write")):
+        sc, view, depth, mocc, _, _ = cases[name]
+        hs = oracle.HostScene(sc)
+        if kind == "write":
+            hs.update_pyramid(depth)
+        out = oracle.cull_pass(hs, oracle.gpu_cull_info(view, kind, mocc), task_payloads=True)
+        nrec = int(out[0][:4].view(np.uint32)[0])
+        pl = S.canon_payload_buffer(out[2], nrec)
+        for shader, entry in golden["task"][name].items():
+            assert S.matches(entry["payloads"], pl), (name, shader)
+            assert int(pl["task_count"].sum()) == entry["tasks"] > 0
+            if "meshlet_visibility_comp_semantics" in entry:
+                assert S.matches(entry["meshlet_visibility_comp_semantics"], hs.meshlet_visibility), (name, shader, "visibility")
