@@ -45,7 +45,7 @@ def main():
             for label, kind in passes:
                 if kind == "write":
                     levels = R.hiz_build(depth, info, log2f)
-                g = O.gpu_cull_info(view, kind, mocc)
+                g = S.tweak_gpu_cull_info(O.gpu_cull_info(view, kind, mocc), name)
                 pyr = levels if kind == "write" else None
                 disp = R.entity_cull(sc, g, ev, mv, pyr, sc.n_records_lod0, log2f)
                 draws = R.meshlet_cull(sc, g, ev, mv, pyr, disp, sc.n_meshlet_instances, log2f)

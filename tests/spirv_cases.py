@@ -35,7 +35,39 @@ def cull_cases():
     v = scenes.orthographic_view(centre - d * 100.0, d, 256, 256, half_width=60.0, near=-20.0, far=250.0)
     out["ortho_pass0"] = (sc, v, None, True, 1, "pass0")
     out["ortho_pass2"] = (sc, v, scenes.make_depth(sc, v), True, 1, "pass2_only")
+    # 12 cull planes, LOD range clamped to [1, 2], model matrices with a bottom row != (0,0,0,1) (the p / p.w division)
+    sc, _ = scenes.config_c1(scale=0.08, lods=(120, 60, 30, 15))
+    m = sc.entities["model_matrix"]            # [n][col][row]
+    rng = np.random.default_rng(5)
+    m[:, 3, 3] = rng.uniform(0.7, 1.4, len(m)).astype(np.float32)
+    m[::3, 0, 3] = rng.uniform(-0.01, 0.01, len(m[::3])).astype(np.float32)
+    v = _persp(320, 180, lod=(4.0, 1.3))
+    extra = []
+    for _ in range(7):
+        nrm = rng.normal(size=3); nrm /= np.linalg.norm(nrm)
+        extra.append([nrm[0], nrm[1], nrm[2], 40.0])
+    v.planes = np.vstack([v.planes, np.array(extra)])
+    v.lod_range = (1, 3)
+    out["persp_planes12_nonaffine_lodclamp"] = (sc, v, scenes.make_depth(sc, v), True, 2, "two_pass")
+    # every alpha mode passes the filter, masked + transparent are "noskip" (drawn in pass 2 even if visible last frame)
+    sc, _ = scenes.config_c1(scale=0.06, lods=(100, 40))
+    v = _persp(256, 144)
+    out["persp_noskip_alpha"] = (sc, v, scenes.make_depth(sc, v), True, 2, "two_pass")
     return out
+
+
+# per-case CullInfo fields that differ from the callers' defaults (draw_gen.rs:105-119)
+CULL_OPTS = {"persp_noskip_alpha": {"alpha_filter": 1 | 2 | 4, "noskip": 2 | 4}}
+
+
+def tweak_gpu_cull_info(g, name):
+    """Applies CULL_OPTS to a packed GpuCullInfo the way CullInfo::to_gpu would have (noskip only exists in pass 2)."""
+    o = CULL_OPTS.get(name, {})
+    if "alpha_filter" in o:
+        g.alpha_mode_flags = o["alpha_filter"]
+    if "noskip" in o and g.occlusion_pass == 2:
+        g.noskip_alpha_mode = o["noskip"]
+    return g
 
 
 def cluster_cases():

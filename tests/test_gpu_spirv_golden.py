@@ -42,18 +42,22 @@ def test_cuda_cull_passes_match_shipped_shaders(gpu_context, golden):
         vs = frame.ViewState(ctx, ds, (view.width, view.height), name="spv_" + name)
         d_depth = torch.from_numpy(depth).to(ctx.device) if depth is not None else None
         mvis = vs.meshlet_visibility if mocc else None
+        opts = S.CULL_OPTS.get(name, {})
         k = 0
         for f in range(frames):
             passes = {"two_pass": [("early", "read"), ("late", "write")], "pass0": [("pass0", "none")], "pass2_only": [("late", "write")]}[protocol]
             for label, kind in passes:
                 if kind == "write":
                     vs.depth_pyramid.update(d_depth)
-                    oc = OcclusionCullInfo("write", vs.entity_visibility, mvis, vs.depth_pyramid, noskip_alphamode=0, aspect_ratio=view.aspect)
+                    oc = OcclusionCullInfo("write", vs.entity_visibility, mvis, vs.depth_pyramid, noskip_alphamode=opts.get("noskip", 0), aspect_ratio=view.aspect)
                 elif kind == "read":
                     oc = OcclusionCullInfo("read", vs.entity_visibility, mvis)
                 else:
                     oc = OcclusionCullInfo("none")
-                disp, draws = frame.cull_pass(ctx, "spv_%s_%s" % (name, label), ds, frame.cull_info_for(view, oc))
+                info = frame.cull_info_for(view, oc)
+                if "alpha_filter" in opts:
+                    info.alpha_mode_filter = opts["alpha_filter"]
+                disp, draws = frame.cull_pass(ctx, "spv_%s_%s" % (name, label), ds, info)
                 torch.cuda.synchronize()
                 step = g["steps"][k]; k += 1
                 hdr, recs = S.canon_records(disp.cpu().numpy())

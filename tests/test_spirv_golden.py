@@ -36,7 +36,7 @@ def test_cull_passes_match_shipped_entity_and_meshlet_shaders(oracle, golden):
             for label, kind in passes:
                 if kind == "write":
                     hs.update_pyramid(depth)
-                out = oracle.cull_pass(hs, oracle.gpu_cull_info(view, kind, mocc))
+                out = oracle.cull_pass(hs, S.tweak_gpu_cull_info(oracle.gpu_cull_info(view, kind, mocc), name))
                 step = g["steps"][k]; k += 1
                 assert (step["frame"], step["pass"]) == (f, label)
                 hdr, recs = S.canon_records(out[0])
