@@ -403,7 +403,8 @@ def run_ours(args, rank, world, local_rank):
 
 
 def cpu_baseline_sample(scene, view, depth_np, frames=4):
-    """The oracle port timed on this box's host cores: a bounded sample of the same workload."""
+    """The oracle port timed on this box's host cores: a bounded sample of the same workload (all cores: 4 frames; one
+    core: 1 frame; SURVEY §8d asks for both)."""
     import oracle_ref as O
     O.build()
     hs = O.HostScene(scene)
@@ -414,9 +415,15 @@ def cpu_baseline_sample(scene, view, depth_np, frames=4):
         O.depth_prepass_culling(hs, view, depth_np)
     dt = (time.perf_counter() - t0) / frames
     cores = int(O.lib().oracle_threads())
+    prev = O.lib().oracle_set_threads(1)
+    t0 = time.perf_counter()
+    O.depth_prepass_culling(hs, view, depth_np)
+    dt1 = time.perf_counter() - t0
+    O.lib().oracle_set_threads(prev)
     return {"value": scene.n_meshlet_instances / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
             "ms_per_step": dt * 1e3,
-            "sample": "%d whole C2 steady-state frames (early+Hi-Z+late) on the oracle port, OpenMP over %d host threads" % (frames, cores)}
+            "sample": "%d whole C2 steady-state frames (early+Hi-Z+late) on the oracle port, OpenMP over %d host threads" % (frames, cores),
+            "single_thread": {"value": scene.n_meshlet_instances / dt1 / 1e9, "ms_per_step": dt1 * 1e3, "sample": "1 frame, 1 thread"}}
 
 
 def main():

@@ -278,6 +278,19 @@ int oracle_threads(void) {
 #endif
 }
 
+// Number of host threads the parallel loops use from now on (bench.py reports a single-thread figure beside the
+// all-cores one). Returns the previous value.
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+    const int prev = omp_get_max_threads();
+    if (n > 0) omp_set_num_threads(n);
+    return prev;
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 void oracle_hiz_geometry(uint32_t dw, uint32_t dh, OrbitHizInfo* out) { hiz_geometry(dw, dh, out); }
 
 float oracle_log2f(float x) { return orbit_log2f(x); }

@@ -44,6 +44,7 @@ def lib():
         h = C.CDLL(LIB_PATH)
         vp, u32, u64, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float
         h.oracle_threads.restype = C.c_int
+        h.oracle_set_threads.restype = C.c_int; h.oracle_set_threads.argtypes = [C.c_int]
         h.oracle_hiz_geometry.argtypes = [u32, u32, C.POINTER(L.HizInfo)]
         h.oracle_log2f.restype = f32; h.oracle_log2f.argtypes = [f32]
         h.oracle_hiz_level.restype = u32; h.oracle_hiz_level.argtypes = [f32, u32]
