@@ -10,6 +10,7 @@ import numpy as np
 from spirv_vm import VM, Buffer, Image, Sampler
 
 SHADERS = "/root/reference/shaders"
+CONTRACT_FMA = False            # sensitivity experiments (tools/spirv_sensitivity.py) flip this; fixtures are made with False
 REDUCE_MIN_SAMPLER = 6          # shaders/include/common.glsl:13
 # descriptor indices handed out to the resources of one run (any distinct numbers do)
 D = {"entity_draws": 3, "mesh_infos": 4, "dispatch": 5, "entities": 6, "cull_info": 7, "meshlets": 8, "draws": 9, "materials": 10,
@@ -27,7 +28,7 @@ class Samplers(dict):
 
 def hiz_build(depth, info, log2f=None):
     """DepthPyramid::update (draw_gen.rs:538-564): one depth_reduce dispatch per mip, each sampling the previous one."""
-    vm = VM(os.path.join(SHADERS, "depth_reduce.comp.spv"), log2f=log2f)
+    vm = VM(os.path.join(SHADERS, "depth_reduce.comp.spv"), log2f=log2f, contract_fma=CONTRACT_FMA)
     vm.resources[(1, 0)] = Samplers()
     levels, src = [], np.ascontiguousarray(depth, np.float32)
     for l in range(info.levels):
@@ -60,7 +61,7 @@ def _bind_cull(vm, scene, cull_info, entity_vis, meshlet_vis, pyramid_levels):
 def entity_cull(scene, cull_info, entity_vis, meshlet_vis, pyramid_levels, record_capacity, log2f):
     """create_meshlet_dispatch_command (draw_gen.rs:327-380). Returns the MeshletDispatchBuffer bytes (records in the order
     the VM's invocations appended them); entity_vis is updated in place in pass 2."""
-    vm = VM(os.path.join(SHADERS, "entity_cull.comp.spv"), spec={0: 32}, log2f=log2f)    # MESHLET_DISPATCH_SIZE = task workgroup size 32
+    vm = VM(os.path.join(SHADERS, "entity_cull.comp.spv"), spec={0: 32}, log2f=log2f, contract_fma=CONTRACT_FMA)    # MESHLET_DISPATCH_SIZE = task workgroup size 32
     bufs = _bind_cull(vm, scene, cull_info, entity_vis, meshlet_vis, pyramid_levels)
     out = np.zeros(12 + 16 * record_capacity, np.uint8)
     out[:12] = np.frombuffer(struct.pack("<3I", 0, 1, 1), np.uint8)                        # fill_buffer + {.,1,1}: draw_gen.rs:356-363
@@ -74,7 +75,7 @@ def entity_cull(scene, cull_info, entity_vis, meshlet_vis, pyramid_levels, recor
 
 def meshlet_cull(scene, cull_info, entity_vis, meshlet_vis, pyramid_levels, dispatch, draw_capacity, log2f):
     """create_meshlet_draw_commands (draw_gen.rs:382-435): dispatch_indirect over the record count."""
-    vm = VM(os.path.join(SHADERS, "meshlet_cull.comp.spv"), spec={0: 32}, log2f=log2f)
+    vm = VM(os.path.join(SHADERS, "meshlet_cull.comp.spv"), spec={0: 32}, log2f=log2f, contract_fma=CONTRACT_FMA)
     bufs = _bind_cull(vm, scene, cull_info, entity_vis, meshlet_vis, pyramid_levels)
     bufs[D["dispatch"]] = Buffer(dispatch)
     out = np.zeros(4 + 28 * draw_capacity, np.uint8)
@@ -101,7 +102,7 @@ def light_cluster(params, depth, lights, log2f):
     index = Buffer(np.zeros(1 + cap, np.uint32))
     image = Image([np.zeros((cz, cy, cx, 2), np.uint32)])
     # ---- mark_active (cluster.rs:399-477)
-    vm = VM(os.path.join(SHADERS, "light_cluster/mark_active.comp.spv"), log2f=log2f)
+    vm = VM(os.path.join(SHADERS, "light_cluster/mark_active.comp.spv"), log2f=log2f, contract_fma=CONTRACT_FMA)
     vm.resources[(0, 0)] = {DD["masks"]: masks, DD["bounds"]: bounds}
     vm.resources[(1, 0)] = Samplers()
     vm.resources[(1, 7)] = {DD["depth"]: Image([np.ascontiguousarray(depth, np.float32)])}
@@ -109,7 +110,7 @@ def light_cluster(params, depth, lights, log2f):
                                  DD["depth"], 1, DD["masks"], DD["bounds"]))
     vm.dispatch(((w + 7) // 8, (h + 7) // 8, 1), (8, 8, 1))
     # ---- compaction (cluster.rs:479-517)
-    vm = VM(os.path.join(SHADERS, "light_cluster/active_cluster_compaction.comp.spv"), log2f=log2f)
+    vm = VM(os.path.join(SHADERS, "light_cluster/active_cluster_compaction.comp.spv"), log2f=log2f, contract_fma=CONTRACT_FMA)
     vm.resources[(0, 0)] = {DD["masks"]: masks, DD["unique"]: unique}
     vm.push = Buffer(struct.pack("<5I", cx, cy, cz, DD["masks"], DD["unique"]))
     vm.dispatch(((cx + 3) // 4, (cy + 3) // 4, (cz + 3) // 4), (4, 4, 4))
@@ -117,7 +118,7 @@ def light_cluster(params, depth, lights, log2f):
     info = type(ci).from_buffer_copy(bytes(ci))
     info.unique_cluster_buffer, info.cluster_offset_image, info.light_index_buffer = DD["unique"], DD["image"], DD["index"]
     info.depth_bounds_buffer, info.global_light_list = DD["bounds"], DD["lights"]
-    vm = VM(os.path.join(SHADERS, "light_cluster/light_culling.comp.spv"), log2f=log2f)
+    vm = VM(os.path.join(SHADERS, "light_cluster/light_culling.comp.spv"), log2f=log2f, contract_fma=CONTRACT_FMA)
     vm.resources[(0, 0)] = {DD["unique"]: unique, DD["bounds"]: bounds, DD["index"]: index, DD["lights"]: Buffer(lights), DD["info"]: Buffer(bytes(info))}
     vm.resources[(2, 0)] = {DD["image"]: image}
     vm.push = Buffer(struct.pack("<I", DD["info"]))
@@ -131,7 +132,7 @@ def task_shader(scene, cull_info, entity_vis, meshlet_vis, pyramid_levels, dispa
     """The mesh-shading path's task stage (context.rs:1093-1099: vkCmdDrawMeshTasksIndirectEXT over the dispatch buffer):
     one 32-lane workgroup per dispatch record. Returns [(record index, emitted task count, payload)] with payload =
     [entity_index, meshlet_offset, [32 x u8 meshlet indices]] as the shader left it."""
-    vm = VM(os.path.join(SHADERS, shader), spec={0: 32}, log2f=log2f)
+    vm = VM(os.path.join(SHADERS, shader), spec={0: 32}, log2f=log2f, contract_fma=CONTRACT_FMA)
     bufs = _bind_cull(vm, scene, cull_info, entity_vis, meshlet_vis, pyramid_levels)
     bufs[D["dispatch"]] = Buffer(dispatch)
     # push constants by member name (the three task shaders lay the block out differently); matrices stay identity,

@@ -90,7 +90,10 @@ class Wait(Exception):
 
 
 class VM:
-    def __init__(self, path, spec=None, log2f=None):
+    def __init__(self, path, spec=None, log2f=None, contract_fma=False):
+        # contract_fma=True: a*b+c chains in OpDot / OpMatrixTimesVector are fused the way an optimising driver compiler
+        # typically does (sensitivity experiments only; the fixtures use the contract's unfused, left-to-right sums)
+        self.contract_fma = contract_fma
         self.m = m = Module(path)
         self.spec = spec or {}
         self.log2f = log2f or (lambda x: F32(math.log2(float(x))) if x > 0 else F32(-np.inf))
@@ -419,16 +422,18 @@ class VM:
         def signed(v, w):
             return v - (1 << w) if v >> (w - 1) else v
 
+        fuse = self.contract_fma
+
         def dot(a, b):
             acc = a[0] * b[0]
-            for i in range(1, len(a)): acc = F32(acc + a[i] * b[i])
+            for i in range(1, len(a)): acc = fma32(a[i], b[i], acc) if fuse else F32(acc + a[i] * b[i])
             return acc
 
         def mat_vec(M, v):
             out = []
             for r in range(len(M[0])):
                 acc = M[0][r] * v[0]
-                for c in range(1, len(M)): acc = F32(acc + M[c][r] * v[c])
+                for c in range(1, len(M)): acc = fma32(M[c][r], v[c], acc) if fuse else F32(acc + M[c][r] * v[c])
                 out.append(acc)
             return out
 
