@@ -53,6 +53,10 @@ def cull_cases():
     sc, _ = scenes.config_c1(scale=0.06, lods=(100, 40))
     v = _persp(256, 144)
     out["persp_noskip_alpha"] = (sc, v, scenes.make_depth(sc, v), True, 2, "two_pass")
+    # BASELINE config C1 at full size (1 k entities / 100 k meshlets; the reference's own CPU-runnable case), 640x360 view
+    sc, _ = scenes.config_c1()
+    v = _persp(640, 360, lod=(16.0, 2.0))
+    out["c1_full_size"] = (sc, v, scenes.make_depth(sc, v), True, 2, "two_pass")
     return out
 
 
