@@ -34,7 +34,8 @@ struct orbit_ctx {
     // scan scratch
     unsigned long long* status = nullptr;
     size_t status_capacity = 0;       // descriptors
-    unsigned int* counters = nullptr; // [0]=ticket [1]=done [2]=hiz ticket [3]=scan epoch (device-advanced) [4]=meshlet survivor total
+    unsigned int* counters = nullptr; // 16 words: [0] ticket, [1] done, [2] hiz ticket, [3] scan epoch (device-advanced), [4,5] meshlet survivor
+                                      // totals per parity, [6,7] parity words A/B of the meshlet stage, [8] scene-update cursor snapshot
     // device-written status, pinned + mapped
     OrbitStatus* status_host = nullptr;
     OrbitStatus* status_dev = nullptr;

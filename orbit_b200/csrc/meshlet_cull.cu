@@ -803,6 +803,4 @@ int meshlet_emit_max_ctas_per_sm() {
     return n;
 }
 
-int meshlet_cull_tile_records(int recs_per_warp) { return (recs_per_warp == 2 || recs_per_warp == 8) ? recs_per_warp : 4; }
-
 }  // namespace orbit

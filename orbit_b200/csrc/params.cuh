@@ -97,7 +97,6 @@ cudaError_t launch_meshlet_cull(const MeshletCullParams&, int recs_per_warp, int
 int meshlet_emit_max_ctas_per_sm();
 int meshlet_cull_max_ctas_per_sm(const MeshletCullParams&, int recs_per_warp);
 int meshlet_cull_variant_index(const OrbitCullInfo&);
-int meshlet_cull_tile_records(int recs_per_warp);
 cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t);
 int entity_cull_max_ctas_per_sm();
 cudaError_t launch_hiz_build(const HizBuildParams&, cudaStream_t);

@@ -47,7 +47,7 @@ def check_case(ctx, oracle, t, slots, vo, cursor, mi, capacity=1 << 26):
     return o_ovf, g_vo, g_cur
 
 
-@pytest.mark.parametrize("n", [1, 31, 256, 257, 5000, 70001])
+@pytest.mark.parametrize("n", [1, 31, 256, 257, 5000, 70001, 300001])   # the last one grows the per-tile scratch (> 1024 tiles)
 def test_scene_update_matches_oracle(gpu_context, oracle, n):
     t, slots, vo, cursor = random_entities(n, 50, 100 + n)
     check_case(gpu_context, oracle, t, slots, vo, cursor, random_mesh_infos(50, n))
