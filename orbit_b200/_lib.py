@@ -88,8 +88,36 @@ def host_lib():
         h = C.CDLL(path)
         h.orbit_host_frame_loop.restype = C.c_int
         h.orbit_host_frame_loop.argtypes = [C.c_void_p, C.POINTER(L.HostFrame), C.c_uint32, C.POINTER(L.HostFrameIO), C.c_uint32, C.c_uint32]
+        h.orbit_host_pinned_alloc.restype = C.c_void_p
+        h.orbit_host_pinned_alloc.argtypes = [C.c_uint64, C.c_int]
+        h.orbit_host_pinned_free.restype = None
+        h.orbit_host_pinned_free.argtypes = [C.c_void_p]
         _host = h
     return _host
+
+
+class PinnedBuffer:
+    """Pinned host memory from the host driver library (optionally write-combined), viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes, write_combined=False):
+        import numpy as np
+        self.nbytes = int(nbytes)
+        self.ptr = host_lib().orbit_host_pinned_alloc(self.nbytes, 1 if write_combined else 0)
+        if not self.ptr:
+            raise MemoryError("cudaHostAlloc(%d bytes) failed" % self.nbytes)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr))
+
+    def data_ptr(self):
+        return self.ptr
+
+    def numel(self):
+        return self.nbytes
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            host_lib().orbit_host_pinned_free(self.ptr)
+            self.ptr = None
 
 
 def check(code, what):

@@ -45,6 +45,16 @@ typedef struct OrbitHostFrameIO {
 uint32_t orbit_host_sizeof_frame(void) { return (uint32_t)sizeof(OrbitHostFrame); }
 uint32_t orbit_host_sizeof_io(void) { return (uint32_t)sizeof(OrbitHostFrameIO); }
 
+// Pinned host staging memory for the loop's inputs. write_combined != 0: cudaHostAllocWriteCombined — the CPU only ever
+// writes these buffers and the copy engines read them without snooping the CPU caches, which is what limits the aggregate
+// host-to-device rate when several GPUs pull their inputs at once.
+void* orbit_host_pinned_alloc(uint64_t bytes, int write_combined) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void orbit_host_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
 #define CU_OK(x) do { if ((x) != cudaSuccess) return ORBIT_ERR_CUDA; } while (0)
 #define OR_OK(x) do { int rc_ = (x); if (rc_ != ORBIT_OK) return rc_; } while (0)
 
