@@ -57,8 +57,11 @@ def time_frame(ctx, copies, reps=7, per_graph=8):
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "sweep"
-    scene, _ = scenes.config_c2()
-    view = bench.c2_view(scenes, scene, 0)
+    if os.environ.get("KBENCH_CONFIG", "c2") == "c3":      # per-stage times of the 50 M-meshlet instanced 4K view
+        scene, view = scenes.config_c3()
+    else:
+        scene, _ = scenes.config_c2()
+        view = bench.c2_view(scenes, scene, 0)
     depth_np = scenes.make_depth(scene, view)
     configs = [(None, None)] if which == "default" else list(itertools.product([2, 4, 8], [2, 3, 4, 6]))
     for rpw, cps in configs:
