@@ -155,7 +155,9 @@ class Context:
     def create_transient(self, name, nbytes):
         t = self._transients.get(name)
         if t is None or t.numel() < nbytes:
-            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            # zero-filled once at creation: the stages read ahead of the device-side counts (orbit_cuda.h, conventions) and
+            # never use what they find there, but tools like compute-sanitizer initcheck would flag the loads
+            t = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
             self._transients[name] = t
         return t
 
