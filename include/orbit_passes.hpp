@@ -147,6 +147,19 @@ private:
     orbit_ctx* ctx_; orbit_hiz* hiz_ = nullptr; uint32_t w_ = 0, h_ = 0;
 };
 
+// SceneData::update_scene, scene.rs:404-492 (mesh part): the caller owns the device arrays (transforms, mesh slots, visibility
+// offsets, the allocator's cursor word) and the two output buffers; `import_to_graph` hands them to the culling passes.
+struct SceneData {
+    OrbitSceneUpdate buffers;   // device pointers + n_entities + visibility_capacity_words (see orbit_cuda.h)
+    void update_scene(orbit_ctx* ctx, const AssetGraphData& assets, void* stream) {
+        OrbitSceneUpdate u = buffers;
+        u.mesh_infos = assets.mesh_info_buffer;
+        check(orbit_scene_update(ctx, &u, stream), "SceneData::update_scene");
+    }
+    // scene.rs:494-502. entity_draw_count is the host's upper bound; the kernels clamp to the device-side count.
+    SceneGraphData import_to_graph() const { return SceneGraphData{buffers.n_entities, buffers.entity_draws, buffers.entity_data}; }
+};
+
 // cluster.rs:15-72
 struct ClusterSettings {
     uint32_t px_size_power = 3, screen_resolution[2] = {0, 0}, z_slice_count = 32, tile_size_px_override = 0;

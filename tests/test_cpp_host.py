@@ -31,6 +31,10 @@ int main() {
     g = o.to_gpu(); fwrite(&g, sizeof(g), 1, stdout);
     ClusterSettings s; s.screen_resolution[0] = 1920; s.screen_resolution[1] = 1080; float zs, zb; s.cluster_grid_info(0.01f, zs, zb);
     fwrite(&zs, 4, 1, stdout); fwrite(&zb, 4, 1, stdout);
+    SceneData sd{}; sd.buffers.n_entities = 7;                                   // compiles + links; no GPU call without a context
+    SceneGraphData sg = sd.import_to_graph();
+    if (sg.entity_draw_count != 7) return 3;
+    try { sd.update_scene(nullptr, AssetGraphData{nullptr, nullptr, nullptr}, nullptr); return 4; } catch (const std::exception&) {}
     return 0;
 }
 '''
