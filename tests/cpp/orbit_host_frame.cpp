@@ -4,6 +4,8 @@
 // Test program: tests/test_gpu_cpp_host.py writes the inputs, runs this, and compares every output with the oracle.
 //
 //   orbit_host_frame <dir>     reads <dir>/{meta,meshlets,mesh_infos,materials,entities,entity_draws,depth}.bin
+//                              and, when present, <dir>/{transforms,mesh_slots}.bin: the entity buffers are then produced on
+//                              the GPU by SceneData::update_scene (orbit_scene_update) instead of being uploaded
 //                              writes <dir>/f<k>_{early,late}_{dispatch,draws}.bin, entity_vis.bin, meshlet_vis.bin, hiz.bin
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -36,6 +38,7 @@ static void write_file(const std::string& p, const void* d, size_t n) {
     std::fclose(f);
 }
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); std::exit(3); } } while (0)
+static void dump(const std::string& p, const void* d, size_t n);
 static void* upload(const std::vector<unsigned char>& h) {
     void* d = nullptr; CU(cudaMalloc(&d, h.size() ? h.size() : 16)); CU(cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice)); return d;
 }
@@ -53,6 +56,28 @@ int main(int argc, char** argv) {
     cudaStream_t stream; CU(cudaStreamCreate(&stream));
     AssetGraphData assets{upload(read_file(dir + "/mesh_infos.bin")), upload(read_file(dir + "/meshlets.bin")), upload(read_file(dir + "/materials.bin"))};
     SceneGraphData scene{m.n_entities, upload(read_file(dir + "/entity_draws.bin")), upload(read_file(dir + "/entities.bin"))};
+    {   // optional: build the entity buffers with the scene update (scene.rs:404-492) from Transforms + mesh slots
+        FILE* probe = std::fopen((dir + "/transforms.bin").c_str(), "rb");
+        if (probe) {
+            std::fclose(probe);
+            SceneData sd{};
+            std::vector<unsigned char> vo((size_t)m.n_entities * 4, 0xFF);            // no visibility ranges yet
+            std::vector<unsigned char> cursor(4, 0);
+            sd.buffers.transforms = (const OrbitTransform*)upload(read_file(dir + "/transforms.bin"));
+            sd.buffers.mesh_slots = (const uint32_t*)upload(read_file(dir + "/mesh_slots.bin"));
+            sd.buffers.visibility_offsets = (uint32_t*)upload(vo);
+            sd.buffers.visibility_cursor = (uint32_t*)upload(cursor);
+            sd.buffers.n_entities = m.n_entities; sd.buffers.visibility_capacity_words = 1u << 26;
+            void *ed = nullptr, *dr = nullptr;
+            CU(cudaMalloc(&ed, (size_t)m.n_entities * 128)); CU(cudaMalloc(&dr, 4 + (size_t)m.n_entities * 12));
+            sd.buffers.entity_data = ed; sd.buffers.entity_draws = dr;
+            sd.update_scene(ctx, assets, stream);
+            scene = sd.import_to_graph();
+            CU(cudaStreamSynchronize(stream));
+            dump(dir + "/entity_data_out.bin", ed, (size_t)m.n_entities * 128);
+            dump(dir + "/entity_draws_out.bin", dr, 4 + (size_t)m.n_entities * 12);
+        }
+    }
     float* depth = (float*)upload(read_file(dir + "/depth.bin"));
     uint32_t *entity_vis = nullptr, *meshlet_vis = nullptr;
     const size_t ev_words = (m.n_entities + 31) / 32 + 1, mv_words = m.n_vis_words ? m.n_vis_words : 1;

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_cpp_host_mirror_two_frames(tmp_path, oracle):
+@pytest.mark.parametrize("with_scene_update", [False, True])
+def test_cpp_host_mirror_two_frames(tmp_path, oracle, with_scene_update):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -37,8 +38,18 @@ def test_cpp_host_mirror_two_frames(tmp_path, oracle):
                        np.float32(view.lod_base), np.float32(view.lod_step))
     meta += view.view.astype(np.float32).T.tobytes() + planes.tobytes()       # view matrix column-major
     open(os.path.join(d, "meta.bin"), "wb").write(meta)
+    if with_scene_update:       # the C++ host builds the entity buffers with SceneData::update_scene; the oracle chain does the same
+        from orbit_b200 import layouts as L
+        sc.transforms.view(np.uint8).tofile(os.path.join(d, "transforms.bin"))
+        sc.draws["mesh_index"].astype(np.uint32).tofile(os.path.join(d, "mesh_slots.bin"))
+        vo = np.full(sc.n_entities, L.NO_VISIBILITY_RANGE, np.uint32)
+        o_ed, o_draws, _ = oracle.scene_update(sc.transforms, sc.draws["mesh_index"].copy(), vo, sc.mesh_infos, np.zeros(1, np.uint32))
+        sc.entities, sc.entity_draws = o_ed.copy(), o_draws.copy()
     out = subprocess.run([str(exe), d], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
+    if with_scene_update:
+        assert np.array_equal(np.fromfile(os.path.join(d, "entity_data_out.bin"), np.uint8), sc.entities.view(np.uint8).reshape(-1))
+        assert np.array_equal(np.fromfile(os.path.join(d, "entity_draws_out.bin"), np.uint8), sc.entity_draws)
     hs = oracle.HostScene(sc)
     for f in range(2):
         o = oracle.depth_prepass_culling(hs, view, depth)
