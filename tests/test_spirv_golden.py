@@ -97,3 +97,14 @@ def test_task_payloads_match_shipped_task_shaders(oracle, golden):
             assert int(pl["task_count"].sum()) == entry["tasks"] > 0
             if "meshlet_visibility_comp_semantics" in entry:
                 assert S.matches(entry["meshlet_visibility_comp_semantics"], hs.meshlet_visibility), (name, shader, "visibility")
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/shaders/meshlet_cull.comp.spv"), reason="reference shaders not present (GPU box)")
+def test_randomised_cases_shipped_shaders_vs_oracle(oracle):
+    """A short run of tools/spirv_fuzz.py (the long runs are recorded in profiles/r1_spirv_fuzz.txt)."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "spirv_fuzz.py"), "6", "77"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    summary = json.loads(out.stdout.strip().splitlines()[-1])
+    assert summary["cases"] == 6 and summary["mismatching_cases"] == 0 and summary["draws_compared"] > 0, out.stdout[-2000:]

@@ -1,0 +1,108 @@
+"""Randomised differential test: the reference's shipped entity_cull / meshlet_cull / depth_reduce SPIR-V (interpreted by
+oracle/spirv_vm) against the C++ oracle on many small random scenes, cameras, LOD settings, plane sets, passes and
+visibility states. Build-container tool (needs /root/reference). Prints one line per mismatch and a summary.
+    python tools/spirv_fuzz.py [n_cases] [seed]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle", "spirv_vm")):
+    sys.path.insert(0, p)
+import oracle_ref as O  # noqa: E402
+import reference_passes as R  # noqa: E402
+import spirv_cases as S  # noqa: E402
+from orbit_b200 import layouts as L, scenes  # noqa: E402
+
+
+def random_case(rng):
+    n_ent = int(rng.integers(3, 40))
+    n_lods = int(rng.integers(1, 5))
+    lods = sorted((int(rng.integers(1, 140)) for _ in range(n_lods)), reverse=True)
+    if rng.random() < 0.5:
+        g = int(np.ceil(np.sqrt(n_ent)))
+        sc = scenes.make_scene("fz", int(rng.integers(1, 1 << 30)), n_ent, max(1, n_ent // int(rng.integers(1, 4))), lods, layout="city",
+                               grid=(g, g), pitch=float(rng.uniform(4, 20)), instanced=bool(rng.random() < 0.5))
+    else:
+        g = int(np.ceil(n_ent ** (1 / 3)))
+        sc = scenes.make_scene("fz", int(rng.integers(1, 1 << 30)), n_ent, max(1, n_ent // 2), lods, layout="lattice3d", grid=(g, g, g + 1),
+                               pitch=float(rng.uniform(4, 20)))
+    centre = (sc.aabb_min + sc.aabb_max) / 2
+    ext = float(np.linalg.norm(sc.aabb_max - sc.aabb_min))
+    d = rng.normal(size=3); d[1] *= 0.3; d /= np.linalg.norm(d)
+    eye = centre - d * rng.uniform(0.05, 0.9) * ext + rng.normal(size=3) * 2.0
+    w, h = int(rng.integers(24, 200)), int(rng.integers(16, 120))
+    if rng.random() < 0.7:
+        view = scenes.perspective_view(tuple(eye), tuple(d), w, h, fov_deg=float(rng.uniform(30, 110)), near=float(10 ** rng.uniform(-2.5, 0)))
+    else:
+        view = scenes.orthographic_view(eye, d, w, h, half_width=float(rng.uniform(5, 0.7 * ext + 6)), near=float(rng.uniform(-20, 1)), far=float(rng.uniform(ext, 3 * ext + 10)))
+    if rng.random() < 0.4:     # extra planes, up to 12 in total
+        extra = []
+        for _ in range(int(rng.integers(1, 12 - len(view.planes) + 1))):
+            nrm = rng.normal(size=3); nrm /= np.linalg.norm(nrm)
+            extra.append([nrm[0], nrm[1], nrm[2], float(rng.uniform(0, ext))])
+        view.planes = np.vstack([view.planes, np.array(extra)])
+    if rng.random() < 0.2:
+        view.planes = view.planes[:0]                       # no frustum culling at all
+    lo = int(rng.integers(0, 4)); view.lod_range = (lo, lo + int(rng.integers(1, 6)))
+    view.lod_base, view.lod_step = float(10 ** rng.uniform(-1, 2)), float(rng.uniform(1.05, 3.0))
+    view.lod_target_view = tuple(rng.normal(size=3) * 3.0) if rng.random() < 0.3 else (0.0, 0.0, 0.0)
+    if rng.random() < 0.3:      # non-affine model matrices
+        m = sc.entities["model_matrix"]
+        m[:, 3, 3] = rng.uniform(0.6, 1.6, len(m)).astype(np.float32)
+        m[:, 0, 3] = rng.uniform(-0.02, 0.02, len(m)).astype(np.float32)
+    depth = scenes.make_depth(sc, view) if rng.random() < 0.7 else rng.random((h, w), dtype=np.float32) ** 4
+    kind = ["none", "read", "write"][int(rng.integers(0, 3))]
+    mocc = bool(rng.random() < 0.7)
+    opts = {}
+    if rng.random() < 0.4:
+        opts = {"alpha_filter": int(rng.integers(1, 8)), "noskip": int(rng.integers(0, 8))}
+    return sc, view, depth, kind, mocc, opts
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    O.build()
+    log2f = lambda x: np.float32(O.log2f(float(x)))
+    rng = np.random.default_rng(seed)
+    bad = 0
+    tot_r = tot_d = 0
+    t0 = time.time()
+    for case in range(n):
+        sc, view, depth, kind, mocc, opts = random_case(rng)
+        hs = O.HostScene(sc)
+        hs.entity_visibility[:] = rng.integers(0, 1 << 32, len(hs.entity_visibility), dtype=np.uint64).astype(np.uint32)
+        hs.meshlet_visibility[:] = rng.integers(0, 1 << 32, len(hs.meshlet_visibility), dtype=np.uint64).astype(np.uint32)
+        ev, mv = hs.entity_visibility.copy(), hs.meshlet_visibility.copy()
+        levels = None
+        if kind == "write":
+            hs.update_pyramid(depth)
+            levels = R.hiz_build(depth, O.hiz_geometry(view.width, view.height), log2f)
+            if not np.array_equal(np.concatenate([l.reshape(-1) for l in levels]).view(np.uint32), hs.hiz_texels.view(np.uint32)):
+                print(json.dumps({"case": case, "what": "hiz", "size": [view.width, view.height]})); bad += 1
+        g = O.gpu_cull_info(view, kind, mocc)
+        if "alpha_filter" in opts: g.alpha_mode_flags = opts["alpha_filter"]
+        if "noskip" in opts and kind == "write": g.noskip_alpha_mode = opts["noskip"]
+        disp = R.entity_cull(sc, g, ev, mv, levels, sc.n_records_lod0, log2f)
+        draws = R.meshlet_cull(sc, g, ev, mv, levels, disp, sc.n_meshlet_instances, log2f)
+        o = O.cull_pass(hs, g)
+        vh, vr = S.canon_records(disp); oh, orr = S.canon_records(o[0])
+        vn, vd = S.canon_draws(draws); on, od = S.canon_draws(o[1])
+        ok = vh == oh and np.array_equal(vr, orr) and vn == on and np.array_equal(vd, od) and np.array_equal(ev, hs.entity_visibility)
+        # meshlet visibility: the shaders only write words of dispatched records; both sides start from the same random words
+        ok = ok and np.array_equal(mv, hs.meshlet_visibility)
+        tot_r += len(orr); tot_d += on
+        if not ok:
+            bad += 1
+            print(json.dumps({"case": case, "seed": seed, "kind": kind, "mocc": mocc, "proj": int(view.projection_type), "planes": len(view.planes),
+                              "records": [vh[0], oh[0]], "draws": [vn, on], "ev_equal": bool(np.array_equal(ev, hs.entity_visibility)),
+                              "mv_equal": bool(np.array_equal(mv, hs.meshlet_visibility)), "lods": view.lod_range, "opts": opts}), flush=True)
+    print(json.dumps({"cases": n, "seed": seed, "mismatching_cases": bad, "records_compared": tot_r, "draws_compared": tot_d, "seconds": round(time.time() - t0)}))
+
+
+if __name__ == "__main__":
+    main()
