@@ -265,9 +265,12 @@ class VM:
                     self._schedule(invs, subgroup)
 
     def _schedule(self, invs, subgroup):
-        # every invocation runs until it finishes or waits at a subgroup operation; waiting invocations of one subgroup
-        # that stand at the same instruction are resolved together
-        state = [None] * len(invs)           # pending (kind, inst id, payload)
+        """Runs one workgroup. Every invocation runs until it finishes or reaches a scheduling point: a subgroup operation,
+        a barrier, or an atomic. The pending point with the EARLIEST instruction is served first, for all invocations standing
+        at it (subgroup operations: per subgroup), so the workgroup advances through the program front to back — one legal
+        interleaving, and the one in which 'every invocation has appended before anyone reads the total' holds for shaders
+        that rely on it without a barrier (active_cluster_compaction.comp does)."""
+        state = [None] * len(invs)           # pending (kind, instruction index, payload)
         alive = [True] * len(invs)
 
         def advance(i, send=None):
@@ -278,42 +281,32 @@ class VM:
         for i in range(len(invs)):
             advance(i)
         while any(alive):
-            progressed = False
-            for sg in range(0, len(invs), subgroup):
-                lanes = [i for i in range(sg, min(sg + subgroup, len(invs))) if alive[i]]
-                if not lanes:
-                    continue
-                by_inst = {}
-                for i in lanes:
-                    by_inst.setdefault(state[i][1], []).append(i)
-                # resolve the group standing at the earliest instruction first (structured control flow: later groups wait)
-                key = min(by_inst)
-                group = by_inst[key]
-                kind = state[group[0]][0]
-                if kind == "barrier":
-                    # workgroup barrier: released when every live invocation of the workgroup stands at it
-                    everyone = [i for i in range(len(invs)) if alive[i]]
-                    if all(state[i][0] == "barrier" and state[i][1] == key for i in everyone):
-                        for i in everyone: advance(i)
-                        progressed = True
-                    elif any(state[i][0] != "barrier" for i in everyone):
+            live = [i for i in range(len(invs)) if alive[i]]
+            key = min(state[i][1] for i in live)
+            group = [i for i in live if state[i][1] == key]
+            kind = state[group[0]][0]
+            if kind == "barrier":
+                if len(group) != len(live):
+                    raise RuntimeError("workgroup barrier not reached by every live invocation")
+                for i in group: advance(i)
+            elif kind == "sync":
+                for i in group: advance(i)
+            elif kind in ("ballot", "elect"):
+                for sg in range(0, len(invs), subgroup):
+                    lanes = [i for i in group if sg <= i < sg + subgroup]
+                    if not lanes:
                         continue
+                    if kind == "ballot":
+                        mask = 0
+                        for i in lanes:
+                            if state[i][2]: mask |= 1 << (i - sg)
+                        res = [mask & 0xFFFFFFFF, 0, 0, 0]
+                        for i in lanes: advance(i, list(res))
                     else:
-                        raise RuntimeError("invocations wait at different barriers")
-                    continue
-                if kind == "ballot":
-                    mask = 0
-                    for i in group:
-                        if state[i][2]: mask |= 1 << (i - sg)
-                    res = [mask & 0xFFFFFFFF, 0, 0, 0]
-                    for i in group: advance(i, list(res))
-                elif kind == "elect":
-                    first = min(group)
-                    for i in group: advance(i, i == first)
-                else:
-                    raise NotImplementedError(kind)
-                progressed = True
-            assert progressed
+                        first = min(lanes)
+                        for i in lanes: advance(i, i == first)
+            else:
+                raise NotImplementedError(kind)
 
     # ---- one invocation ------------------------------------------------------------------------------------
     def _run(self, builtins):
@@ -550,6 +543,7 @@ class VM:
                         vals[a[1]] = vmap(lambda x: signed(x, ws) & ((1 << w) - 1), V(a[2]))
                     elif op == 12: vals[a[1]] = self._ext(a, V, vmap, dot)
                     elif op in (234, 239, 241, 237, 240, 242, 235, 229, 230):
+                        yield ("sync", inst.index, None)      # scheduling point: see _schedule
                         p = vals[a[2]] if a[2] in vals else var_pointer(a[2])
                         old = load(p)
                         v = V(a[5]) if len(a) > 5 else None

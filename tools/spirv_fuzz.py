@@ -63,7 +63,51 @@ def random_case(rng):
     return sc, view, depth, kind, mocc, opts
 
 
+def cluster_fuzz(n, seed, log2f):
+    """mark_active / active_cluster_compaction / light_culling (shipped SPIR-V) vs the oracle on random grids and lights."""
+    rng = np.random.default_rng(seed)
+    bad = 0
+    t0 = time.time()
+    lists = 0
+    for case in range(n):
+        w, h = int(rng.integers(16, 120)), int(rng.integers(12, 80))
+        tile = int(rng.choice([4, 8, 10, 16, 24, 33]))
+        cz = int(rng.integers(1, 33))
+        near, far = float(10 ** rng.uniform(-2, 0)), float(10 ** rng.uniform(1, 2.7))
+        sc, _ = scenes.config_c1(scale=float(rng.uniform(0.02, 0.08)))
+        d = rng.normal(size=3); d[1] *= 0.2; d /= np.linalg.norm(d)
+        view = scenes.perspective_view((-6.0 + rng.normal() * 3, 2.0 + abs(rng.normal()) * 3, -6.0 + rng.normal() * 3), tuple(d), w, h,
+                                       fov_deg=float(rng.uniform(40, 100)), near=near)
+        depth = scenes.make_depth(sc, view) if rng.random() < 0.6 else (rng.random((h, w), dtype=np.float32) ** 3) * (rng.random((h, w)) < 0.8)
+        depth = np.ascontiguousarray(depth, np.float32)
+        lights = scenes.make_lights(int(rng.integers(1, 1 << 20)), int(rng.integers(1, 600)), sc.aabb_min, sc.aabb_max)
+        if rng.random() < 0.3:
+            lights["outer_radius"] *= np.float32(rng.uniform(2, 30))
+        p = L.ClusterParams()
+        cx, cy = -(-w // tile), -(-h // tile)
+        p.info.world_to_view_matrix.set(view.view)
+        p.info.screen_to_view_matrix.set(np.linalg.inv(np.asarray(view.projection_matrix, np.float64)))
+        p.info.cluster_count[0], p.info.cluster_count[1], p.info.cluster_count[2] = cx, cy, cz
+        p.info.tile_size_px = tile
+        p.info.screen_size[0], p.info.screen_size[1] = w, h
+        p.info.z_near, p.info.z_far = near, far
+        p.info.global_light_count = len(lights)
+        p.z_scale, p.z_bias = scenes.cluster_grid_info(near, far, cz)
+        a = S.canon_clusters(R.light_cluster(p, depth, lights, log2f))
+        b = S.canon_clusters(O.light_cluster(p, depth, lights))
+        ok = a["header"] == b["header"] and a["total"] == b["total"] and all(np.array_equal(a[k], b[k]) for k in ("masks", "bounds", "active", "counts", "lists"))
+        lists += int(b["total"])
+        if not ok:
+            bad += 1
+            print(json.dumps({"cluster_case": case, "seed": seed, "size": [w, h], "tile": tile, "cz": cz, "header": [a["header"], b["header"]], "total": [a["total"], b["total"]]}), flush=True)
+    print(json.dumps({"cluster_cases": n, "seed": seed, "mismatching_cases": bad, "light_indices_compared": lists, "seconds": round(time.time() - t0)}))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "clusters":
+        O.build()
+        cluster_fuzz(int(sys.argv[2]) if len(sys.argv) > 2 else 20, int(sys.argv[3]) if len(sys.argv) > 3 else 1, lambda x: np.float32(O.log2f(float(x))))
+        return
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     O.build()
