@@ -224,6 +224,7 @@ def run_ours(args, rank, world, local_rank):
     def time_stage(fn, reps=7, per_graph=8):
         for pf in copies:
             pf.launch()
+            fn(pf, pf._stream())      # the stage itself once outside the capture: transient buffers are created (and zero-filled) here
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

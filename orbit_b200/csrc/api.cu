@@ -330,6 +330,7 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     // emit kernel: two CTAs per SM (every CTA repeats the 2048-entry chunk scan; more CTAs only add to that)
     if (c->emit_occupancy <= 0) c->emit_occupancy = meshlet_emit_max_ctas_per_sm();
     int emit_per_sm = c->emit_occupancy < 2 ? (c->emit_occupancy > 0 ? c->emit_occupancy : 1) : 2;
+    if (const char* s = std::getenv("ORBIT_EMIT_CTAS_PER_SM")) { const int v = std::atoi(s); if (v >= 1 && v <= c->emit_occupancy) emit_per_sm = v; }   // tuning knob
     const uint64_t emit_grid = (uint64_t)c->sm_count * (uint64_t)emit_per_sm;
     CK(launch_meshlet_cull(p, rpw, c->debug_skip == 2 ? 0 : (int)grid, c->debug_skip == 1 ? 0 : (int)emit_grid, (cudaStream_t)stream));
     c->launches += 2;   // test kernel + emit kernel

@@ -17,7 +17,10 @@
 
 namespace orbit {
 
-constexpr int kEcThreads = 256;
+#ifndef ORBIT_EC_THREADS
+#define ORBIT_EC_THREADS 256
+#endif
+constexpr int kEcThreads = ORBIT_EC_THREADS;   // entity draws per CTA (tuning experiments: -DORBIT_EC_THREADS=128)
 
 
 template <bool kFlat>
