@@ -39,6 +39,7 @@ def time_frame(ctx, copies, reps=7, per_graph=8):
     for name, fn in stages.items():
         for pf in copies:          # consistent steady-state inputs for every stage
             pf.launch()
+            fn(pf, pf._stream())   # the stage itself once outside the capture: transient buffers are created (and zero-filled) here
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
