@@ -131,7 +131,13 @@ class PeerExchange:
         dist.barrier(group=self.group)   # every rank's stores into my buffer are complete and visible
         return total, counts
 
-    def exchange_async(self, local_draw_buffer, root=None):
+    def fence(self):
+        """Closing fence of exchange_async(..., fence=False): completes on a rank only after every rank's stores were issued and flushed."""
+        if not hasattr(self, "_fence"):
+            self._fence = torch.zeros(1, dtype=torch.int32, device=self.context.device)
+        dist.all_reduce(self._fence, group=self.group)
+
+    def exchange_async(self, local_draw_buffer, root=None, fence=True):
         """Same exchange without any host round trip: the all-gathered counts stay on the device and
         `orbit_draws_scatter_ranked` derives each rank's offset from them; a 4-byte all-reduce enqueued behind the
         stores is the closing barrier. Everything is stream-ordered, so a sharded frame can be enqueued back to back.
@@ -147,9 +153,8 @@ class PeerExchange:
                                                      C.c_void_p(self.counts.data_ptr()), self.rank, self.world, self.capacity, stream)
             if rc:
                 raise RuntimeError("orbit_draws_scatter_ranked: %d" % rc)
-        if not hasattr(self, "_fence"):
-            self._fence = torch.zeros(1, dtype=torch.int32, device=self.context.device)
-        dist.all_reduce(self._fence, group=self.group)   # completes on a rank only after every rank's stores were issued and flushed
+        if fence:
+            self.fence()
         return self.counts
 
     def read(self, total):
@@ -197,6 +202,35 @@ class ShardedView:
         """Use NVLink peer stores (PeerExchange) for the survivor exchange instead of the padded NCCL all-gather."""
         self.peer_early = PeerExchange(self.context, capacity_draws)
         self.peer_late = PeerExchange(self.context, capacity_draws)
+
+    def step_overlapped(self, root=0):
+        """The same frame with the EARLY list's exchange overlapped with the rest of the frame: the early survivors are final
+        as soon as the early pass ends, so their counts all-gather and peer stores run on a side stream while this rank builds /
+        receives the pyramid and runs the late pass; the late list follows, and ONE fence closes both. (The fence has to come
+        last: torch keeps one NCCL stream per group, so a fence issued right after the early stores would hold the pyramid
+        broadcast back until those stores are done.) root=None: every rank receives both lists."""
+        pf = self.prepared
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream()
+        if not self.empty:
+            pf.entity(False); pf.meshlet(False)
+        else:
+            pf.early_draws[:4].zero_()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            c_e = self.peer_early.exchange_async(pf.early_draws, root, fence=False)
+        if self.rank == 0:
+            pf.hiz()
+        broadcast_pyramid(self.vstate.depth_pyramid.texels, src=0)
+        if not self.empty:
+            pf.entity(True); pf.meshlet(True)
+        else:
+            pf.late_draws[:4].zero_()
+        c_l = self.peer_late.exchange_async(pf.late_draws, root, fence=False)
+        main.wait_stream(self._side)
+        self.peer_late.fence()
+        return c_e, c_l
 
     def step(self, exchange=True):
         """One two-pass frame: early cull (local range) -> Hi-Z on rank 0 + broadcast -> late cull -> survivor exchange:

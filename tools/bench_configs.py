@@ -132,6 +132,18 @@ def run_c3(args, rank, world, ctx):
             if rank == 0 or mode == "peer_async":
                 ok = bool(torch.equal(sv.peer_early.read(int(c_e.sum())), early) and torch.equal(sv.peer_late.read(int(c_l.sum())), late))
                 t_async[mode + "_ok"] = ok
+        # early list's exchange overlapped with Hi-Z + late pass, one closing fence
+        sv.step_overlapped(0)
+        t_async["gather_overlapped"] = event_time(lambda: sv.step_overlapped(0))[0]
+        sv.peer_early.clear(); sv.peer_late.clear()
+        dist.barrier()
+        c_e, c_l = sv.step_overlapped(0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            t_async["gather_overlapped_ok"] = bool(torch.equal(sv.peer_early.read(int(c_e.sum())), early) and torch.equal(sv.peer_late.read(int(c_l.sum())), late))
+        tt = torch.tensor([t_async["gather_overlapped"]], device=ctx.device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_async["gather_overlapped"] = float(tt[0])
         t = torch.tensor([t_compute, t_full, t_peer, t_gather, t_async["peer_async"], t_async["gather_async"]], device=ctx.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_compute, t_full, t_peer, t_gather = float(t[0]), float(t[1]), float(t[2]), float(t[3])
@@ -149,6 +161,8 @@ def run_c3(args, rank, world, ctx):
         res["gmeshlets_per_s_with_gather"] = scene.n_meshlet_instances / t_gather / 1e3
         res["device_side_counts"] = {"us_with_peer_exchange": t_async["peer_async"], "us_with_gather_to_rank0": t_async["gather_async"],
                                      "peer_ok": t_async.get("peer_async_ok"), "gather_ok_on_rank0": t_async.get("gather_async_ok"),
+                                     "us_with_gather_overlapped": t_async["gather_overlapped"], "gather_overlapped_ok_on_rank0": t_async.get("gather_overlapped_ok"),
+                                     "gmeshlets_per_s_with_gather_overlapped": scene.n_meshlet_instances / t_async["gather_overlapped"] / 1e3,
                                      "gmeshlets_per_s_with_gather": scene.n_meshlet_instances / t_async["gather_async"] / 1e3,
                                      "gmeshlets_per_s_with_peer_exchange": scene.n_meshlet_instances / t_async["peer_async"] / 1e3}
     if rank == 0:
