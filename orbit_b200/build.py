@@ -41,8 +41,8 @@ def build(force=False, verbose=False, extra_flags=()):
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [_nvcc()] + flags + list(extra_flags) + ["-shared", "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("ORBIT_EXTRA_NVCC", "").split()   # development knob
+    cmd = [_nvcc()] + flags + list(extra_flags) + ["-shared", "-o", os.environ.get("ORBIT_LIB_OUT", LIB_PATH)] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

@@ -49,8 +49,7 @@ struct orbit_ctx {
     // light scratch
     float4* light_view = nullptr;
     size_t light_capacity = 0;
-    // tuning (ORBIT_MC_RECS_PER_WARP / ORBIT_MC_CTAS_PER_SM environment overrides, read once)
-    int mc_recs_per_warp = 4;
+    // tuning (ORBIT_MC_CTAS_PER_SM environment override, read once)
     int mc_ctas_per_sm = 0;
     int emit_occupancy = 0;
     int debug_skip = 0;               // ORBIT_DEBUG_SKIP: 1 = skip emit kernel, 2 = skip test kernel (timing experiments only)
@@ -144,7 +143,7 @@ int orbit_ctx_create(int device, orbit_ctx** out) {
     CK(cudaHostGetDevicePointer(&c->status_dev, c->status_host, 0));
     int rc = ensure_status(c, 4096);
     if (rc != ORBIT_OK) return rc;
-    if (const char* s = std::getenv("ORBIT_MC_RECS_PER_WARP")) { int v = std::atoi(s); if (v == 2 || v == 4 || v == 8) c->mc_recs_per_warp = v; }
+    CK(meshlet_cull_configure_device());
     if (const char* s = std::getenv("ORBIT_DEBUG_SKIP")) c->debug_skip = std::atoi(s);
     if (const char* s = std::getenv("ORBIT_MC_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->mc_ctas_per_sm = v; }
     *out = c;
@@ -296,7 +295,6 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     if (rc != ORBIT_OK) return rc;
     // The record count lives on the device (the reference's dispatch_indirect); scratch and grid are sized for
     // the dispatch buffer's capacity and the kernel clamps the device-side count to it.
-    const int rpw = c->mc_recs_per_warp;
     const uint64_t max_records = capacity_records;
     if (max_records > c->draw_mask_capacity) {
         if (c->draw_masks) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->draw_masks)); c->draw_masks = nullptr; c->draw_mask_capacity = 0; }
@@ -320,9 +318,15 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     p.chunk_counts = c->chunk_counts;
     p.capacity_records = max_records;
     p.capacity_draws = capacity_draws;
+    p.pk_one = make_float2(1.0f, 1.0f); p.pk_mone = make_float2(-1.0f, -1.0f);
+    for (uint32_t j = 0; j < 6u; ++j) {
+        const uint32_t n = cull->cull_plane_count;
+        const uint32_t a = 2u * j < n ? 2u * j : (n ? n - 1u : 0u), b = 2u * j + 1u < n ? 2u * j + 1u : a;
+        for (int cc = 0; cc < 4; ++cc) p.planes_t[j][cc] = make_float2(cull->cull_planes[a][cc], cull->cull_planes[b][cc]);
+    }
     // test kernel: persistent warps, cyclic tiles, no inter-CTA dependency -> one full wave of CTAs
     int& occ_slot = c->mc_occupancy[meshlet_cull_variant_index(*cull)];
-    if (occ_slot <= 0) occ_slot = meshlet_cull_max_ctas_per_sm(p, rpw);
+    if (occ_slot <= 0) occ_slot = meshlet_cull_max_ctas_per_sm(p);
     const int occ = occ_slot;
     int per_sm = c->mc_ctas_per_sm;
     if (per_sm <= 0) per_sm = occ > 0 ? occ : 1;
@@ -332,7 +336,7 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     int emit_per_sm = c->emit_occupancy < 2 ? (c->emit_occupancy > 0 ? c->emit_occupancy : 1) : 2;
     if (const char* s = std::getenv("ORBIT_EMIT_CTAS_PER_SM")) { const int v = std::atoi(s); if (v >= 1 && v <= c->emit_occupancy) emit_per_sm = v; }   // tuning knob
     const uint64_t emit_grid = (uint64_t)c->sm_count * (uint64_t)emit_per_sm;
-    CK(launch_meshlet_cull(p, rpw, c->debug_skip == 2 ? 0 : (int)grid, c->debug_skip == 1 ? 0 : (int)emit_grid, (cudaStream_t)stream));
+    CK(launch_meshlet_cull(p, c->debug_skip == 2 ? 0 : (int)grid, c->debug_skip == 1 ? 0 : (int)emit_grid, (cudaStream_t)stream));
     c->launches += 2;   // test kernel + emit kernel
     return ORBIT_OK;
 }

@@ -34,55 +34,20 @@ namespace orbit {
 constexpr int kMcWarps = 8;
 constexpr int kMcThreads = kMcWarps * 32;
 constexpr int kMvStride = 20;   // 16 matrix entries + scale, padded
-#ifndef ORBIT_DIRECT_MIN_CTAS
-#define ORBIT_DIRECT_MIN_CTAS 3
-#endif
-constexpr int kDirectMinCtas = ORBIT_DIRECT_MIN_CTAS;
-
-// ---- TMA bulk copy + mbarrier plumbing (PTX; SASS: UBLKCP / SYNCS) --------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
+constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 struct ItemTest {
     Sphere s;
     bool pre_visible;   // passed frustum + cone
 };
 
-// frustum + cone for one meshlet against the model-view matrix `mv` (17 floats in shared memory)
+// frustum + cone for one meshlet against the model-view matrix (columns c0..c3, largest column scale `scale`)
 // kProj: 0 perspective, 1 orthographic, -1 decided at run time from ci.projection_type
 template <int kProj>
-__device__ __forceinline__ ItemTest test_item(const OrbitCullInfo& ci, const float* __restrict__ mv, const uint4 ma, const uint32_t cone) {
+__device__ __forceinline__ ItemTest test_item(const OrbitCullInfo& ci, const float4 c0, const float4 c1, const float4 c2, const float4 c3,
+                                              const float scale, const float cx, const float cy, const float cz, const float r_model,
+                                              const uint32_t cone) {
     ItemTest out;
-    const float4 c0 = *reinterpret_cast<const float4*>(mv + 0);
-    const float4 c1 = *reinterpret_cast<const float4*>(mv + 4);
-    const float4 c2 = *reinterpret_cast<const float4*>(mv + 8);
-    const float4 c3 = *reinterpret_cast<const float4*>(mv + 12);
-    const float scale = mv[16];
-    const float cx = __uint_as_float(ma.x), cy = __uint_as_float(ma.y), cz = __uint_as_float(ma.z);
     // (M * (c,1))[row]; m3*1.0f == m3 exactly
     float px = add(add(add(mul(c0.x, cx), mul(c1.x, cy)), mul(c2.x, cz)), c3.x);
     float py = add(add(add(mul(c0.y, cx), mul(c1.y, cy)), mul(c2.y, cz)), c3.y);
@@ -91,14 +56,14 @@ __device__ __forceinline__ ItemTest test_item(const OrbitCullInfo& ci, const flo
     if (pw != 1.0f) { px = fdiv(px, pw); py = fdiv(py, pw); pz = fdiv(pz, pw); }   // x/1 == x exactly
     Sphere& s = out.s;
     s.x = px; s.y = py; s.z = pz;
-    s.r_model = __uint_as_float(ma.w); s.s = scale;
+    s.r_model = r_model; s.s = scale;
     s.r = mul(s.r_model, scale);
     const float nr = -s.r;
     bool visible = true;
     const uint32_t n = ci.cull_plane_count;
     if (n == 5u) {
         // the main-view case (forward.rs:268 passes planes[0..5]): straight-line code, plane coefficients as constant-bank
-        // operands, no loop control (the generic loop below costs ~25 more instructions per record)
+        // operands, no loop control
 #pragma unroll
         for (uint32_t i = 0; i < 5u; ++i) {
             const float d = add(dot3(ci.cull_planes[i][0], ci.cull_planes[i][1], ci.cull_planes[i][2], px, py, pz), ci.cull_planes[i][3]);
@@ -111,7 +76,9 @@ __device__ __forceinline__ ItemTest test_item(const OrbitCullInfo& ci, const flo
             visible = visible && (d > nr);
         }
     }
-    if (visible) {
+    {
+        // cone test: computed for every lane (no branch on `visible`: a warp nearly always has a visible lane, and the
+        // branch + reconvergence cost more than the predicated-off work saved)
         const float K = 0.007874015718698502f;
         const float kx = mul((float)(int)(int8_t)(cone & 0xFFu), K);
         const float ky = mul((float)(int)(int8_t)((cone >> 8) & 0xFFu), K);
@@ -125,13 +92,13 @@ __device__ __forceinline__ ItemTest test_item(const OrbitCullInfo& ci, const flo
         if (proj == 0u) {
             const float lhs = dot3(px, py, pz, axx, axy, axz);
             const float len = fsqrt(dot3(px, py, pz, px, py, pz));
-            visible = !(lhs >= fma_(cutoff, len, s.r));
+            visible = visible && !(lhs >= fma_(cutoff, len, s.r));
         } else if (proj == 1u) {
             const float camx = sub(px, 0.0f), camy = sub(py, 0.0f), camz = sub(pz, -1.0f);
             const float qx = sub(px, camx), qy = sub(py, camy), qz = sub(pz, camz);
             const float lhs = dot3(qx, qy, qz, axx, axy, axz);
             const float len = fsqrt(dot3(qx, qy, qz, qx, qy, qz));
-            visible = !(lhs >= fma_(cutoff, len, s.r));
+            visible = visible && !(lhs >= fma_(cutoff, len, s.r));
         }
     }
     out.pre_visible = visible;
@@ -160,37 +127,300 @@ __device__ __forceinline__ void store_command(uint32_t* __restrict__ dst, uint32
     dst[6] = meshlet_index;
 }
 
-template <int R>
-struct __align__(128) WarpSmem {
-    uint4 meshlets[R * 64];        // R records x 32 meshlets x 2 x 16 B, filled by TMA (packed mode: item list aliases this)
-    float mv[R][kMvStride];        // view*model + scale per record
-    float q[6][64];                // ring buffer of Hi-Z candidates: x, y, z, r, r_model, scale
-    uint32_t qid[64];              //   (record << 5) | lane
-    uint32_t mask[R];              // per-record visible masks under construction
-    uint32_t aok[R], nsk[R];       // per-record "alpha mode passes the filter" / "alpha mode is noskip" lane masks
-    unsigned long long bar;        // mbarrier of the TMA copies
-};
-
 // Survivor counts are accumulated per CHUNK of consecutive records by the test kernel (integer atomics: the sums are
 // order-independent) so that the emit kernel can order its output with a shared-memory scan instead of an
-// inter-CTA exchange. Chunk size: a multiple of 32 records such that there are at most kMaxChunks chunks.
+// inter-CTA exchange. Chunk size: a power of two >= 32 records such that there are at most kMaxChunks chunks.
 constexpr uint32_t kMaxChunks = 2048u;
-__device__ __forceinline__ uint32_t chunk_records(uint32_t nrec) {
-    const uint32_t per = (nrec + kMaxChunks - 1u) / kMaxChunks;
-    return max(32u, (per + 31u) & ~31u);
+__device__ __forceinline__ uint32_t chunk_shift_of(uint32_t nrec) {
+    const uint32_t per = (nrec + kMaxChunks - 1u) / kMaxChunks;            // records per chunk needed, >= 0
+    const uint32_t sh = per <= 1u ? 0u : 32u - (uint32_t)__clz((int)(per - 1u));   // ceil(log2(per))
+    return max(5u, sh);
 }
+
+// ---- asynchronous global -> shared copies (cp.async, SASS: LDGSTS + LDGDEPBAR / DEPBAR) -----------------------------
+// The stream kernel prefetches through shared memory, NOT through registers: a register prefetch carried around the
+// loop ties the data to one of the six SASS scoreboards, and ptxas put a wait on that scoreboard ~100 instructions
+// after the loads were issued (measured: 12 % of all warp time in one FMUL, profiles/r2_meshlet_test_history.txt) —
+// a warp then exposes a full DRAM latency per record. cp.async completion is tracked by its own group counter.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_16_stream(uint32_t dst, const void* src, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// ---- packed binary32 pairs (sm_100: FMUL2 / FFMA2, PTX mul.rn.f32x2 / fma.rn.f32x2) ------------------------------------
+// Instruction issue, not HBM, bounds the meshlet test, so the multiplies / adds / fmas of the pinned arithmetic contract
+// are issued two at a time wherever two independent values go through the same operation. Each half is rounded exactly
+// like the scalar operation (IEEE round-to-nearest per component), so results stay bit-identical to the
+// scalar oracle — PROVIDED nothing is contracted: ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under
+// -fmad=false (it does not do that to the scalar .rn forms). The packed ADD is therefore never emitted: a + b is issued
+// as fma(a, ONE, b) and a - b as fma(b, MINUS_ONE, a) with ONE / MINUS_ONE read from the kernel parameters (the compiler
+// cannot know their values, so there is no multiply-add pair left to contract; the single rounding of the fma equals the
+// rounding of the sum). tests/test_gpu_packed_math.py compares the packed leaf functions with the scalar ones bit for bit.
+struct PkConsts { float2 one, mone; };
+ORBIT_DEV float2 pk(float a, float b) { return make_float2(a, b); }
+ORBIT_DEV float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+ORBIT_DEV float2 pmuls(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+ORBIT_DEV float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+ORBIT_DEV float2 padd(const PkConsts& k, float2 a, float2 b) { return __ffma2_rn(a, k.one, b); }
+ORBIT_DEV float2 psub(const PkConsts& k, float2 a, float2 b) { return __ffma2_rn(b, k.mone, a); }
+ORBIT_DEV float2 pneg(const PkConsts& k, float2 a) { return __fmul2_rn(a, k.mone); }
+ORBIT_DEV float2 pdot3(const PkConsts& k, float2 ax, float2 ay, float2 az, float2 bx, float2 by, float2 bz) {
+    return padd(k, padd(k, pmul(ax, bx), pmul(ay, by)), pmul(az, bz));
+}
+ORBIT_DEV float2 psqrt(float2 a) { return make_float2(fsqrt(a.x), fsqrt(a.y)); }
+ORBIT_DEV float2 pdiv(float2 a, float2 b) { return make_float2(fdiv(a.x, b.x), fdiv(a.y, b.y)); }
+
+// test_item with the arithmetic packed two-wide ACROSS COMPONENTS of one meshlet: the (x, y) and (z, w) rows of the
+// transform, two cull planes at a time (coefficients pre-paired on the host: MeshletCullParams::planes_t), the (x, y)
+// rows of the cone axis. The matrix columns come out of shared memory as natural (x, y) / (z, w) pairs and the meshlet's
+// scalars are broadcast operands, so no register pairs have to be assembled. Same operations, same order, same rounding
+// per component as test_item (pinned by tests/test_gpu_packed_math.py and by the parity suite).
+struct ItemXY { float2 pxy; float pz, r; bool pre_visible; };
+ORBIT_DEV float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
+ORBIT_DEV float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
+
+template <int kProj>
+__device__ __forceinline__ ItemXY test_item_xy(const OrbitCullInfo& ci, const MeshletCullParams& p, const PkConsts& k, const float4 c0, const float4 c1,
+                                              const float4 c2, const float4 c3, const float scale, const float cx, const float cy, const float cz,
+                                              const float r_model, const uint32_t cone) {
+    ItemXY out;
+    // (M * (c,1)) rows (x,y) and (z,w); m3*1.0f == m3 exactly
+    float2 pxy = padd(k, padd(k, padd(k, pmuls(lo2(c0), cx), pmuls(lo2(c1), cy)), pmuls(lo2(c2), cz)), lo2(c3));
+    const float2 pzw = padd(k, padd(k, padd(k, pmuls(hi2(c0), cx), pmuls(hi2(c1), cy)), pmuls(hi2(c2), cz)), hi2(c3));
+    float pz = pzw.x;
+    if (pzw.y != 1.0f) { pxy.x = fdiv(pxy.x, pzw.y); pxy.y = fdiv(pxy.y, pzw.y); pz = fdiv(pz, pzw.y); }   // x/1 == x exactly
+    const float r = mul(r_model, scale);
+    out.pxy = pxy; out.pz = pz; out.r = r;
+    bool visible = true;
+    const uint32_t n = ci.cull_plane_count;
+    if (n == 5u) {
+        // the main-view case (forward.rs:268 passes planes[0..5]): straight-line code; the sixth slot repeats plane 4
+#pragma unroll
+        for (uint32_t j = 0; j < 3u; ++j) {
+            const float2 d = padd(k, padd(k, padd(k, pmuls(p.planes_t[j][0], pxy.x), pmuls(p.planes_t[j][1], pxy.y)), pmuls(p.planes_t[j][2], pz)), p.planes_t[j][3]);
+            visible = visible && (d.x > -r) && (d.y > -r);
+        }
+    } else {
+        const uint32_t np = (n + 1u) >> 1;
+#pragma unroll 1
+        for (uint32_t j = 0; j < np; ++j) {
+            const float2 d = padd(k, padd(k, padd(k, pmuls(p.planes_t[j][0], pxy.x), pmuls(p.planes_t[j][1], pxy.y)), pmuls(p.planes_t[j][2], pz)), p.planes_t[j][3]);
+            visible = visible && (d.x > -r) && (d.y > -r);
+        }
+    }
+    {
+        const float K = 0.007874015718698502f;
+        const float kx = mul((float)(int)(int8_t)(cone & 0xFFu), K);
+        const float ky = mul((float)(int)(int8_t)((cone >> 8) & 0xFFu), K);
+        const float kz = mul((float)(int)(int8_t)((cone >> 16) & 0xFFu), K);
+        const float cutoff = mul((float)((int)cone >> 24), K);
+        // (M * (k,0)).xyz: the w column contributes m3*0.0f (kept: +-0 / NaN propagate as in the oracle)
+        const float2 axy = padd(k, padd(k, padd(k, pmuls(lo2(c0), kx), pmuls(lo2(c1), ky)), pmuls(lo2(c2), kz)), pmuls(lo2(c3), 0.0f));
+        const float az = add(add(add(mul(c0.z, kx), mul(c1.z, ky)), mul(c2.z, kz)), mul(c3.z, 0.0f));
+        const uint32_t proj = kProj >= 0 ? (uint32_t)kProj : ci.projection_type;
+        if (proj == 0u) {
+            const float2 t = pmul(pxy, axy), u = pmul(pxy, pxy);
+            const float lhs = add(add(t.x, t.y), mul(pz, az));
+            const float len = fsqrt(add(add(u.x, u.y), mul(pz, pz)));
+            visible = visible && !(lhs >= fma_(cutoff, len, r));
+        } else if (proj == 1u) {
+            // camera = c - (0,0,-1); q = c - camera (two subtractions, not simplified: meshlet_cull.comp:150-156)
+            const float2 camxy = psub(k, pxy, pk(0.0f, 0.0f));
+            const float camz = sub(pz, -1.0f);
+            const float2 qxy = psub(k, pxy, camxy);
+            const float qz = sub(pz, camz);
+            const float2 t = pmul(qxy, axy), u = pmul(qxy, qxy);
+            const float lhs = add(add(t.x, t.y), mul(qz, az));
+            const float len = fsqrt(add(add(u.x, u.y), mul(qz, qz)));
+            visible = visible && !(lhs >= fma_(cutoff, len, r));
+        }
+    }
+    out.pre_visible = visible;
+    return out;
+}
+
+// occlusion_test (orbit_device.cuh) for two candidates at once: component .x = first, .y = second candidate.
+// Returns bit 0 / bit 1 = candidate visible.
+template <int kProj>
+__device__ __forceinline__ uint32_t occlusion_pair(const OrbitCullInfo& ci, const PkConsts& k, const float2 x, const float2 y, const float2 z,
+                                                  const float2 r_model, const float2 s, const HizDevice& hz, const uint32_t hiz_lw,
+                                                  const uint32_t hiz_lh) {
+    float2 ax, ay, az, aw, depth;
+    bool cull_a = true, cull_b = true;        // cullable (perspective only)
+    const float2 r = pmul(r_model, s);
+    const uint32_t proj = kProj >= 0 ? (uint32_t)kProj : ci.projection_type;
+    if (proj == 0u) {
+        const float2 zp = pneg(k, z);
+        const float2 lim = pfma(r_model, s, pk(ci.z_near, ci.z_near));
+        cull_a = zp.x >= lim.x; cull_b = zp.y >= lim.y;
+        const float P00 = ci.p00_or_width_recip_x2, P11 = ci.p11_or_height_recip_x2;
+        const float2 nr = pneg(k, r);
+        const float2 c0 = pneg(k, x), c1 = pneg(k, zp), d0 = pneg(k, y);
+        const float2 zz = pmul(c1, c1);
+        const float2 sx = psqrt(pfma(nr, r, padd(k, pmul(c0, c0), zz)));
+        const float2 sy = psqrt(pfma(nr, r, padd(k, pmul(d0, d0), zz)));
+        const float2 nrc1 = pmul(nr, c1), rc1 = pmul(r, c1);
+        const float2 sxc0 = pmul(sx, c0), sxc1 = pmul(sx, c1), syd0 = pmul(sy, d0), syc1 = pmul(sy, c1);
+        const float2 minx0 = padd(k, sxc0, nrc1), minx1 = padd(k, pmul(r, c0), sxc1);
+        const float2 maxx0 = padd(k, sxc0, rc1), maxx1 = padd(k, pmul(nr, c0), sxc1);
+        const float2 miny0 = padd(k, syd0, nrc1), miny1 = padd(k, pmul(r, d0), syc1);
+        const float2 maxy0 = padd(k, syd0, rc1), maxy1 = padd(k, pmul(nr, d0), syc1);
+        const float2 a0 = pmuls(pdiv(minx0, minx1), P00), a1 = pmuls(pdiv(miny0, miny1), P11);
+        const float2 a2 = pmuls(pdiv(maxx0, maxx1), P00), a3 = pmuls(pdiv(maxy0, maxy1), P11);
+        const float2 h = pk(0.5f, 0.5f), nh = pk(-0.5f, -0.5f);
+        ax = pfma(a0, h, h); ay = pfma(a3, nh, h);
+        az = pfma(a2, h, h); aw = pfma(a1, nh, h);
+        depth = pdiv(pk(ci.z_near, ci.z_near), pfma(pneg(k, r_model), s, zp));
+    } else if (proj == 1u) {
+        const float sr = ci.p00_or_width_recip_x2;
+        const float2 ctrx = pmuls(x, sr), ctry = pmuls(y, sr);
+        const float2 box = pmuls(r, sr);
+        const float2 one = pk(1.0f, 1.0f), mone = pk(-1.0f, -1.0f);
+        float2 b0 = pfma(box, mone, ctrx), b1 = pfma(box, mone, ctry);
+        float2 b2 = pfma(box, one, ctrx), b3 = pfma(box, one, ctry);
+        b0 = pk(fminf(fmaxf(b0.x, -1.0f), 1.0f), fminf(fmaxf(b0.y, -1.0f), 1.0f));
+        b1 = pk(fminf(fmaxf(b1.x, -1.0f), 1.0f), fminf(fmaxf(b1.y, -1.0f), 1.0f));
+        b2 = pk(fminf(fmaxf(b2.x, -1.0f), 1.0f), fminf(fmaxf(b2.y, -1.0f), 1.0f));
+        b3 = pk(fminf(fmaxf(b3.x, -1.0f), 1.0f), fminf(fmaxf(b3.y, -1.0f), 1.0f));
+        const float2 h = pk(0.5f, 0.5f), nh = pk(-0.5f, -0.5f);
+        ax = pfma(b0, h, h); ay = pfma(b1, nh, h);
+        az = pfma(b2, h, h); aw = pfma(b3, nh, h);
+        const float kk = fdiv(1.0f, sub(ci.z_far, ci.z_near));
+        depth = pmuls(padd(k, pfma(r_model, s, z), pk(ci.z_far, ci.z_far)), kk);
+    } else {
+        return 3u;
+    }
+    const float2 W = pmuls(psub(k, az, ax), (float)hz.width);
+    const float2 H = pmuls(psub(k, aw, ay), (float)hz.height);
+    const float2 u = pmuls(padd(k, ax, az), 0.5f), v = pmuls(padd(k, ay, aw), 0.5f);
+    uint32_t vis = 0u;
+    {
+        const uint32_t lvl = hiz_level(fmaxf(W.x, H.x), hz.levels);
+        const float sampled = hiz_sample(hz, hiz_lw, hiz_lh, lvl, u.x, v.x);
+        if (!cull_a || depth.x >= sampled) vis |= 1u;
+    }
+    {
+        const uint32_t lvl = hiz_level(fmaxf(W.y, H.y), hz.levels);
+        const float sampled = hiz_sample(hz, hiz_lw, hiz_lh, lvl, u.y, v.y);
+        if (!cull_b || depth.y >= sampled) vis |= 2u;
+    }
+    return vis;
+}
+struct RecordWords { uint32_t ent, moff, cnt, vo; };
+
+// Hi-Z test of `n` (<= 64) queued candidates starting at ring position qhead (even), two per lane; publishes the
+// results (see the kernel comment) and returns the number of draws found by the warp. Inlined at its single call site (between tiles).
+template <int kProj>
+__device__ __forceinline__ uint32_t drain_candidates(const MeshletCullParams& p, const PkConsts& k, const uint32_t qbase, const uint32_t ring_mask, const uint32_t qhead,
+                                                  const uint32_t n, uint32_t* const chunk_counts, const uint32_t chunk_shift,
+                                                  const uint32_t hiz_lw, const uint32_t hiz_lh, const uint32_t lane) {
+    const OrbitCullInfo& ci = p.cull;
+    const uint32_t cs4 = (ring_mask + 1u) * 4u;      // bytes between the component arrays of the ring
+    uint32_t drawn = 0u;
+    if (2u * lane < n) {
+        // candidates 2*lane and 2*lane+1 sit in adjacent slots (qhead is even: the ring advances by 64 or empties)
+        const uint32_t qa = qbase + ((qhead + 2u * lane) & ring_mask) * 4u;
+        float2 cx, cy, cz, crm, cs;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cx.x), "=f"(cx.y) : "r"(qa) : "memory");
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cy.x), "=f"(cy.y) : "r"(qa + 1u * cs4) : "memory");
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cz.x), "=f"(cz.y) : "r"(qa + 2u * cs4) : "memory");
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(crm.x), "=f"(crm.y) : "r"(qa + 3u * cs4) : "memory");
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cs.x), "=f"(cs.y) : "r"(qa + 4u * cs4) : "memory");
+        uint32_t vis = occlusion_pair<kProj>(ci, k, cx, cy, cz, crm, cs, p.hiz, hiz_lw, hiz_lh);
+        if (2u * lane + 1u >= n) vis &= 1u;                               // odd tail: the second slot is stale
+#pragma unroll
+        for (uint32_t c = 0; c < 2u; ++c) {
+            if ((vis >> c) & 1u) {
+                const uint32_t rec = lds32(qa + 5u * cs4 + c * 4u), vo = lds32(qa + 6u * cs4 + c * 4u), id = lds32(qa + 7u * cs4 + c * 4u);
+                const uint32_t bit = 1u << (id & 31u);
+                atomicOr(p.meshlet_visibility + vo, bit);
+                // should_draw = visible && alpha passes the filter; in pass 2, unless the alpha mode is "noskip",
+                // should_draw = visible && !visible_last_frame (this overrides the alpha filter, meshlet_cull.comp:207-213)
+                const uint32_t abit = shl1(id >> 6);
+                const bool draw = (abit & ci.noskip_alpha_mode) ? (abit & ci.alpha_mode_flags) != 0u : (id & 32u) == 0u;
+                if (draw) {
+                    atomicOr(reinterpret_cast<uint32_t*>(p.draw_masks + rec), bit);
+                    atomicAdd(chunk_counts + (rec >> chunk_shift), 1u);
+                    ++drawn;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    return __reduce_add_sync(0xFFFFFFFFu, drawn);
+}
+
+// ---- TMA bulk copy + mbarrier plumbing (PTX; SASS: UBLKCP / SYNCS) --------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int R>
+struct __align__(128) WarpSmem {
+    uint4 meshlets[R * 64];        // R records x 32 meshlets x 2 x 16 B, filled by TMA
+    float mv[R][kMvStride];        // view*model + scale per record
+    float4 rows[R][4];             // model matrices of the NEXT tile's entities (cp.async, issued with the TMA copy)
+    uint32_t vis[4 * ((R + 3) / 4)];   // last frame's visibility words of the NEXT tile's records (pass 2)
+    uint32_t q[8][128];            // Hi-Z candidate ring (pass 2): x, y, z, r_model, scale, record, visibility offset, id
+    unsigned long long bar;        // mbarrier of the TMA copies
+};
+constexpr uint32_t kRing = 128u;
+#ifndef ORBIT_DIRECT_MIN_CTAS
+#define ORBIT_DIRECT_MIN_CTAS 3
+#endif
 
 // view * model (+ largest column scale) for every record of a tile: 16 lanes per record, two records per step
 template <int R>
-__device__ __forceinline__ void tile_model_view(const MeshletCullParams& p, float* mv_base, uint32_t my_word, uint32_t lane,
+__device__ __forceinline__ void tile_model_view(const float4* rows, float* mv_base, uint32_t my_word, uint32_t lane,
                                                 float v0, float v1, float v2, float v3) {
 #pragma unroll
     for (int st = 0; st < R / 2; ++st) {
         const uint32_t half = lane >> 4, e = lane & 15u;
-        const uint32_t ent = __shfl_sync(0xFFFFFFFFu, my_word, (2 * st + half) * 4 + 0);
         const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, my_word, (2 * st + half) * 4 + 2);
         if (cnt != 0u) {
-            const float4 b = __ldg(p.entities + (size_t)ent * 8u + (e >> 2));
+            const float4 b = rows[(2 * st + half) * 4 + (e >> 2)];
             mv_base[(2 * st + half) * kMvStride + e] = add(add(add(mul(v0, b.x), mul(v1, b.y)), mul(v2, b.z)), mul(v3, b.w));
         }
     }
@@ -202,29 +432,67 @@ __device__ __forceinline__ void tile_model_view(const MeshletCullParams& p, floa
 // ---------------------------------------------------------------------------------------------------------
 // Direct mode: pass 0, pass 2, and pass 1 without a meshlet visibility buffer — every lane of every record is
 // tested. kPass2 = (occlusion_pass == 2 && meshlet occlusion culling on); kProj as in test_item.
+//
+// Persistent warps; a TILE is R consecutive records, tested one after the other with lane j = meshlet j of the record
+// (the reference's 32-lane group, so a ballot is the reference's visibility word). Tile t belongs to CTA t % gridDim.x
+// (static, cyclic: every CTA gets the same mix of cheap and expensive stretches of the record list); inside the CTA the
+// warps take their CTA's tiles from a SHARED-MEMORY counter (first tile: the warp's index, the next two requested
+// ahead), because the cost of a record varies 3x between one whose meshlets all fail the frustum and one that queues 30
+// Hi-Z tests — with a static split the 2.5 tiles per warp of C2 quantise to 3, and a device-wide atomic ticket
+// (measured) serialises 13 k same-address atomics in L2 for as long as the math takes.
+// The tile's meshlets (R x 1 KB contiguous) are staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier,
+// one copy per record issued by R lanes): R KB per warp in flight without holding registers or scoreboards, the next
+// tile's copy issued as soon as the current one has been consumed; the record words are prefetched two tiles ahead.
+// (A per-lane register prefetch and per-lane cp.async staging were both measured and lost: profiles/r2_meshlet_test_history.txt.)
+// view*model is computed once per record by 16 lanes (two records per step) and broadcast through shared memory —
+// the reference recomputes the 4x4 product in every lane.
+//
+// Instruction issue, not HBM, bounds this stage, so the arithmetic of the pinned contract is issued two-wide (FMUL2 /
+// FFMA2, see PkConsts): across the components of a meshlet in the frustum / cone test (test_item_xy) and across two
+// candidates per lane in the Hi-Z test (occlusion_pair).
+//
+// Pass 2: lanes surviving frustum + cone are packed into a per-warp ring (8 words per candidate) and the Hi-Z
+// projection (5 IEEE divisions, 2 square roots) runs on 64 candidates at a time, two per lane, across record and tile
+// boundaries; only the very last drain of a warp is partial. Results leave per candidate: the records' visibility
+// words are stored as 0 when their tile starts and visible candidates OR their bit in afterwards (RED.OR; a __syncwarp
+// between the stores and the first drain orders the two), likewise the draw masks and the chunks' survivor counts — so
+// a record never waits for its candidates and there are no per-record result masks to carry.
 template <int R, bool kPass2, int kProj>
-__global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direct_kernel(const __grid_constant__ MeshletCullParams p) {
+__global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_test_direct_kernel(const __grid_constant__ MeshletCullParams p) {
     static_assert(R == 2 || R == 4 || R == 8, "records per warp tile");
     extern __shared__ __align__(128) unsigned char s_raw[];
-    WarpSmem<R>* const all = reinterpret_cast<WarpSmem<R>*>(s_raw);
+    WarpSmem<R>* const all = reinterpret_cast<WarpSmem<R>*>(s_raw + 128);
+    uint32_t* const s_next_tile = reinterpret_cast<uint32_t*>(s_raw);
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     WarpSmem<R>& ws = all[warp];
     const OrbitCullInfo& ci = p.cull;
+    const PkConsts k = {p.pk_one, p.pk_mone};
     pdl_wait();
+    if (threadIdx.x == 0) *s_next_tile = kMcWarps;
+    __syncthreads();
+    // ---- this CTA's tiles: local index j -> tile blockIdx.x + j * gridDim.x; j = warp first, then from the counter
+    auto fetch_tile = [&]() -> uint32_t {
+        uint32_t j = 0u;
+        if (lane == 0u) j = atomicAdd(s_next_tile, 1u);
+        j = __shfl_sync(0xFFFFFFFFu, j, 0);
+        const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x;
+        return t < 0x7FFFFFFFull ? (uint32_t)t : 0x7FFFFFFFu;
+    };
+    uint32_t t_cur = blockIdx.x + warp * gridDim.x, t_next = fetch_tile(), t_next2 = fetch_tile();
     // The record words of this warp's first two tiles are requested BEFORE the record count is known (bounded by the
     // dispatch buffer's capacity, masked by the count afterwards): one dependent round trip less in the prologue.
-    uint32_t spec_word0 = 0u, spec_word1 = 0u;
-    {
-        const uint32_t t0 = blockIdx.x * kMcWarps + warp, t1 = t0 + gridDim.x * kMcWarps;
-        const uint64_t ra = (uint64_t)t0 * R + (lane >> 2), rb = (uint64_t)t1 * R + (lane >> 2);
-        if (lane < 4u * R && ra < p.capacity_records) spec_word0 = __ldcg(p.dispatch_words + 3u + (size_t)t0 * R * 4u + lane);
-        if (lane < 4u * R && rb < p.capacity_records) spec_word1 = __ldcg(p.dispatch_words + 3u + (size_t)t1 * R * 4u + lane);
-    }
+    // record words of a tile: lane l < 4R holds word l (entity, meshlet_offset, meshlet_count, visibility_offset per record)
+    auto load_words = [&](uint32_t tile, uint64_t bound) -> uint32_t {
+        uint32_t w = 0u;
+        if (lane < 4u * R && (uint64_t)tile * R + (lane >> 2) < bound) w = __ldcg(p.dispatch_words + 3u + (size_t)tile * R * 4u + lane);
+        return w;
+    };
+    uint32_t cur_word = load_words(t_cur, p.capacity_records), next_word = load_words(t_next, p.capacity_records);
     uint32_t nrec = __ldcg(p.dispatch_words);  // workgroup_count_x written by the entity stage
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
-    const uint32_t chunk_rec = chunk_records(nrec);
+    const uint32_t chunk_shift = chunk_shift_of(nrec);
     // Scratch is double-buffered by a parity that lives in device memory (CUDA-graph replays must see fresh state).
     // Word A is read by test kernels and written by emit kernels; word B the other way round: a kernel never writes
     // a word that CTAs of the same launch read, so the stream order of the launches is the only synchronisation.
@@ -232,32 +500,38 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
     if (blockIdx.x == 0 && threadIdx.x == 0) p.chunk_parity[1] = half;
     uint32_t* const chunk_counts = p.chunk_counts + half * kMaxChunks;
     uint32_t* const draw_total = p.draw_total + half;
-    // cyclic tile assignment over all warps of the grid: balances hot and cold regions of the record list
     const uint32_t tiles_total = (nrec + R - 1) / R;
-    const uint32_t w_stride = gridDim.x * kMcWarps;
-    const uint32_t w_t0 = blockIdx.x * kMcWarps + warp;
-    const uint32_t w_t1 = tiles_total;
     // row `lane&3` of the view matrix, for the 16-lane view*model product
     const uint32_t vrow_i = lane & 3u;
     const float v0 = ci.view_matrix.m[0][vrow_i], v1 = ci.view_matrix.m[1][vrow_i];
     const float v2 = ci.view_matrix.m[2][vrow_i], v3 = ci.view_matrix.m[3][vrow_i];
+    const uint32_t hiz_lw = 31u - (uint32_t)__clz((int)max(p.hiz.width, 1u)), hiz_lh = 31u - (uint32_t)__clz((int)max(p.hiz.height, 1u));
     float* const mv_base = &ws.mv[0][0];
     const uint32_t bar = smem_addr(&ws.bar);
     const uint32_t buf = smem_addr(&ws.meshlets[0]);
+    const uint32_t qbase = smem_addr(&ws.q[0][0]);
+    const uint32_t rows_s = smem_addr(&ws.rows[0][0]), vis_s = smem_addr(&ws.vis[0]);
     if (lane == 0u) { mbar_init(bar, R); mbar_fence_init(); }
     __syncwarp();
     uint32_t parity = 0u;
 
-    // record words of a tile: lane l < 4R holds word l (entity, meshlet_offset, meshlet_count, visibility_offset per record)
-    auto load_words = [&](uint32_t tile) -> uint32_t {
-        uint32_t w = 0u;
-        if (tile < w_t1 && lane < 4u * R && tile * R + (lane >> 2) < nrec) w = __ldcg(p.dispatch_words + 3u + (size_t)tile * R * 4u + lane);
-        return w;
-    };
     // lane r < R issues the bulk copy of record r (count x 32 B) and arrives on the barrier
+    // ... and the tile's model matrices (lane l < 4R: column l&3 of record l>>2) and, in pass 2, last frame's visibility
+    // words (lane 16+r... of record r) go through cp.async into their staging slots: none of the three waits for a load
     auto issue_tma = [&](uint32_t words) {
         const uint32_t off = __shfl_sync(0xFFFFFFFFu, words, (lane * 4u + 1u) & 31u);
         const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, words, (lane * 4u + 2u) & 31u);
+        {
+            const uint32_t rr = (lane >> 2) & (uint32_t)(R - 1);
+            const uint32_t ent_r = __shfl_sync(0xFFFFFFFFu, words, rr * 4u + 0u), cnt_r = __shfl_sync(0xFFFFFFFFu, words, rr * 4u + 2u);
+            if (lane < 4u * R && cnt_r != 0u) cp_async_16(rows_s + lane * 16u, p.entities + (size_t)ent_r * 8u + (lane & 3u));
+            if (kPass2) {
+                const uint32_t rv = lane & (uint32_t)(R - 1);
+                const uint32_t vo_r = __shfl_sync(0xFFFFFFFFu, words, rv * 4u + 3u), cnt_v = __shfl_sync(0xFFFFFFFFu, words, rv * 4u + 2u);
+                if (lane >= 16u && lane < 16u + (uint32_t)R && cnt_v != 0u) cp_async_4(vis_s + rv * 4u, p.meshlet_visibility + vo_r);
+            }
+            cp_async_commit();
+        }
         if (lane < (uint32_t)R) {
             if (cnt != 0u) {
                 const uint32_t bytes = min(cnt, 32u) * 32u;
@@ -268,116 +542,112 @@ __global__ void __launch_bounds__(kMcThreads, kDirectMinCtas) meshlet_test_direc
             }
         }
     };
-
-    uint32_t warp_total = 0u;   // survivors found by this warp (lets the emit kernel skip everything when zero)
-    uint32_t cur_word = spec_word0, next_word = spec_word1;
     {   // the two speculative loads were bounded by the buffer capacity; now apply the real record count
-        const uint32_t rec_a = w_t0 * R + (lane >> 2), rec_b = (w_t0 + w_stride) * R + (lane >> 2);
-        if (!(lane < 4u * R && rec_a < nrec)) cur_word = 0u;
-        if (!(lane < 4u * R && rec_b < nrec)) next_word = 0u;
+        if (!(lane < 4u * R && (uint64_t)t_cur * R + (lane >> 2) < (uint64_t)nrec)) cur_word = 0u;
+        if (!(lane < 4u * R && (uint64_t)t_next * R + (lane >> 2) < (uint64_t)nrec)) next_word = 0u;
     }
-    if (w_t0 < w_t1) issue_tma(cur_word);
-    uint32_t qhead = 0u;   // ring-buffer read position (entries [qhead, qhead+qn) mod 64 are pending)
-    for (uint32_t tile = w_t0; tile < w_t1; tile += w_stride) {
-        const uint32_t rec0 = tile * R;
-        const uint32_t my_word = cur_word;
-        cur_word = next_word;
-        next_word = load_words(tile + 2u * w_stride);
-        // ---- lane r keeps count / visibility offset / visibility word of record r
-        const uint32_t my_cnt = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 2u) & 31u);
-        const uint32_t my_vo = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 3u) & 31u);
-        uint32_t vw = 0xFFFFFFFFu;   // pass 2: last frame's visibility (decides should_draw); otherwise unused
-        if (kPass2 && lane < (uint32_t)R && my_cnt != 0u) vw = __ldcg(p.meshlet_visibility + my_vo);
-        tile_model_view<R>(p, mv_base, my_word, lane, v0, v1, v2, v3);
-
-        uint32_t qn = 0u;
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-        // The record loop is deliberately NOT unrolled: four inlined copies of the test (~600 SASS instructions each)
-        // overflowed the instruction cache (9% of issue stalls were "no instruction"); per-record results live in
-        // shared memory as warp-uniform 32-bit masks instead of register arrays.
+    uint32_t warp_total = 0u;   // survivors found by this warp (lets the emit kernel skip everything when zero)
+    uint32_t qhead = 0u, qn = 0u;   // ring-buffer read position and fill (entries [qhead, qhead+qn) mod 128 are pending)
+    if (t_cur < tiles_total) issue_tma(cur_word);
+    // One extra, empty iteration after the last tile flushes what is left in the ring through the same drain code.
+    bool final_pass = t_cur >= tiles_total;
+    while (true) {
+        const uint32_t rec0 = t_cur * R;
+        const uint32_t my_word = final_pass ? 0u : cur_word;
+        uint32_t my_mask = 0u;       // lane r < R: draw mask of record r (passes without Hi-Z)
+        uint32_t vw = 0u;            // lane r < R, pass 2: last frame's visibility word of record r (decides should_draw)
+        if (!final_pass) {
+            cur_word = next_word;
+            next_word = t_next2 < tiles_total ? load_words(t_next2, nrec) : 0u;
+            if (kPass2) {
+                // lane r: the record's visibility word is read, then stored as 0 — visible candidates OR their bits in
+                // afterwards (meshlet_cull.comp:235-242); likewise the draw mask
+                const uint32_t ent = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 0u) & 31u);
+                const uint32_t mof = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 1u) & 31u);
+                const uint32_t my_cnt = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 2u) & 31u);
+                const uint32_t my_vo = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 3u) & 31u);
+                cp_async_wait_all();
+                __syncwarp();
+                if (lane < (uint32_t)R && my_cnt != 0u) {
+                    vw = ws.vis[lane];
+                    p.meshlet_visibility[my_vo] = 0u;
+                }
+                if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(0u, ent, mof, 0u);
+            } else {
+                cp_async_wait_all();
+                __syncwarp();
+            }
+            tile_model_view<R>(&ws.rows[0][0], mv_base, my_word, lane, v0, v1, v2, v3);
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        }
+        // The record loop is deliberately NOT unrolled (instruction cache). The extra, empty iteration after a warp's last
+        // tile (final_pass) only runs the drain below, on whatever is left in the ring.
 #pragma unroll 1
         for (uint32_t r = 0; r < (uint32_t)R; ++r) {
             const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, my_word, r * 4u + 2u);   // 0 for records past the end
-            if (cnt == 0u) { if (lane == 0u) { ws.mask[r] = 0u; ws.aok[r] = 0u; ws.nsk[r] = 0u; } continue; }   // warp-uniform
-            bool pre = false, alpha_ok = false, noskip = false;
-            ItemTest t;
-            if (lane < cnt) {
+            if (cnt != 0u) {                                                        // warp-uniform
+                const float* mvr = mv_base + r * kMvStride;
+                const float4 c0 = *reinterpret_cast<const float4*>(mvr), c1 = *reinterpret_cast<const float4*>(mvr + 4);
+                const float4 c2 = *reinterpret_cast<const float4*>(mvr + 8), c3 = *reinterpret_cast<const float4*>(mvr + 12);
+                const float scale = mvr[16];
+                const bool in_rec = lane < cnt;
                 const uint4 a = ws.meshlets[r * 64u + lane * 2u];
                 const uint4 b = ws.meshlets[r * 64u + lane * 2u + 1u];
-                const uint32_t alpha = __ldg(reinterpret_cast<const uint32_t*>(
+                uint32_t alpha = 32u;                                               // out-of-record lanes: no alpha bit
+                if (in_rec) alpha = __ldg(reinterpret_cast<const uint32_t*>(      // L1-resident table; issued here, used after the test
                     p.materials + (size_t)(b.w & 0xFFFFu) * ORBIT_MATERIAL_STRIDE_BYTES + ORBIT_MATERIAL_ALPHA_MODE_OFFSET));
-                alpha_ok = (shl1(alpha) & ci.alpha_mode_flags) != 0u;
-                noskip = (shl1(alpha) & ci.noskip_alpha_mode) != 0u;
-                t = test_item<kProj>(ci, mv_base + r * kMvStride, a, b.x);
-                pre = t.pre_visible;
+                const ItemXY t = test_item_xy<kProj>(ci, p, k, c0, c1, c2, c3, scale, __uint_as_float(a.x), __uint_as_float(a.y),
+                                                     __uint_as_float(a.z), __uint_as_float(a.w), b.x);
+                const bool pre = in_rec && t.pre_visible;
+                if (!kPass2) {
+                    // should_draw = visible && alpha passes the filter (meshlet_cull.comp:207)
+                    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pre && (shl1(alpha) & ci.alpha_mode_flags) != 0u);
+                    if (lane == r) my_mask = mask;
+                } else {
+                    // queue the survivors for the Hi-Z test
+                    const uint32_t pre_mask = __ballot_sync(0xFFFFFFFFu, pre);
+                    const uint32_t vwr = __shfl_sync(0xFFFFFFFFu, vw, r);
+                    const uint32_t vo = __shfl_sync(0xFFFFFFFFu, my_word, r * 4u + 3u);
+                    if (pre) {
+                        // id word: lane | visible-last-frame << 5 | min(alpha mode, 32) << 6 (alpha modes >= 32 select no bit)
+                        const uint32_t id = lane | (((vwr >> lane) & 1u) << 5) | (min(alpha, 32u) << 6);
+                        const uint32_t qa = qbase + ((qhead + qn + (uint32_t)__popc(pre_mask & lt)) & (kRing - 1u)) * 4u;
+                        constexpr uint32_t cs4 = kRing * 4u;
+                        sts32(qa, __float_as_uint(t.pxy.x)); sts32(qa + cs4, __float_as_uint(t.pxy.y)); sts32(qa + 2u * cs4, __float_as_uint(t.pz));
+                        sts32(qa + 3u * cs4, a.w); sts32(qa + 4u * cs4, __float_as_uint(scale));
+                        sts32(qa + 5u * cs4, rec0 + r); sts32(qa + 6u * cs4, vo); sts32(qa + 7u * cs4, id);
+                    }
+                    qn += (uint32_t)__popc(pre_mask);
+                }
             }
-            const uint32_t pre_mask = __ballot_sync(0xFFFFFFFFu, pre);
-            const uint32_t aok_mask = __ballot_sync(0xFFFFFFFFu, alpha_ok);
-            const uint32_t nsk_mask = kPass2 ? __ballot_sync(0xFFFFFFFFu, noskip) : 0u;
-            if (lane == 0u) { ws.mask[r] = pre_mask; ws.aok[r] = aok_mask; ws.nsk[r] = nsk_mask; }
-            if (kPass2) {
-                // queue the survivors for the Hi-Z test; run it whenever a full warp of them is waiting
-                if (pre) {
-                    const uint32_t slot = (qhead + qn + __popc(pre_mask & lt)) & 63u;
-                    ws.q[0][slot] = t.s.x; ws.q[1][slot] = t.s.y; ws.q[2][slot] = t.s.z;
-                    ws.q[3][slot] = t.s.r; ws.q[4][slot] = t.s.r_model; ws.q[5][slot] = t.s.s;
-                    ws.qid[slot] = (r << 5) | lane;
-                }
-                qn += __popc(pre_mask);
+            // ---- Hi-Z test of 64 queued candidates (the ring holds the < 64 left over plus a record's 32); the warp's
+            // very last drain takes whatever is left
+            if (kPass2 && (qn >= 64u || (final_pass && qn != 0u))) {
+                const uint32_t n = min(qn, 64u);
                 __syncwarp();
-                if (qn >= 32u) {
-                    const uint32_t slot = (qhead + lane) & 63u;
-                    Sphere s;
-                    s.x = ws.q[0][slot]; s.y = ws.q[1][slot]; s.z = ws.q[2][slot];
-                    s.r = ws.q[3][slot]; s.r_model = ws.q[4][slot]; s.s = ws.q[5][slot];
-                    const uint32_t id = ws.qid[slot];
-                    if (!occlusion_test<kProj>(ci, s, p.hiz)) atomicAnd(&ws.mask[id >> 5], ~(1u << (id & 31u)));
-                    qhead = (qhead + 32u) & 63u;
-                    qn -= 32u;
-                    __syncwarp();
-                }
+                warp_total += drain_candidates<kProj>(p, k, qbase, kRing - 1u, qhead, n, chunk_counts, chunk_shift, hiz_lw, hiz_lh, lane);
+                qhead = (qhead + n) & (kRing - 1u);
+                qn -= n;
             }
         }
+        if (final_pass) break;
         // every lane has read its meshlets: the staging buffer is free -> start the next tile's copy now
         __syncwarp();
-        if (tile + w_stride < w_t1) issue_tma(cur_word);
-        if (kPass2) {
-            if (lane < qn) {
-                const uint32_t slot = (qhead + lane) & 63u;
-                Sphere s;
-                s.x = ws.q[0][slot]; s.y = ws.q[1][slot]; s.z = ws.q[2][slot];
-                s.r = ws.q[3][slot]; s.r_model = ws.q[4][slot]; s.s = ws.q[5][slot];
-                const uint32_t id = ws.qid[slot];
-                if (!occlusion_test<kProj>(ci, s, p.hiz)) atomicAnd(&ws.mask[id >> 5], ~(1u << (id & 31u)));
-            }
-            qhead = (qhead + qn) & 63u;
-            __syncwarp();
-        }
-        // lane r < R finishes record r with warp-uniform bit logic (meshlet_cull.comp:207-213):
-        //   should_draw = visible && alpha passes the filter; in pass 2, unless the alpha mode is "noskip",
-        //   should_draw = visible && !visible_last_frame (this overrides the alpha filter)
-        uint32_t my_draw_mask = 0u;
-        if (lane < (uint32_t)R) {
-            const uint32_t vis = ws.mask[lane], aok = ws.aok[lane], nsk = ws.nsk[lane];
-            if (kPass2) {
-                if (my_cnt != 0u) p.meshlet_visibility[my_vo] = vis;   // ballot(visible), meshlet_cull.comp:235-242
-                my_draw_mask = vis & ((nsk & aok) | (~nsk & ~vw));
-            } else {
-                my_draw_mask = vis & aok;
-            }
-        }
-        __syncwarp();
-        // one {draw mask, entity, meshlet offset} per record, kept L2-resident for the emit kernel (so it needs one
-        // load per record and never touches the dispatch buffer); survivors counted per chunk
-        {
+        if (t_next < tiles_total) issue_tma(cur_word);
+        if (!kPass2) {
+            // one {draw mask, entity, meshlet offset} per record, kept L2-resident for the emit kernel (so it needs one
+            // load per record and never touches the dispatch buffer); survivors counted per chunk
             const uint32_t ent = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 0u) & 31u);
             const uint32_t mof = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 1u) & 31u);
-            if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(my_draw_mask, ent, mof, 0u);
+            if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(my_mask, ent, mof, 0u);
+            const uint32_t tile_total = __reduce_add_sync(0xFFFFFFFFu, __popc(my_mask));
+            if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + (rec0 >> chunk_shift), tile_total);   // a tile never straddles a chunk
+            warp_total += tile_total;
         }
-        const uint32_t tile_total = __reduce_add_sync(0xFFFFFFFFu, __popc(my_draw_mask));
-        if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + rec0 / chunk_rec, tile_total);
-        warp_total += tile_total;
+        t_cur = t_next; t_next = t_next2;
+        t_next2 = t_next2 < tiles_total ? fetch_tile() : 0x7FFFFFFFu;
+        final_pass = t_cur >= tiles_total;
     }
     pdl_launch_dependents();
     if (lane == 0u && warp_total != 0u) atomicAdd(draw_total, warp_total);
@@ -457,8 +727,8 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
     uint32_t cur_word = spec_words(tile0), next_word = spec_words(tile0 + w_stride);
     uint32_t nrec = __ldcg(p.dispatch_words);
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
-    const uint32_t chunk_rec = chunk_records(nrec);
-    const uint32_t half = __ldcg(p.chunk_parity) & 1u;   // see meshlet_test_direct_kernel
+    const uint32_t chunk_rec = 1u << chunk_shift_of(nrec);
+    const uint32_t half = __ldcg(p.chunk_parity) & 1u;   // see meshlet_test_stream_kernel
     if (blockIdx.x == 0 && threadIdx.x == 0) p.chunk_parity[1] = half;
     uint32_t* const chunk_counts = p.chunk_counts + half * kMaxChunks;
     uint32_t* const draw_total = p.draw_total + half;
@@ -507,7 +777,10 @@ __global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(cons
                     const uint32_t r = id >> 5, j = id & 31u;
                     const uint4* m = p.meshlets + 2u * ((size_t)moff + j);
                     const uint4 a = __ldg(m), b = __ldg(m + 1);
-                    const ItemTest t = test_item<-1>(ci, mv_base + r * kMvStride, a, b.x);
+                    const float* mvr = mv_base + r * kMvStride;
+                    const ItemTest t = test_item<-1>(ci, *reinterpret_cast<const float4*>(mvr), *reinterpret_cast<const float4*>(mvr + 4),
+                                                     *reinterpret_cast<const float4*>(mvr + 8), *reinterpret_cast<const float4*>(mvr + 12), mvr[16],
+                                                     __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w), b.x);
                     if (draw_rule(ci, p, t.pre_visible, true, false, b.w)) atomicOr(&ws.mask[r], 1u << j);
                 }
             }
@@ -590,7 +863,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
     if (blockIdx.x == 0 && tid == 0) { p.draw_total[parity ^ 1u] = 0u; p.chunk_parity[0] = parity ^ 1u; }   // word A for the next call
     const uint32_t gw = blockIdx.x * kEmitWarps + warp, GW = gridDim.x * kEmitWarps;
     if (grand_total != 0u) {
-        const uint32_t chunk_rec = chunk_records(nrec);
+        const uint32_t chunk_rec = 1u << chunk_shift_of(nrec);
         const uint32_t nchunks = (nrec + chunk_rec - 1u) / chunk_rec;
         // ---- 1. chunk counts -> inclusive prefix in shared memory (8 consecutive chunks per thread)
         uint32_t v[8], local = 0u;
@@ -732,48 +1005,48 @@ static TestVariant variant_of(const OrbitCullInfo& ci) {
     return v;
 }
 
-template <int R, bool kPass2, int kProj>
-static cudaError_t launch_direct(const MeshletCullParams& p, int grid, cudaStream_t stream, int* occupancy) {
-    const size_t smem = sizeof(WarpSmem<R>) * kMcWarps;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(meshlet_test_direct_kernel<R, kPass2, kProj>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+#ifndef ORBIT_TILE_RECORDS
+#define ORBIT_TILE_RECORDS 4
+#endif
+constexpr int kTileR = ORBIT_TILE_RECORDS;   // records per warp tile of the direct test kernel
+static constexpr size_t direct_smem_bytes() { return 128u + sizeof(WarpSmem<kTileR>) * kMcWarps; }
+
+template <bool kPass2, int kProj>
+static cudaError_t launch_stream(const MeshletCullParams& p, int grid, cudaStream_t stream, int* occupancy) {
     if (occupancy) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_direct_kernel<R, kPass2, kProj>, kMcThreads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_direct_kernel<kTileR, kPass2, kProj>, kMcThreads, direct_smem_bytes());
         return cudaSuccess;
     }
-    return launch_kernel(meshlet_test_direct_kernel<R, kPass2, kProj>, dim3(grid), dim3(kMcThreads), smem, stream, p);
+    return launch_kernel(meshlet_test_direct_kernel<kTileR, kPass2, kProj>, dim3(grid), dim3(kMcThreads), direct_smem_bytes(), stream, p);
 }
 
-template <int R>
+// The direct test kernels use more than 48 KB of dynamic shared memory: opt in once per DEVICE (the attribute is per device,
+// so this is called from orbit_ctx_create with the context's device current).
+cudaError_t meshlet_cull_configure_device() {
+    cudaError_t e;
+#define ORBIT_SET(kp2, proj) \
+    e = cudaFuncSetAttribute(meshlet_test_direct_kernel<kTileR, kp2, proj>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)direct_smem_bytes()); \
+    if (e != cudaSuccess) return e;
+    ORBIT_SET(false, 0) ORBIT_SET(false, 1) ORBIT_SET(false, -1) ORBIT_SET(true, 0) ORBIT_SET(true, 1) ORBIT_SET(true, -1)
+#undef ORBIT_SET
+    return cudaSuccess;
+}
+
 static cudaError_t launch_test(const MeshletCullParams& p, int grid, cudaStream_t stream, int* occupancy) {
     const TestVariant v = variant_of(p.cull);
     if (v.packed) {
-        // the packed kernel fills its 32-lane test batches from a whole tile: with the default R = 4 a batch is 44 % full
-        // on C2, so it takes 8-record tiles instead (measured 8.9 -> 8.4 us); ORBIT_MC_RECS_PER_WARP=2 or 8 are taken as given
-        constexpr int RP = R == 4 ? 8 : R;
-        if (occupancy) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_packed_kernel<RP>, kMcThreads, 0); return cudaSuccess; }
-        return launch_kernel(meshlet_test_packed_kernel<RP>, dim3(grid), dim3(kMcThreads), 0, stream, p);
+        // the packed kernel fills its 32-lane test batches from a whole tile of 8 records (a 4-record tile's batch is 44 % full on C2)
+        if (occupancy) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_packed_kernel<8>, kMcThreads, 0); return cudaSuccess; }
+        return launch_kernel(meshlet_test_packed_kernel<8>, dim3(grid), dim3(kMcThreads), 0, stream, p);
     }
     if (v.pass2) {
-        if (v.proj == 0) return launch_direct<R, true, 0>(p, grid, stream, occupancy);
-        if (v.proj == 1) return launch_direct<R, true, 1>(p, grid, stream, occupancy);
-        return launch_direct<R, true, -1>(p, grid, stream, occupancy);
+        if (v.proj == 0) return launch_stream<true, 0>(p, grid, stream, occupancy);
+        if (v.proj == 1) return launch_stream<true, 1>(p, grid, stream, occupancy);
+        return launch_stream<true, -1>(p, grid, stream, occupancy);
     }
-    if (v.proj == 0) return launch_direct<R, false, 0>(p, grid, stream, occupancy);
-    if (v.proj == 1) return launch_direct<R, false, 1>(p, grid, stream, occupancy);
-    return launch_direct<R, false, -1>(p, grid, stream, occupancy);
-}
-
-static cudaError_t launch_test_r(const MeshletCullParams& p, int recs_per_warp, int grid, cudaStream_t stream, int* occupancy) {
-    switch (recs_per_warp) {
-        case 2: return launch_test<2>(p, grid, stream, occupancy);
-        case 8: return launch_test<8>(p, grid, stream, occupancy);
-        default: return launch_test<4>(p, grid, stream, occupancy);
-    }
+    if (v.proj == 0) return launch_stream<false, 0>(p, grid, stream, occupancy);
+    if (v.proj == 1) return launch_stream<false, 1>(p, grid, stream, occupancy);
+    return launch_stream<false, -1>(p, grid, stream, occupancy);
 }
 
 // Index of the kernel variant a CullInfo selects (api.cu caches one occupancy per variant).
@@ -782,15 +1055,15 @@ int meshlet_cull_variant_index(const OrbitCullInfo& ci) {
     return v.packed ? 0 : 1 + (v.pass2 ? 3 : 0) + (v.proj + 1);
 }
 
-int meshlet_cull_max_ctas_per_sm(const MeshletCullParams& p, int recs_per_warp) {
+int meshlet_cull_max_ctas_per_sm(const MeshletCullParams& p) {
     int n = 0;
-    launch_test_r(p, recs_per_warp, 0, nullptr, &n);
+    launch_test(p, 0, nullptr, &n);
     return n;
 }
 
-cudaError_t launch_meshlet_cull(const MeshletCullParams& p, int recs_per_warp, int grid, int emit_grid, cudaStream_t stream) {
+cudaError_t launch_meshlet_cull(const MeshletCullParams& p, int grid, int emit_grid, cudaStream_t stream) {
     if (grid > 0) {
-        cudaError_t e = launch_test_r(p, recs_per_warp, grid, stream, nullptr);
+        cudaError_t e = launch_test(p, grid, stream, nullptr);
         if (e != cudaSuccess) return e;
     }
     if (emit_grid > 0) return launch_kernel(meshlet_emit_kernel, dim3(emit_grid), dim3(kEmitWarps * 32), 0, stream, p);

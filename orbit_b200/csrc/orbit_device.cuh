@@ -92,47 +92,49 @@ ORBIT_DEV bool frustum_test(const OrbitCullInfo& ci, const Sphere& s) {
     return visible;
 }
 
-// Nearest-mip level of lod = log2(x), exact on exponent / mantissa (no log2 evaluation), clamped.
+// Nearest-mip level of lod = log2(x), exact on exponent / mantissa (no log2 evaluation), clamped to [0, levels-1].
+// Branch-free: x <= 0 / NaN / denormal -> 0, +inf -> levels-1; for a normal x = m * 2^e the level is e + (m > fl(sqrt 2)),
+// and adding (0x800000 - 0x3504F4) to the bit pattern carries into the exponent exactly when the 23 mantissa bits exceed
+// those of fl(sqrt 2) = 0x3FB504F3. (Was ~20 instructions with three branches; the oracle keeps the branching form.)
 ORBIT_DEV uint32_t hiz_level(float x, uint32_t levels) {
-    if (!(x > 0.0f)) return 0u;
-    uint32_t u = __float_as_uint(x);
-    if (u >= 0x7F800000u) return levels - 1u;
-    if (u < 0x00800000u) return 0u;
-    int e = (int)(u >> 23) - 127;
-    float m = __uint_as_float((u & 0x007FFFFFu) | 0x3F800000u);
-    int k = e + (m > 1.41421354f ? 1 : 0);
-    k = max(k, 0);
-    k = min(k, (int)levels - 1);
-    return (uint32_t)k;
+    const float xc = fmaxf(x, 0.0f);                                  // NaN, negatives, -0 -> +-0
+    const int k = ((int)(__float_as_uint(xc) + 0x004AFB0Cu) >> 23) - 127;
+    return (uint32_t)min(max(k, 0), (int)levels - 1);
 }
 
-// Depth pyramid as the kernels see it: one linear allocation, levels back to back.
+// Depth pyramid as the kernels see it: one linear allocation, levels back to back. Level sizes are powers of two
+// (orbit_hiz_geometry: npot(depth)/2), which the sampling code below relies on.
 struct HizDevice {
     const float* texels;
     uint32_t width, height, levels;
     uint32_t level_offset[ORBIT_HIZ_MAX_LEVELS];
 };
 
-ORBIT_DEV void footprint(float u, uint32_t w, int& i0, int& i1) {
-    float fx = sub(mul(u, (float)w), 0.5f);
-    float f = floorf(fx);
-    int a;
-    if (!(f >= 0.0f)) a = -1; else if (f >= (float)w) a = (int)w; else a = (int)f;
-    int hi = (int)w - 1;
+// Texel indices i0, i1 of the bilinear footprint along one axis of a level whose size is 2^lw (as float: wf):
+//   fx = u*w - 0.5; i0 = floor(fx); i1 = i0 + 1, both clamped to [0, w-1]   (NaN -> the pair (0, 0))
+// fmaxf(fx, -1) maps NaN and everything below -1 to -1, fminf(., w) everything above w to w, so the conversion cannot
+// overflow and the clamps are two integer min/max.
+ORBIT_DEV void footprint(float u, float wf, int hi, int& i0, int& i1) {
+    const float fx = sub(mul(u, wf), 0.5f);
+    const int a = __float2int_rd(fminf(fmaxf(fx, -1.0f), wf));      // in [-1, w]
     i0 = min(max(a, 0), hi);
-    i1 = min(max(a + 1, 0), hi);
+    i1 = min(a + 1, hi);
 }
 
+ORBIT_DEV void footprint(float u, uint32_t w, int& i0, int& i1) { footprint(u, (float)w, (int)w - 1, i0, i1); }   // any size (depth buffer)
+
 // ReduceMin sampler (device.rs:1404-1420) on level `lvl`: min of the 2x2 bilinear footprint, read through the
-// non-coherent (texture / L1) path.
-ORBIT_DEV float hiz_sample(const HizDevice& hz, uint32_t lvl, float u, float v) {
-    uint32_t w = max(hz.width >> lvl, 1u), h = max(hz.height >> lvl, 1u);
-    const float* base = hz.texels + hz.level_offset[lvl];
+// non-coherent (texture / L1) path with 32-bit texel indices.
+ORBIT_DEV float hiz_sample(const HizDevice& hz, uint32_t lw0, uint32_t lh0, uint32_t lvl, float u, float v) {
+    const uint32_t lw = lw0 > lvl ? lw0 - lvl : 0u, lh = lh0 > lvl ? lh0 - lvl : 0u;   // log2 of the level's size
+    const float wf = __uint_as_float((127u + lw) << 23), hf = __uint_as_float((127u + lh) << 23);
     int x0, x1, y0, y1;
-    footprint(u, w, x0, x1);
-    footprint(v, h, y0, y1);
-    float a = __ldg(base + (size_t)y0 * w + x0), b = __ldg(base + (size_t)y0 * w + x1);
-    float c = __ldg(base + (size_t)y1 * w + x0), d = __ldg(base + (size_t)y1 * w + x1);
+    footprint(u, wf, (int)((1u << lw) - 1u), x0, x1);
+    footprint(v, hf, (int)((1u << lh) - 1u), y0, y1);
+    const uint32_t base = hz.level_offset[lvl];
+    const uint32_t r0 = base + ((uint32_t)y0 << lw), r1 = base + ((uint32_t)y1 << lw);
+    const float a = __ldg(hz.texels + (r0 + (uint32_t)x0)), b = __ldg(hz.texels + (r0 + (uint32_t)x1));
+    const float c = __ldg(hz.texels + (r1 + (uint32_t)x0)), d = __ldg(hz.texels + (r1 + (uint32_t)x1));
     return fminf(fminf(a, b), fminf(c, d));
 }
 
@@ -140,7 +142,7 @@ ORBIT_DEV float hiz_sample(const HizDevice& hz, uint32_t lvl, float u, float v) 
 // (the entity stage's LOD distance later reads the negated value, as in the reference).
 // kProj: 0 perspective, 1 orthographic, -1 decided at run time from ci.projection_type.
 template <int kProj = -1>
-ORBIT_DEV bool occlusion_test(const OrbitCullInfo& ci, Sphere& s, const HizDevice& hz) {
+ORBIT_DEV bool occlusion_test(const OrbitCullInfo& ci, Sphere& s, const HizDevice& hz, const uint32_t hiz_lw, const uint32_t hiz_lh) {
     float ax, ay, az, aw, depth;
     const uint32_t proj = kProj >= 0 ? (uint32_t)kProj : ci.projection_type;
     if (proj == 0u) {
@@ -183,8 +185,12 @@ ORBIT_DEV bool occlusion_test(const OrbitCullInfo& ci, Sphere& s, const HizDevic
     float H = mul(sub(aw, ay), (float)hz.height);
     float u = mul(add(ax, az), 0.5f), v = mul(add(ay, aw), 0.5f);
     uint32_t lvl = hiz_level(fmaxf(W, H), hz.levels);
-    float sampled = hiz_sample(hz, lvl, u, v);
+    float sampled = hiz_sample(hz, hiz_lw, hiz_lh, lvl, u, v);
     return depth >= sampled;
+}
+template <int kProj = -1>
+ORBIT_DEV bool occlusion_test(const OrbitCullInfo& ci, Sphere& s, const HizDevice& hz) {
+    return occlusion_test<kProj>(ci, s, hz, 31u - (uint32_t)__clz((int)max(hz.width, 1u)), 31u - (uint32_t)__clz((int)max(hz.height, 1u)));
 }
 
 // Loads that are issued where they are written. In the latency-bound kernels the order of the independent loads is

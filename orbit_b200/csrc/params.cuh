@@ -37,6 +37,8 @@ struct MeshletCullParams {
     uint32_t* chunk_parity;           // scratch[2]: word A (read by test, written by emit), word B (written by test, read by emit)
     uint64_t capacity_records;
     uint64_t capacity_draws;
+    float2 pk_one, pk_mone;           // (1, 1) and (-1, -1): operands of the packed add / subtract (see PkConsts in meshlet_cull.cu)
+    float2 planes_t[6][4];            // cull planes paired for the packed test: [j][c] = (planes[2j][c], planes[2j+1][c]); an odd last plane is repeated
     ScanState scan;
 };
 
@@ -93,10 +95,11 @@ struct ClusterParams {
     ScanState scan;
 };
 
-cudaError_t launch_meshlet_cull(const MeshletCullParams&, int recs_per_warp, int grid, int emit_grid, cudaStream_t);
+cudaError_t launch_meshlet_cull(const MeshletCullParams&, int grid, int emit_grid, cudaStream_t);
 int meshlet_emit_max_ctas_per_sm();
-int meshlet_cull_max_ctas_per_sm(const MeshletCullParams&, int recs_per_warp);
+int meshlet_cull_max_ctas_per_sm(const MeshletCullParams&);
 int meshlet_cull_variant_index(const OrbitCullInfo&);
+cudaError_t meshlet_cull_configure_device();
 cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t);
 int entity_cull_max_ctas_per_sm();
 cudaError_t launch_hiz_build(const HizBuildParams&, cudaStream_t);
