@@ -4,10 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Workload (N=1): BASELINE config C2 — procedural 10k-entity / 2M-meshlet city, one 1920x1080 view, two-pass
-occlusion. One *step* = the reference's depth-prepass culling of one steady-state frame
-(forward.rs:266-403): EARLY entity+meshlet cull (pass 1) -> Hi-Z build -> LATE entity+meshlet cull (pass 2),
-7 kernel launches (the meshlet stage is a test kernel + an emit kernel). `value` = scene meshlet instances x views / step time with every input resident in HBM;
+occlusion. One *step* = the reference's culling of one steady-state frame (BASELINE.md protocol):
+EARLY entity+meshlet cull (pass 1) -> Hi-Z build -> LATE entity+meshlet cull (pass 2) (forward.rs:266-403), then the
+MAIN pass (pass 1 again with the bits the late pass wrote, forward.rs:518-548): 10 kernel launches (the meshlet stage is a
+test kernel + an emit kernel). `value` = scene meshlet instances x views / step time with every input resident in HBM;
 the step rotates over 4 independent copies of the scene + view state (> L2) so inputs come from HBM.
+Besides the contract's K timed steps the line carries `repeats` (5 x >= 50 steps: median and min), `moving_camera`
+(a frame whose late pass finds survivors), and — nested, not separate lines — `c3_sharded` and `c5_many_view`:
+the two BASELINE configs whose work is split over the ranks, each with a parity bit against the oracle.
 N>1 (torchrun, one rank per GPU): views are sharded over GPUs with no data-path collective (each rank culls
 its own instance of the C2 view on a replicated city) -> weak scaling; value = sum of meshlets over ranks / max-over-ranks time.
 
@@ -36,7 +40,9 @@ import numpy as np  # noqa: E402
 
 METRIC = "Gmeshlets culled/s (C2: 10k entities / 2M meshlets, 1920x1080, two-pass occlusion, steady-state frame)"
 UNIT = "Gmeshlets/s"
+WORKLOAD = "C2 city 10k entities / 2M meshlets, one 1920x1080 view per GPU, steady-state frame: early cull + Hi-Z + late cull + main cull"
 N_COPIES = 4
+KERNELS_PER_STEP = 10   # 3 x entity_cull, 3 x (meshlet test + meshlet_emit), 1 x hiz_build
 
 
 def c2_view(scenes, scene, index):
@@ -94,7 +100,7 @@ def measured_peak_gbs():
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_final_meshlet_test_ncu.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_meshlet_test_ncu.json")) as f:
             return int(json.load(f)["dram_traffic_bytes_per_launch"])
     except Exception:
         return None
@@ -117,30 +123,210 @@ def run_reference(args, rank, world):
     import oracle_ref as O
     from orbit_b200 import scenes
     O.build()
+    O.lib().oracle_set_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: ask for every host thread explicitly
     scene, _ = scenes.config_c2()
     view = c2_view(scenes, scene, 0)
     depth = scenes.make_depth(scene, view)
     hs = O.HostScene(scene)
+
+    def frame_once():
+        O.depth_prepass_culling(hs, view, depth)
+        O.main_pass_culling(hs, view)
     for _ in range(2):  # reach the steady state (frame 0 fills the visibility bits)
-        O.depth_prepass_culling(hs, view, depth)
+        frame_once()
     for _ in range(max(args.warmup, 1)):
-        O.depth_prepass_culling(hs, view, depth)
+        frame_once()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.depth_prepass_culling(hs, view, depth)
+        frame_once()
     dt = (time.perf_counter() - t0) / args.steps
     value = scene.n_meshlet_instances / dt / 1e9
     cores = int(O.lib().oracle_threads())
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 city 10k entities / 2M meshlets, 1 view 1920x1080, steady-state frame: early cull + Hi-Z + late cull",
-                       "note": "reference GLSL cannot run here (no Vulkan/Rust); CPU restatement of the shaders (oracle port)"},
+            "config": {"workload": WORKLOAD,
+                       "note": "the reference's GLSL needs Rust + a Vulkan loader (neither in the image); CPU restatement of the shaders (oracle port), one view"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d whole C2 frames (early+Hi-Z+late), OpenMP over %d host threads" % (args.steps, cores)},
+                             "sample": "%d whole C2 frames (early + Hi-Z + late + main), OpenMP over %d host threads" % (args.steps, cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+
+def sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).tobytes()).hexdigest()[:16]
+
+
+def event_us(fn, reps=5):
+    import torch
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def max_over_ranks(values, dev, world):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return [float(v) for v in values]
+    t = torch.tensor(list(values), device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.tolist()]
+
+
+def moving_camera_extra(ctx, frame, scenes, scene, copies, O):
+    """A frame whose late pass finds survivors: every scene copy alternates between the named C2 camera (A) and the same
+    camera yawed by 15 degrees (B), both on ONE ViewState, so each frame reads the visibility bits the OTHER camera's
+    frame wrote. Parity: copy 0's B-after-A frame against the oracle, outside the timed region."""
+    import torch
+    view_a, view_b = copies[0].view, c2_view(scenes, scene, 4)
+    depth_b_np = scenes.make_depth(scene, view_b)
+    pf_b = []
+    for i, pf in enumerate(copies):
+        d = torch.from_numpy(depth_b_np).to(ctx.device)
+        q = frame.PreparedFrame(ctx, pf.dscene, pf.vstate, view_b, d, name="c%d_moved" % i, main_pass=True)
+        q.launch(); pf.launch(); q.launch(); pf.launch()
+        torch.cuda.synchronize()
+        q.capture()
+        pf_b.append(q)
+    torch.cuda.synchronize()
+    # parity (copy 0): the bits are A's steady state now; one B frame, compared with the oracle taken through the same history
+    ok = None
+    pf_b[0].launch()
+    torch.cuda.synchronize()
+    n_late_b, late_b = frame.read_draws(pf_b[0].late_draws)
+    n_main_b, main_b = frame.read_draws(pf_b[0].main_draws)
+    if O is not None:
+        hs = O.HostScene(scene)
+        depth_a_np = copies[0].depth.cpu().numpy()
+        seq = [(view_a, depth_a_np)] * 3 + [(view_b, depth_b_np)]
+        for v, d in seq:
+            o = O.depth_prepass_culling(hs, v, d)
+            om = O.main_pass_culling(hs, v)
+        on, od = O.parse_draws(o["late"][1]); mn, md = O.parse_draws(om[1])
+        ok = bool(on == n_late_b and mn == n_main_b and sha(od) == sha(late_b) and sha(md) == sha(main_b))
+    copies[0].launch()
+    torch.cuda.synchronize()
+    n_late_a, _ = frame.read_draws(copies[0].late_draws, capacity=0)
+    # timed: A on every copy, then B on every copy, ... (a copy's two frames are separated by the other copies' frames: inputs out of L2)
+    def sweep(rounds):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(rounds):
+            for q in pf_b:
+                q.replay()
+            for pf in copies:
+                pf.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (rounds * 2 * len(copies))
+    sweep(2)
+    ms = [sweep(8) for _ in range(5)]
+    for pf in copies:      # back to camera A's steady state for whatever follows
+        pf.launch(); pf.launch()
+    torch.cuda.synchronize()
+    return {"what": "camera alternates between the named view and the same view yawed by 15 degrees: every frame reads the other camera's visibility bits, so the late pass tests AND emits",
+            "ms_per_step_median": float(np.median(ms)), "ms_per_step_min": float(np.min(ms)),
+            "late_survivors": [int(n_late_b), int(n_late_a)], "main_survivors_moved": int(n_main_b),
+            "value": scene.n_meshlet_instances / (float(np.median(ms)) * 1e-3) / 1e9, "unit": UNIT, "bit_exact_vs_oracle": ok}
+
+
+def c3_sharded_extra(ctx, rank, world, O):
+    """BASELINE config C3: one 3840x2160 view over 50 M instanced meshlets, entity ranges split over the ranks (equal
+    meshlet sums), depth pyramid distributed, survivor lists gathered on rank 0 (the GPU that submits the draws).
+    STRONG scaling: the work is fixed as N grows. Parity: the assembled lists on rank 0 against the unsharded oracle."""
+    import torch
+    import torch.distributed as dist
+    from orbit_b200 import multi_gpu, scenes
+    scene, view = scenes.config_c3(1.0)
+    depth = scenes.make_depth(scene, view) if rank == 0 else np.zeros((view.height, view.width), np.float32)
+    sv = multi_gpu.ShardedView(ctx, scene, view, depth, rank, world)
+    for _ in range(2):
+        sv.step(exchange=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_compute = event_us(lambda: sv.step(exchange=False))
+    variant = "none (one GPU: the lists are already where they are consumed)"
+    if world > 1:
+        sv.enable_peer_exchange(scene.n_meshlet_instances)
+        variant = sv.best_exchange_name()
+        sv.step_best()
+        torch.cuda.synchronize(); dist.barrier()
+        t_full = event_us(lambda: sv.step_best())
+        sv.clear_gathered()
+        dist.barrier()
+        res = sv.step_best()
+        torch.cuda.synchronize(); dist.barrier()
+    else:
+        t_full = t_compute
+        sv.step(exchange=False)
+        torch.cuda.synchronize()
+    t_c, t_f = max_over_ranks([t_compute[0], t_full[0]], ctx.device, world)
+    out = None
+    if rank == 0:
+        if world > 1:
+            early, late = sv.gathered_lists(res)
+        else:
+            early, late = sv.prepared.early_draws, sv.prepared.late_draws
+        n_e = int(early[:4].view(torch.int32).item()); n_l = int(late[:4].view(torch.int32).item())
+        ok = None
+        if O is not None:
+            hs = O.HostScene(scene)
+            n_frames = 2 + 5 + (0 if world == 1 else 1 + 5 + 1) + 1     # every step above was one frame on the same visibility bits
+            for _ in range(min(n_frames, 3)):                            # the steady state is reached after frame 1 (static camera)
+                o = O.depth_prepass_culling(hs, view, depth)
+            on, od = O.parse_draws(o["early"][1]); ln, ld = O.parse_draws(o["late"][1])
+            ge = early[4:4 + 28 * n_e].cpu().numpy(); gl = late[4:4 + 28 * n_l].cpu().numpy()
+            ok = bool(on == n_e and ln == n_l and sha(od) == sha(ge) and sha(ld) == sha(gl))
+        out = {"config": "C3: 250k entities / 50M instanced meshlets, one 3840x2160 view, two-pass, entity ranges sharded over the ranks",
+               "scaling": "strong", "n_gpus": world, "us_compute": t_c, "us_with_exchange": t_f, "exchange": variant,
+               "value": scene.n_meshlet_instances / t_f / 1e3, "value_compute_only": scene.n_meshlet_instances / t_c / 1e3, "unit": UNIT,
+               "survivors_early": n_e, "survivors_late": n_l, "list_bytes_on_rank0": 28 * (n_e + n_l), "bit_exact_vs_oracle": ok}
+    sv.close()
+    return out
+
+
+def c5_many_view_extra(ctx, rank, world, O, n_views=256):
+    """BASELINE config C5: 256 cameras over a 20 M-meshlet scene, view v on rank v mod N, no inter-GPU traffic; pass 0
+    (frustum + cone) for every view. Parity: the first view of rank 0 against the oracle."""
+    import torch
+    import torch.distributed as dist
+    from orbit_b200 import frame, multi_gpu, scenes
+    from orbit_b200.passes import OcclusionCullInfo
+    scene, views = scenes.config_c5(1.0, n_views=n_views)
+    mine = multi_gpu.views_for_rank(len(views), rank, world)
+    ds = frame.DeviceScene.upload(ctx, scene)
+    infos = [frame.cull_info_for(views[v], OcclusionCullInfo("none")) for v in mine]
+    pair = frame.cull_pass(ctx, "c5view", ds, infos[0])
+    torch.cuda.synchronize()
+    ok = None
+    if rank == 0 and O is not None:
+        hs = O.HostScene(scene)
+        o = O.cull_pass(hs, O.gpu_cull_info(views[mine[0]], "none"))
+        ghdr, grecs = frame.read_dispatch(pair[0]); ohdr, orecs = O.parse_dispatch(o[0])
+        gn, gd = frame.read_draws(pair[1]); on, od = O.parse_draws(o[1])
+        ok = bool(ghdr.tolist() == ohdr.tolist() and gn == on and sha(grecs) == sha(orecs) and sha(gd) == sha(od))
+
+    def all_views():
+        for info in infos:
+            frame.cull_pass(ctx, "c5view", ds, info)
+    all_views(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = event_us(all_views, reps=3)[0]
+    (t,) = max_over_ranks([t], ctx.device, world)
+    if rank != 0:
+        return None
+    return {"config": "C5: 100k entities / 20M meshlets, %d cameras 1920x1080, pass 0 (frustum + cone), view v on rank v mod N" % len(views),
+            "scaling": "strong", "n_gpus": world, "views": len(views), "us_all_views_max_rank": t, "us_per_view": t / max(len(mine), 1),
+            "value": len(views) * scene.n_meshlet_instances / t / 1e3, "unit": UNIT, "bit_exact_vs_oracle_view0": ok}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -167,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
         ds = frame.DeviceScene.upload(ctx, scene)
         vs = frame.ViewState(ctx, ds, (view.width, view.height), name="view%d" % i)
         d = torch.from_numpy(depth_np).to(dev)
-        pf = frame.PreparedFrame(ctx, ds, vs, view, d, name="c%d_forward_depth_prepass" % i)
+        pf = frame.PreparedFrame(ctx, ds, vs, view, d, name="c%d_forward_depth_prepass" % i, main_pass=True)
         copies.append(pf)
     for pf in copies:          # frame 0 + frame 1: reach the steady state, grow scratch, then capture the graph
         pf.launch(); pf.launch()
@@ -211,12 +397,25 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     step_ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()
-    if args.step_only:   # for `ncu` launch lists: the last 7 x steps kernels of the process are exactly the timed region
+    if args.step_only:   # for `ncu` launch lists: the last KERNELS_PER_STEP x steps kernels of the process are exactly the timed region
         if rank == 0:
             print(json.dumps({"step_only": True, "ms_per_step": step_ms, "steps": args.steps}), flush=True)
         ctx.close()
         return
-    gpu_launches = 7 * args.steps  # per step: 2 x entity_cull, 2 x (meshlet_test + meshlet_emit), 1 x hiz_build (graph replays bypass the ABI counter)
+    gpu_launches = KERNELS_PER_STEP * args.steps  # (graph replays bypass the ABI counter)
+
+    # ---- the same step again, 5 repeats of >= 50 steps each (BASELINE.md protocol: median and min), whatever --steps was
+    rep_steps = max(args.steps, 50)
+    rep_ms = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for i in range(rep_steps):
+            copies[i % N_COPIES].replay()
+        b.record()
+        barrier()
+        rep_ms.append(a.elapsed_time(b) / rep_steps)
 
     # ---- per-stage device times: a CUDA graph of 8 back-to-back launches of ONE stage rotating over the scene copies
     #      (no CPU in the loop, inputs out of L2), replayed several times; us per launch. The meshlet stage is two
@@ -241,7 +440,8 @@ def run_ours(args, rank, world, local_rank):
 
     stages = {"entity_early": lambda pf, s: pf.entity(False, s), "meshlet_early": lambda pf, s: pf.meshlet(False, s),
               "hiz": lambda pf, s: pf.hiz(s), "entity_late": lambda pf, s: pf.entity(True, s),
-              "meshlet_late": lambda pf, s: pf.meshlet(True, s)}
+              "meshlet_late": lambda pf, s: pf.meshlet(True, s), "entity_main": lambda pf, s: pf.entity("main", s),
+              "meshlet_main": lambda pf, s: pf.meshlet("main", s)}
     k_times = {k: time_stage(fn) for k, fn in stages.items()}
     # the late-pass TEST kernel alone (the dominant kernel the roofline object is quoted on): a second context whose
     # meshlet stage skips the emit launch (ORBIT_DEBUG_SKIP=1, read at context creation; timing only — in the steady
@@ -329,33 +529,63 @@ def run_ours(args, rank, world, local_rank):
         sds.append(sd)
     torch.cuda.synchronize()
     assert np.array_equal(copies[0].dscene.scene.entity_draw_buffer.cpu().numpy(), scene.entity_draws), "scene update draws"
-    h_count = torch.zeros(2, dtype=torch.int32).pin_memory()
+    h_count = torch.zeros(3, dtype=torch.int32).pin_memory()
     h_out_early = torch.empty(28 * scene.n_meshlet_instances, dtype=torch.uint8).pin_memory()
     h_out_late = torch.empty(28 * scene.n_meshlet_instances, dtype=torch.uint8).pin_memory()
+    h_out_main = torch.empty(28 * scene.n_meshlet_instances, dtype=torch.uint8).pin_memory()
     h2d_bytes = h_transforms.numel() + h_depth.numel()
     # The loop itself is the compiled host driver (orbit_b200/host/frame_driver.cpp, the stand-in for the reference's
     # Rust host): three streams (copy-in / compute / copy-out), two steps enqueued ahead of the one being read back,
     # every GPU operation a C-ABI stage call or a cudaMemcpyAsync. A Python loop issuing the same calls spends ~185 us
     # of interpreter time per step (measured), which is as long as the step's PCIe transfers.
     e2e_steps = max(8, min(args.steps, 100))
-    frame.host_frame_loop(ctx, copies, sds, h_transforms, h_depth, h_count, h_out_early, h_out_late, 6)      # warm-up
+
+    def e2e_run(steps, depth_resident=False):
+        return frame.host_frame_loop(ctx, copies, sds, h_transforms, h_depth, h_count, h_out_early, h_out_late, h_out_main, steps,
+                                     depth_resident=depth_resident)
+    e2e_run(6)      # warm-up
     barrier()
-    rep = frame.host_frame_loop(ctx, copies, sds, h_transforms, h_depth, h_count, h_out_early, h_out_late, e2e_steps)
+    rep = e2e_run(e2e_steps)
     e2e_ms = rep["ms_per_step"]
     assert rep["h2d_bytes_per_step"] == h2d_bytes
     d2h_bytes_box = [rep["d2h_bytes_per_step"]]
     # (the entity matrices are now the ones orbit_scene_update computes in binary32, a few ulps from the generator's
     #  float64-rounded ones, so the survivor count may move by a handful of meshlets)
     assert abs(int(h_count[0]) - n_early_draws) <= max(16, n_early_draws // 100), "e2e early survivors differ from the device-resident run"
+    # the same loop with the depth buffer already on the device (what Vulkan interop gives: the depth attachment is imported,
+    # not copied) — reported beside `e2e`, never instead of it
+    for pf in copies:
+        pf.depth.copy_(torch.from_numpy(depth_np))
+    e2e_run(6, depth_resident=True)
+    barrier()
+    rep_res = e2e_run(e2e_steps, depth_resident=True)
+    e2e_res_ms = rep_res["ms_per_step"]
+
+    # ---- extras: moving camera (C2), then the two BASELINE configs whose work is split over the ranks
+    O = None
+    if not args.no_parity:
+        import oracle_ref as O
+        O.build()
+        O.lib().oracle_set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1
+    moving = moving_camera_extra(ctx, frame, scenes, scene, copies, O if rank == 0 else None)
 
     # ---- max over ranks
-    if world > 1:
-        t = torch.tensor([step_ms, e2e_ms, cv_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, e2e_ms, cv_ms = float(t[0]), float(t[1]), float(t[2])
+    step_ms, e2e_ms, cv_ms, e2e_res_ms = max_over_ranks([step_ms, e2e_ms, cv_ms, e2e_res_ms], dev, world)
+    rep_ms = max_over_ranks(rep_ms, dev, world)
+    mv = max_over_ranks([moving["ms_per_step_median"], moving["ms_per_step_min"]], dev, world)
+    moving["ms_per_step_median"], moving["ms_per_step_min"] = mv
+    moving["value"] = scene.n_meshlet_instances * world / (mv[0] * 1e-3) / 1e9
     units = scene.n_meshlet_instances * world
     value = units / (step_ms * 1e-3) / 1e9
     e2e_value = units / (e2e_ms * 1e-3) / 1e9
+
+    for c in cv_ctx:
+        c.close()
+    ctx_test_only.close()
+    c3 = c5 = None
+    if not args.no_configs:
+        c3 = c3_sharded_extra(ctx, rank, world, O if rank == 0 else None)
+        c5 = c5_many_view_extra(ctx, rank, world, O if rank == 0 else None)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -369,13 +599,16 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "C2 city 10k entities / 2M meshlets, 1 view 1920x1080 per GPU, steady-state frame: early cull + Hi-Z + late cull",
+            "config": {"workload": WORKLOAD,
                        "l2": "rotating %d independent copies of scene + view state (~%d MB each) so inputs come from HBM" % (
                            N_COPIES, sum(scene.bytes_summary().values()) // 2 ** 20),
-                       "launch": "one CUDA graph replay per step (7 kernels: 2x entity_cull, 2x meshlet_test+meshlet_emit, hiz_build)", "views": "every rank culls its own instance of the C2 view on a replicated scene; no data-path collective"},
+                       "launch": "one CUDA graph replay per step (%d kernels: 3x entity_cull, 3x meshlet test + meshlet_emit, hiz_build)" % KERNELS_PER_STEP,
+                       "views": "every rank culls its own instance of the C2 view on a replicated scene; no data-path collective"},
+            "repeats": {"what": "the timed step again, 5 repeats of %d steps each (BASELINE.md protocol)" % rep_steps,
+                        "ms_per_step_median": float(np.median(rep_ms)), "ms_per_step_min": float(np.min(rep_ms)), "ms_per_step_all": rep_ms},
             "roofline": {"bound": "hbm", "kernel": "meshlet_test_direct_kernel<4,pass2,persp> (late pass, occlusion_pass=2)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
-                         "traffic_source": "profiles/r1_final_meshlet_test_ncu.json (ncu --set full, per launch, bytes)",
+                         "traffic_source": "profiles/r2_meshlet_test_ncu.json (ncu --set full, per launch, bytes)",
                          "algorithmic_bytes_per_launch": late_bytes, "launch_us_median": late_us, "launch_us_min": k_times["meshlet_late_test_kernel"][1],
                          "stage_us_median": stage_us, "frac_stage": late_bytes / (stage_us * 1e-6) / 1e9 / peak,
                          "stage": "test kernel + meshlet_emit_kernel (nothing to emit in the steady-state late pass)",
@@ -391,21 +624,23 @@ def run_ours(args, rank, world, local_rank):
                                  "stage_gmeshlets_per_s": lanes0 / (t_pass0[0] * 1e-6) / 1e9},
             "early_pass": {"lanes": early_lanes, "survivors": n_early_draws,
                            "stage_gmeshlets_per_s": early_lanes / (k_times["meshlet_early"][0] * 1e-6) / 1e9},
-            "concurrent_views": {"what": "%d independent views of the scene in flight (one context + stream + CUDA graph each), same work per view as the timed step" % N_COPIES,
+            "concurrent_views": {"what": "%d independent views of the scene in flight (one context + stream + CUDA graph each), depth-prepass culling only (early + Hi-Z + late)" % N_COPIES,
                                  "views_in_flight": N_COPIES, "ms_per_view": cv_ms, "value": units / (cv_ms * 1e-3) / 1e9, "unit": UNIT},
+            "moving_camera": moving,
+            "c3_sharded": c3, "c5_many_view": c5,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes_box[0]),
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "what": "per step: pinned host entity Transforms (48 B each) + depth -> device, orbit_scene_update + 5 stage calls (C ABI), both draw lists + counts -> host; issued by the compiled host driver (orbit_b200/host/frame_driver.cpp), software-pipelined over 3 streams (copy-in / compute / copy-out), two steps enqueued ahead of the one being read back; PCIe-bound: the step's H2D bytes / ms_per_step is the ~50 GB/s the same copies reach alone (tools/pcie_floor.py, profiles/r1_scene_update.txt)"},
+                    "what": "per step: pinned host entity Transforms (48 B each) + depth -> device, orbit_scene_update + 7 stage calls (C ABI: early, Hi-Z, late, main), three draw lists + counts -> host; issued by the compiled host driver (orbit_b200/host/frame_driver.cpp), software-pipelined over 3 streams (copy-in / compute / copy-out), two steps enqueued ahead of the one being read back",
+                    "depth_resident": {"what": "same loop with the depth buffer already on the device (Vulkan interop imports the depth attachment instead of copying it)",
+                                       "value": units / (e2e_res_ms * 1e-3) / 1e9, "ms_per_step": e2e_res_ms,
+                                       "h2d_bytes_per_step": int(rep_res["h2d_bytes_per_step"]), "d2h_bytes_per_step": int(rep_res["d2h_bytes_per_step"])}},
             "gpu_launches": gpu_launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    for c in cv_ctx:
-        c.close()
-    ctx_test_only.close()
     ctx.close()
 
 
@@ -414,22 +649,27 @@ def cpu_baseline_sample(scene, view, depth_np, frames=4):
     core: 1 frame; SURVEY §8d asks for both)."""
     import oracle_ref as O
     O.build()
+    O.lib().oracle_set_threads(os.cpu_count() or 1)
     hs = O.HostScene(scene)
-    for _ in range(2):
+
+    def frame_once():
         O.depth_prepass_culling(hs, view, depth_np)
+        O.main_pass_culling(hs, view)
+    for _ in range(2):
+        frame_once()
     t0 = time.perf_counter()
     for _ in range(frames):
-        O.depth_prepass_culling(hs, view, depth_np)
+        frame_once()
     dt = (time.perf_counter() - t0) / frames
     cores = int(O.lib().oracle_threads())
     prev = O.lib().oracle_set_threads(1)
     t0 = time.perf_counter()
-    O.depth_prepass_culling(hs, view, depth_np)
+    frame_once()
     dt1 = time.perf_counter() - t0
     O.lib().oracle_set_threads(prev)
     return {"value": scene.n_meshlet_instances / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
             "ms_per_step": dt * 1e3,
-            "sample": "%d whole C2 steady-state frames (early+Hi-Z+late) on the oracle port, OpenMP over %d host threads" % (frames, cores),
+            "sample": "%d whole C2 steady-state frames (early + Hi-Z + late + main) on the oracle port, OpenMP over %d host threads" % (frames, cores),
             "single_thread": {"value": scene.n_meshlet_instances / dt1 / 1e9, "ms_per_step": dt1 * 1e3, "sample": "1 frame, 1 thread"}}
 
 
@@ -441,6 +681,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--step-only", action="store_true", help="stop after the timed region (profiling aid)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the nested C3 / C5 measurements")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity bits of the extras")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

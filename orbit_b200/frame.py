@@ -108,13 +108,15 @@ def read_draws(buf, capacity=None):
 
 
 class PreparedFrame:
-    """One view's depth-prepass culling (EARLY -> Hi-Z -> LATE) with every argument packed once.
+    """One view's culling for a frame with every argument packed once: the depth prepass EARLY -> Hi-Z -> LATE
+    (forward.rs:266-403) and, with `main_pass`, the MAIN pass after it (forward.rs:518-548: pass 1 again, reading the
+    visibility bits the late pass just wrote — the same CullInfo as EARLY, other output buffers).
 
     The reference re-declares the passes each frame on its render graph; the packed form is the CUDA analogue:
-    five asynchronous launches on one stream, optionally captured into a CUDA graph (`capture()` / `replay()`) so
+    asynchronous stage calls on one stream, optionally captured into a CUDA graph (`capture()` / `replay()`) so
     a frame costs one graph launch. Safe to replay: the scan epoch and tickets live in device memory."""
 
-    def __init__(self, context, dscene, vstate, view, depth_buffer, meshlet_occlusion=True, name="forward_depth_prepass"):
+    def __init__(self, context, dscene, vstate, view, depth_buffer, meshlet_occlusion=True, name="forward_depth_prepass", main_pass=False):
         import ctypes as C
         from . import _lib
         from .passes import _ptr, _scene_buffers
@@ -135,6 +137,11 @@ class PreparedFrame:
         self.early_draws = mk("early_" + name + "_meshlet_draw_command_buffer", L.DRAW_HEADER + 28 * self.dcap)
         self.late_dispatch = mk("late_" + name + "_meshlet_dispatch_buffer", L.DISPATCH_HEADER + 16 * self.rcap)
         self.late_draws = mk("late_" + name + "_meshlet_draw_command_buffer", L.DRAW_HEADER + 28 * self.dcap)
+        self.main_pass = main_pass
+        self.main_dispatch = self.main_draws = None
+        if main_pass:
+            self.main_dispatch = mk("main_" + name + "_meshlet_dispatch_buffer", L.DISPATCH_HEADER + 16 * self.rcap)
+            self.main_draws = mk("main_" + name + "_meshlet_draw_command_buffer", L.DRAW_HEADER + 28 * self.dcap)
         self.graph = None
         h, w = depth_buffer.shape
         self._hw = (w, h)
@@ -145,7 +152,10 @@ class PreparedFrame:
     def entity(self, late, s=None):
         C, lib, p = self._C, self._lib, self._ptr
         s = s or self._stream()
-        g, sb, out = (self.g_late, self.sb_late, self.late_dispatch) if late else (self.g_early, self.sb_early, self.early_dispatch)
+        if late == "main":
+            late, g, sb, out = False, self.g_early, self.sb_early, self.main_dispatch
+        else:
+            g, sb, out = (self.g_late, self.sb_late, self.late_dispatch) if late else (self.g_early, self.sb_early, self.early_dispatch)
         rc = lib.orbit_entity_cull(self.context._h, C.byref(g), C.byref(sb), self.vstate.depth_pyramid._h if late else None,
                                    p(out), self.rcap, s)
         if rc:
@@ -155,8 +165,11 @@ class PreparedFrame:
         """`context`: run the stage on another Context's scratch (bench.py times the test kernel alone that way)."""
         C, lib, p = self._C, self._lib, self._ptr
         s = s or self._stream()
-        g, sb, disp, out = ((self.g_late, self.sb_late, self.late_dispatch, self.late_draws) if late
-                            else (self.g_early, self.sb_early, self.early_dispatch, self.early_draws))
+        if late == "main":
+            late, g, sb, disp, out = False, self.g_early, self.sb_early, self.main_dispatch, self.main_draws
+        else:
+            g, sb, disp, out = ((self.g_late, self.sb_late, self.late_dispatch, self.late_draws) if late
+                                else (self.g_early, self.sb_early, self.early_dispatch, self.early_draws))
         rc = lib.orbit_meshlet_cull((context or self.context)._h, C.byref(g), C.byref(sb), self.vstate.depth_pyramid._h if late else None,
                                     p(disp), self.rcap, p(out), self.dcap, None, s)
         if rc:
@@ -171,6 +184,8 @@ class PreparedFrame:
     def launch(self):
         s = self._stream()
         self.entity(False, s); self.meshlet(False, s); self.hiz(s); self.entity(True, s); self.meshlet(True, s)
+        if self.main_pass:
+            self.entity("main", s); self.meshlet("main", s)
 
     def capture(self):
         self.launch()  # warm: scratch growth / occupancy queries must not happen during capture
@@ -185,10 +200,11 @@ class PreparedFrame:
         self.graph.replay()
 
 
-def host_frame_loop(context, prepared, scene_datas, h_transforms, h_depth, h_counts, h_early_draws, h_late_draws, steps, lookahead=2):
+def host_frame_loop(context, prepared, scene_datas, h_transforms, h_depth, h_counts, h_early_draws, h_late_draws, h_main_draws, steps,
+                    lookahead=2, depth_resident=False):
     """End-to-end frame loop with HOST inputs/outputs run by the compiled host driver (orbit_b200/host/frame_driver.cpp):
-    per step, pinned-host Transforms + depth -> device, orbit_scene_update, the five culling-stage calls, both survivor
-    lists -> pinned host; `lookahead` steps in flight ahead of the one being read back, rotating over `prepared`
+    per step, pinned-host Transforms + depth -> device (`depth_resident`: the depth buffer stays on the device, as with
+    Vulkan interop), orbit_scene_update, the stage calls of EARLY / Hi-Z / LATE / MAIN, the three survivor lists -> pinned host; `lookahead` steps in flight ahead of the one being read back, rotating over `prepared`
     (PreparedFrame) / `scene_datas` (scene.SceneData) copies. Returns the driver's report."""
     import ctypes as C
     from . import _lib
@@ -202,11 +218,13 @@ def host_frame_loop(context, prepared, scene_datas, h_transforms, h_depth, h_cou
         f.depth = pf.depth.data_ptr()
         f.early_dispatch, f.early_draws = pf.early_dispatch.data_ptr(), pf.early_draws.data_ptr()
         f.late_dispatch, f.late_draws = pf.late_dispatch.data_ptr(), pf.late_draws.data_ptr()
+        f.main_dispatch, f.main_draws = pf.main_dispatch.data_ptr(), pf.main_draws.data_ptr()
         f.capacity_records, f.capacity_draws = pf.rcap, pf.dcap
         f.width, f.height = pf._hw
     torch.cuda.synchronize()
     io = L.HostFrameIO()
     io.h_transforms, io.h_depth, io.h_counts = h_transforms.data_ptr(), h_depth.data_ptr(), h_counts.data_ptr()
-    io.h_early_draws, io.h_late_draws = h_early_draws.data_ptr(), h_late_draws.data_ptr()
+    io.h_early_draws, io.h_late_draws, io.h_main_draws = h_early_draws.data_ptr(), h_late_draws.data_ptr(), h_main_draws.data_ptr()
+    io.depth_resident = 1 if depth_resident else 0
     _lib.check(_lib.host_lib().orbit_host_frame_loop(context._h, frames, n, C.byref(io), int(steps), int(lookahead)), "orbit_host_frame_loop")
     return {"ms_per_step": io.ms_per_step, "h2d_bytes_per_step": int(io.h2d_bytes_per_step), "d2h_bytes_per_step": int(io.d2h_bytes_last_step)}

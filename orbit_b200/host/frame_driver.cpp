@@ -3,8 +3,8 @@
 // The reference's host is compiled code (Rust: SceneData::update_scene, scene.rs:404-492, then the depth-prepass
 // culling passes of forward.rs:266-403 recorded every frame). This is its stand-in for end-to-end measurements: a
 // software-pipelined frame loop with HOST inputs and outputs — per step: pinned-host Transforms + depth buffer ->
-// device, orbit_scene_update, EARLY entity+meshlet cull, Hi-Z build, LATE entity+meshlet cull, both survivor counts
-// and both survivor lists -> pinned host — with `lookahead` steps enqueued ahead of the one being read back, each on
+// device, orbit_scene_update, EARLY entity+meshlet cull, Hi-Z build, LATE entity+meshlet cull, MAIN entity+meshlet cull
+// (forward.rs:518-548: pass 1 again with the bits the late pass wrote), the three survivor counts and lists -> pinned host — with `lookahead` steps enqueued ahead of the one being read back, each on
 // its own copy of the scene/view buffers. Three streams: copy-in, compute, copy-out. No kernels here; every GPU
 // operation is a C-ABI stage call or a cudaMemcpyAsync. Built into liborbit_host.so by orbit_b200/build.py.
 #include <cuda_runtime.h>
@@ -25,7 +25,7 @@ typedef struct OrbitHostFrame {
     OrbitSceneBuffers scene_early, scene_late;
     orbit_hiz* hiz;
     float* depth;                       // W x H f32
-    void *early_dispatch, *early_draws, *late_dispatch, *late_draws;
+    void *early_dispatch, *early_draws, *late_dispatch, *late_draws, *main_dispatch, *main_draws;
     uint64_t capacity_records, capacity_draws;
     uint32_t width, height;
 } OrbitHostFrame;
@@ -33,9 +33,12 @@ typedef struct OrbitHostFrame {
 typedef struct OrbitHostFrameIO {
     const void* h_transforms;           // pinned host, n_entities x 48 B
     const float* h_depth;               // pinned host, W x H f32
-    uint32_t* h_counts;                 // pinned host, 2 words (early, late)
+    uint32_t* h_counts;                 // pinned host, 3 words (early, late, main)
     void* h_early_draws;                // pinned host, 28 B x capacity
     void* h_late_draws;
+    void* h_main_draws;
+    uint32_t depth_resident;            // != 0: the depth buffer already lives on the device (what Vulkan interop gives): not copied
+    uint32_t reserved;
     uint64_t h2d_bytes_per_step;        // out
     uint64_t d2h_bytes_last_step;       // out
     double ms_per_step;                 // out: host wall clock over `steps`, everything drained
@@ -75,14 +78,14 @@ int orbit_host_frame_loop(orbit_ctx* ctx, const OrbitHostFrame* frames, uint32_t
     }
     const size_t transform_bytes = (size_t)frames[0].update.n_entities * sizeof(OrbitTransform);
     const size_t depth_bytes = (size_t)frames[0].width * frames[0].height * sizeof(float);
-    io->h2d_bytes_per_step = transform_bytes + depth_bytes;
+    io->h2d_bytes_per_step = transform_bytes + (io->depth_resident ? 0 : depth_bytes);
 
     auto enqueue = [&](uint32_t step) -> int {
         const uint32_t k = step % n_frames;
         const OrbitHostFrame& f = frames[k];
         CU_OK(cudaStreamWaitEvent(s_in, ev_free[k], 0));          // this copy's previous outputs have been read back
         CU_OK(cudaMemcpyAsync((void*)f.update.transforms, io->h_transforms, transform_bytes, cudaMemcpyHostToDevice, s_in));
-        CU_OK(cudaMemcpyAsync(f.depth, io->h_depth, depth_bytes, cudaMemcpyHostToDevice, s_in));
+        if (!io->depth_resident) CU_OK(cudaMemcpyAsync(f.depth, io->h_depth, depth_bytes, cudaMemcpyHostToDevice, s_in));
         CU_OK(cudaEventRecord(ev_in[k], s_in));
         CU_OK(cudaStreamWaitEvent(s_comp, ev_in[k], 0));
         OR_OK(orbit_scene_update(ctx, &f.update, s_comp));
@@ -93,6 +96,9 @@ int orbit_host_frame_loop(orbit_ctx* ctx, const OrbitHostFrame* frames, uint32_t
         OR_OK(orbit_entity_cull(ctx, &f.cull_late, &f.scene_late, f.hiz, f.late_dispatch, f.capacity_records, s_comp));
         OR_OK(orbit_meshlet_cull(ctx, &f.cull_late, &f.scene_late, f.hiz, f.late_dispatch, f.capacity_records, f.late_draws,
                                  f.capacity_draws, nullptr, s_comp));
+        OR_OK(orbit_entity_cull(ctx, &f.cull_early, &f.scene_early, nullptr, f.main_dispatch, f.capacity_records, s_comp));   // MAIN = pass 1 again
+        OR_OK(orbit_meshlet_cull(ctx, &f.cull_early, &f.scene_early, nullptr, f.main_dispatch, f.capacity_records, f.main_draws,
+                                 f.capacity_draws, nullptr, s_comp));
         CU_OK(cudaEventRecord(ev_done[k], s_comp));
         return ORBIT_OK;
     };
@@ -102,14 +108,17 @@ int orbit_host_frame_loop(orbit_ctx* ctx, const OrbitHostFrame* frames, uint32_t
         CU_OK(cudaStreamWaitEvent(s_out, ev_done[k], 0));
         CU_OK(cudaMemcpyAsync(io->h_counts, f.early_draws, 4, cudaMemcpyDeviceToHost, s_out));
         CU_OK(cudaMemcpyAsync(io->h_counts + 1, f.late_draws, 4, cudaMemcpyDeviceToHost, s_out));
+        CU_OK(cudaMemcpyAsync(io->h_counts + 2, f.main_draws, 4, cudaMemcpyDeviceToHost, s_out));
         CU_OK(cudaStreamSynchronize(s_out));
-        uint64_t ne = io->h_counts[0], nl = io->h_counts[1];
+        uint64_t ne = io->h_counts[0], nl = io->h_counts[1], nm = io->h_counts[2];
         if (ne > f.capacity_draws) ne = f.capacity_draws;
         if (nl > f.capacity_draws) nl = f.capacity_draws;
+        if (nm > f.capacity_draws) nm = f.capacity_draws;
+        if (nm) CU_OK(cudaMemcpyAsync(io->h_main_draws, (const char*)f.main_draws + 4, 28 * nm, cudaMemcpyDeviceToHost, s_out));
         if (ne) CU_OK(cudaMemcpyAsync(io->h_early_draws, (const char*)f.early_draws + 4, 28 * ne, cudaMemcpyDeviceToHost, s_out));
         if (nl) CU_OK(cudaMemcpyAsync(io->h_late_draws, (const char*)f.late_draws + 4, 28 * nl, cudaMemcpyDeviceToHost, s_out));
         CU_OK(cudaEventRecord(ev_free[k], s_out));
-        io->d2h_bytes_last_step = 8 + 28 * (ne + nl);
+        io->d2h_bytes_last_step = 12 + 28 * (ne + nl + nm);
         return ORBIT_OK;
     };
 

@@ -140,13 +140,15 @@ class HostFrame(C.Structure):
     _fields_ = [("update", SceneUpdate), ("cull_early", CullInfo), ("cull_late", CullInfo),
                 ("scene_early", SceneBuffers), ("scene_late", SceneBuffers), ("hiz", C.c_void_p), ("depth", C.c_void_p),
                 ("early_dispatch", C.c_void_p), ("early_draws", C.c_void_p), ("late_dispatch", C.c_void_p),
-                ("late_draws", C.c_void_p), ("capacity_records", C.c_uint64), ("capacity_draws", C.c_uint64),
+                ("late_draws", C.c_void_p), ("main_dispatch", C.c_void_p), ("main_draws", C.c_void_p),
+                ("capacity_records", C.c_uint64), ("capacity_draws", C.c_uint64),
                 ("width", C.c_uint32), ("height", C.c_uint32)]
 
 
 class HostFrameIO(C.Structure):
     _fields_ = [("h_transforms", C.c_void_p), ("h_depth", C.c_void_p), ("h_counts", C.c_void_p),
-                ("h_early_draws", C.c_void_p), ("h_late_draws", C.c_void_p), ("h2d_bytes_per_step", C.c_uint64),
+                ("h_early_draws", C.c_void_p), ("h_late_draws", C.c_void_p), ("h_main_draws", C.c_void_p),
+                ("depth_resident", C.c_uint32), ("reserved", C.c_uint32), ("h2d_bytes_per_step", C.c_uint64),
                 ("d2h_bytes_last_step", C.c_uint64), ("ms_per_step", C.c_double)]
 assert C.sizeof(CullInfo) == 400 and C.sizeof(ClusterCullInfo) == 192 and C.sizeof(ClusterParams) == 208
 assert C.sizeof(SceneBuffers) == 72

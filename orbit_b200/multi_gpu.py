@@ -259,3 +259,26 @@ class ShardedView:
         early, _ = exchange_survivors(pf.early_draws)
         late, _ = exchange_survivors(pf.late_draws)
         return early, late
+
+    # ---- what bench.py times as "the sharded frame including the exchange" ------------------------------------------
+    def best_exchange_name(self):
+        return ("survivor lists gathered on rank 0 by NVLink peer stores (device-side counts, no host round trip), the early "
+                "list's exchange overlapped with Hi-Z + late pass, one closing fence")
+
+    def step_best(self):
+        return self.step_overlapped(0)
+
+    def clear_gathered(self):
+        self.peer_early.clear(); self.peer_late.clear()
+
+    def gathered_lists(self, result):
+        """The two assembled MeshletDrawCommandBuffers on this rank after step_best() (meaningful on rank 0)."""
+        c_e, c_l = result
+        return self.peer_early.read(int(c_e.sum())), self.peer_late.read(int(c_l.sum()))
+
+    def close(self):
+        for name in ("peer_early", "peer_late"):
+            if hasattr(self, name):
+                getattr(self, name).close()
+                delattr(self, name)
+

@@ -134,27 +134,31 @@ def test_compiled_host_frame_loop_matches_oracle(gpu_context, oracle):
     for i in range(4):
         ds = frame.DeviceScene.upload(ctx, sc)
         vs = frame.ViewState(ctx, ds, (view.width, view.height), name="hfl%d" % i)
-        pf = frame.PreparedFrame(ctx, ds, vs, view, torch.zeros((view.height, view.width), dtype=torch.float32, device=ctx.device), name="hfl%d" % i)
+        pf = frame.PreparedFrame(ctx, ds, vs, view, torch.zeros((view.height, view.width), dtype=torch.float32, device=ctx.device), name="hfl%d" % i,
+                                 main_pass=True)
         sd = SceneData(ctx, sc.n_entities)
         sd.set_entities(sc.transforms, sc.draws["mesh_index"])
         sd.transforms.zero_()                                           # the loop must bring the transforms in itself
         sd.entity_data_buffer, sd.entity_draw_buffer = ds.scene.entity_buffer, ds.scene.entity_draw_buffer
         copies.append(pf); sds.append(sd)
     h_t, h_d = pin(sc.transforms), torch.from_numpy(depth).pin_memory()
-    h_c = torch.zeros(2, dtype=torch.int32).pin_memory()
+    h_c = torch.zeros(3, dtype=torch.int32).pin_memory()
     h_e = torch.zeros(28 * sc.n_meshlet_instances, dtype=torch.uint8).pin_memory()
     h_l = torch.zeros(28 * sc.n_meshlet_instances, dtype=torch.uint8).pin_memory()
-    rep = frame.host_frame_loop(ctx, copies, sds, h_t, h_d, h_c, h_e, h_l, steps=6, lookahead=2)
+    h_m = torch.zeros(28 * sc.n_meshlet_instances, dtype=torch.uint8).pin_memory()
+    rep = frame.host_frame_loop(ctx, copies, sds, h_t, h_d, h_c, h_e, h_l, h_m, steps=6, lookahead=2)
     assert rep["h2d_bytes_per_step"] == h_t.numel() + depth.nbytes
     # step 5 ran on copy 1 and was that copy's second frame
     vo = np.full(sc.n_entities, L.NO_VISIBILITY_RANGE, np.uint32)
     o_ed, o_draws, _ = oracle.scene_update(sc.transforms, sc.draws["mesh_index"].copy(), vo, sc.mesh_infos, np.zeros(1, np.uint32))
     sc.entities, sc.entity_draws = o_ed.copy(), o_draws.copy()
     hs = oracle.HostScene(sc)
-    oracle.depth_prepass_culling(hs, view, depth)
+    oracle.depth_prepass_culling(hs, view, depth); oracle.main_pass_culling(hs, view)
     o = oracle.depth_prepass_culling(hs, view, depth)
-    ne, e = oracle.parse_draws(o["early"][1]); nl, l = oracle.parse_draws(o["late"][1])
-    assert (int(h_c[0]), int(h_c[1])) == (ne, nl) and ne > 0
+    om = oracle.main_pass_culling(hs, view)                             # MAIN: pass 1 with the bits the late pass wrote
+    ne, e = oracle.parse_draws(o["early"][1]); nl, l = oracle.parse_draws(o["late"][1]); nm, m = oracle.parse_draws(om[1])
+    assert (int(h_c[0]), int(h_c[1]), int(h_c[2])) == (ne, nl, nm) and ne > 0 and nm >= ne
     assert np.array_equal(h_e.numpy()[:28 * ne], e.view(np.uint8).reshape(-1))
     assert np.array_equal(h_l.numpy()[:28 * nl], l.view(np.uint8).reshape(-1))
-    assert rep["d2h_bytes_per_step"] == 8 + 28 * (ne + nl)
+    assert np.array_equal(h_m.numpy()[:28 * nm], m.view(np.uint8).reshape(-1))
+    assert rep["d2h_bytes_per_step"] == 12 + 28 * (ne + nl + nm)
