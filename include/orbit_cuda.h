@@ -18,8 +18,13 @@
  *   - OrbitCullInfo / OrbitClusterParams / OrbitSceneBuffers are HOST structs, copied into kernel parameter
  *     space at launch; the pointers inside OrbitSceneBuffers are DEVICE pointers.
  *   - a context owns the small device scratch used by the scan-based compaction (tile descriptors, tickets).
- *     One context must not be used from two streams concurrently; contexts are independent of each other and
- *     of the calling thread (the reference records passes from rayon workers: context.rs:1392-1423).
+ *     Calls of the SAME stage on one context must not run concurrently (two streams), but the stages own disjoint
+ *     scratch: one orbit_entity_cull, one orbit_meshlet_cull, one orbit_hiz_build, one orbit_scene_update and one
+ *     orbit_light_cluster call may overlap on different streams of one context (orbit_light_cluster shares the scan
+ *     descriptors with orbit_entity_cull: those two must not overlap); the orbit_draws_scatter* / orbit_device_copy /
+ *     orbit_peer_* helpers touch no context scratch at all. Contexts are independent of each other and of the calling
+ *     thread: every entry point makes the context's device current for the duration of the call and restores the caller's
+ *     (the reference records passes from rayon workers: context.rs:1392-1423).
  *   - output order is deterministic: dispatch records are ordered by (entity-draw index, chunk), draw
  *     commands by (dispatch record index, lane), compacted clusters and light indices ascending.  The
  *     reference appends with atomicAdd (entity_cull.comp:211, meshlet_cull.comp:228), i.e. in arbitrary
@@ -29,9 +34,9 @@
  *     `entity_draw_count`; the buffers must be allocated to the stated capacities (contents beyond the counts are
  *     never used; zero them once if a tool such as compute-sanitizer initcheck is to stay quiet).
  *   - scratch grows on the first call that needs more than the context has seen so far (larger capacity_records,
- *     more clusters, more lights); growing synchronises the device once, so warm a context up with its real
- *     capacities before capturing calls into a CUDA graph. Captured calls are replay-safe: scan epochs, tickets and
- *     scratch parities live in device memory, never in kernel parameters.
+ *     more clusters, more lights): one cudaMalloc inside that call, no synchronisation (orbit_ctx_reserve pre-sizes it);
+ *     size a context (reserve or warm-up) before capturing calls into a CUDA graph. Captured calls are replay-safe:
+ *     scan epochs, tickets and scratch parities live in device memory, never in kernel parameters.
  *   - there is no CPU fallback: without a CUDA device every entry point that needs one fails.
  */
 #ifndef ORBIT_CUDA_H
@@ -44,7 +49,7 @@
 extern "C" {
 #endif
 
-#define ORBIT_ABI_VERSION 1
+#define ORBIT_ABI_VERSION 2
 
 enum {
     ORBIT_OK = 0,
@@ -114,6 +119,13 @@ void        orbit_ctx_destroy(orbit_ctx* ctx);
 int         orbit_ctx_poll_status(orbit_ctx* ctx, OrbitStatus* out);
 /* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
 uint64_t    orbit_ctx_launch_count(const orbit_ctx* ctx);
+/* Pre-sizes the context's scratch for the largest calls it will see (entity draws per launch, dispatch-buffer capacity in
+ * records, lights, clusters, scene-update entities; 0 = leave as is), so that no later stage call allocates. This is the one
+ * call that may synchronise the device. Without it scratch grows on demand inside the stage call (cudaMalloc, never a
+ * synchronisation or a free: outgrown scratch is parked until orbit_ctx_destroy) — not capturable into a CUDA graph, so
+ * reserve, or warm up, before capturing. */
+int         orbit_ctx_reserve(orbit_ctx* ctx, uint64_t entity_draws, uint64_t capacity_records, uint64_t n_lights,
+                              uint64_t n_clusters, uint64_t n_entities);
 
 /* ---- depth pyramid: DepthPyramid::{new,resize,update,get_current}, draw_gen.rs:451-567 ------------------ */
 int  orbit_hiz_geometry(uint32_t depth_width, uint32_t depth_height, OrbitHizInfo* out);  /* host only */
@@ -183,15 +195,35 @@ int orbit_scene_update(orbit_ctx* ctx, const OrbitSceneUpdate* update, void* str
 /* Appends `count` draw commands read from src (a MeshletDrawCommandBuffer, device-side count honoured) into
  * dst (possibly a peer-mapped MeshletDrawCommandBuffer) starting at draw index `dst_first`; when
  * `total_count` != UINT32_MAX also stores it as dst's header. One coalesced copy kernel; used to assemble the
- * rank-major survivor list of a meshlet-range-sharded view through NVLink peer stores. */
-int orbit_draws_scatter(orbit_ctx* ctx, const void* src_draw_buffer, void* dst_draw_buffer,
+ * rank-major survivor list of a meshlet-range-sharded view through NVLink peer stores. A source count above
+ * `src_capacity_draws` (the source overflowed: its header is exact, the excess commands were dropped) is clamped to it. */
+int orbit_draws_scatter(orbit_ctx* ctx, const void* src_draw_buffer, uint64_t src_capacity_draws, void* dst_draw_buffer,
                         uint32_t dst_first, uint32_t total_count, uint64_t dst_capacity_draws, void* stream);
 /* Same, with the placement taken from the DEVICE: rank_counts[world] = every rank's survivor count (e.g. the result
  * of an all-gather enqueued on the same stream); dst_first = sum of rank_counts[0..rank), header = their total.
- * Nothing is read back to the host, so a whole sharded frame stays asynchronous. */
-int orbit_draws_scatter_ranked(orbit_ctx* ctx, const void* src_draw_buffer, void* dst_draw_buffer,
+ * Nothing is read back to the host, so a whole sharded frame stays asynchronous. Every rank's count is clamped to
+ * `src_capacity_draws` (the ranks of one sharded view use equal capacities), so an overflowing rank leaves no gap. */
+int orbit_draws_scatter_ranked(orbit_ctx* ctx, const void* src_draw_buffer, uint64_t src_capacity_draws, void* dst_draw_buffer,
                                const uint32_t* rank_counts, uint32_t rank, uint32_t world,
                                uint64_t dst_capacity_draws, void* stream);
+
+/* The same exchange with 16-byte record entries instead of 28-byte commands (config C3: 28 MB instead of 229 MB to the rank
+ * that submits the draws). orbit_meshlet_test = the test half of orbit_meshlet_cull: visibility words are written as usual,
+ * and for every dispatch record r < count one entry {u32 draw mask, u32 entity, u32 meshlet offset, u32 1} goes to
+ * record_masks[r] (16-byte aligned, capacity_records entries); no draw commands are produced.
+ * orbit_record_masks_scatter_ranked stores this rank's entries into dst (usually peer-mapped) at entry index
+ * sum(rank_record_counts[0..rank)) — rank_record_counts = the all-gathered dispatch-buffer headers, read on the device.
+ * orbit_draws_from_masks runs on the receiving rank: recounts the survivors of the combined list and emits the
+ * MeshletDrawCommandBuffer in canonical order (command words are read from scene->meshlets). Counts above
+ * rank_capacity_records are clamped to it. */
+int orbit_meshlet_test(orbit_ctx* ctx, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
+                       const void* meshlet_dispatch_buffer, uint64_t capacity_records, void* record_masks, void* stream);
+int orbit_record_masks_scatter_ranked(orbit_ctx* ctx, const void* src_record_masks, uint64_t src_capacity_records,
+                                      void* dst_record_masks, const uint32_t* rank_record_counts, uint32_t rank, uint32_t world,
+                                      uint64_t dst_capacity_records, void* stream);
+int orbit_draws_from_masks(orbit_ctx* ctx, const OrbitSceneBuffers* scene, const void* record_masks, uint64_t capacity_records,
+                           const uint32_t* rank_record_counts, uint32_t world, uint64_t rank_capacity_records,
+                           void* draw_command_buffer, uint64_t capacity_draws, void* stream);
 
 /* Peer-visible device memory for that assembly: one process per GPU, so a rank's output buffer is shared with the
  * other ranks through CUDA IPC. `orbit_peer_alloc` returns cudaMalloc'd memory plus its 64-byte IPC handle;

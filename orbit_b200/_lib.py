@@ -21,6 +21,7 @@ PROTOTYPES = {
     "orbit_ctx_destroy": (None, [C.c_void_p]),
     "orbit_ctx_poll_status": (C.c_int, [C.c_void_p, C.POINTER(L.Status)]),
     "orbit_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "orbit_ctx_reserve": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "orbit_hiz_geometry": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(L.HizInfo)]),
     "orbit_hiz_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "orbit_hiz_wrap": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -34,10 +35,16 @@ PROTOTYPES = {
     "orbit_light_cluster": (C.c_int, [C.c_void_p, C.POINTER(L.ClusterParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "orbit_scene_update": (C.c_int, [C.c_void_p, C.POINTER(L.SceneUpdate), C.c_void_p]),
-    "orbit_draws_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
+    "orbit_draws_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
                                       C.c_void_p]),
-    "orbit_draws_scatter_ranked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
+    "orbit_draws_scatter_ranked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
                                              C.c_void_p]),
+    "orbit_meshlet_test": (C.c_int, [C.c_void_p, C.POINTER(L.CullInfo), C.POINTER(L.SceneBuffers), C.c_void_p, C.c_void_p, C.c_uint64,
+                                     C.c_void_p, C.c_void_p]),
+    "orbit_record_masks_scatter_ranked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                                    C.c_uint64, C.c_void_p]),
+    "orbit_draws_from_masks": (C.c_int, [C.c_void_p, C.POINTER(L.SceneBuffers), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64,
+                                         C.c_void_p, C.c_uint64, C.c_void_p]),
     "orbit_peer_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]),
     "orbit_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "orbit_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -68,7 +75,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if handle.orbit_abi_version() != 1:
+        if handle.orbit_abi_version() != 2:
             raise ImportError("liborbit_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -28,20 +28,36 @@ static thread_local int g_last_cuda_error = 0;
         if (e_ != cudaSuccess) { g_last_cuda_error = (int)e_; return ORBIT_ERR_CUDA; } \
     } while (0)
 
+// Makes `device` current for the duration of an entry point and restores the caller's device afterwards: a context may be
+// used from any thread (the reference records its passes from rayon workers), whatever device that thread has current.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+        if (cur != device) { ok = cudaSetDevice(device) == cudaSuccess; prev = cur; }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define GUARD(c) DeviceGuard guard_((c)->device); if (!guard_.ok) { g_last_cuda_error = (int)cudaGetLastError(); return ORBIT_ERR_CUDA; }
+
 struct orbit_ctx {
     int device = 0;
     int sm_count = 0;
     // scan scratch
     unsigned long long* status = nullptr;
     size_t status_capacity = 0;       // descriptors
-    unsigned int* counters = nullptr; // 16 words: [0] ticket, [1] done, [2] hiz ticket, [3] scan epoch (device-advanced), [4,5] meshlet survivor
-                                      // totals per parity, [6,7] parity words A/B of the meshlet stage, [8] scene-update cursor snapshot
+    unsigned int* counters = nullptr; // 32 words: [0] ticket, [1] done, [2] hiz ticket, [3] scan epoch (device-advanced), [4,5] meshlet survivor
+                                      // totals per parity, [6,7] parity words A/B of the meshlet stage, [8] scene-update cursor snapshot,
+                                      // [10..13] the same four words for test-only calls, [16..18] dispatch header of orbit_draws_from_masks
     // device-written status, pinned + mapped
     OrbitStatus* status_host = nullptr;
     OrbitStatus* status_dev = nullptr;
     uint32_t* chunk_counts = nullptr; // 2 x 2048 per-chunk survivor counts
     // meshlet stage scratch: one draw mask per dispatch record
     uint4* draw_masks = nullptr;
+    uint4* cmd_side = nullptr;        // 32 entries per dispatch record, same capacity as draw_masks
     size_t draw_mask_capacity = 0;
     // scene-update scratch: per-tile sums (kept apart from `status`, whose words carry scan epochs)
     unsigned long long* tile_sums = nullptr;
@@ -55,6 +71,13 @@ struct orbit_ctx {
     int debug_skip = 0;               // ORBIT_DEBUG_SKIP: 1 = skip emit kernel, 2 = skip test kernel (timing experiments only)
     int entity_occupancy = 0;
     int mc_occupancy[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cached occupancy per meshlet test-kernel variant
+    int emit_ctas_per_sm = 0;         // ORBIT_EMIT_CTAS_PER_SM (tuning knob, read once at creation)
+    // Scratch that was outgrown is parked here until the context is destroyed: freeing it would need a device
+    // synchronisation (work that uses it may still be in flight), and a stage call never synchronises.
+    void* retired[64] = {};
+    int n_retired = 0;
+    unsigned long long* trace = nullptr;   // -DORBIT_TRACE builds only: 16 blocks of 1024 x 16 stamps
+    unsigned trace_seq = 0;
     std::atomic<uint64_t> launches{0};
 };
 
@@ -65,13 +88,29 @@ struct orbit_hiz {
     int device;
 };
 
-static int ensure_status(orbit_ctx* c, size_t tiles) {
+// Outgrown scratch is retired, not freed (see orbit_ctx::retired). With doubling capacities a context retires a handful of
+// buffers in its life; if the list ever fills up the oldest entries are freed after one device synchronisation.
+static int retire(orbit_ctx* c, void* p) {
+    if (!p) return ORBIT_OK;
+    if (c->n_retired == 64) {
+        CK(cudaDeviceSynchronize());
+        for (int i = 0; i < 64; ++i) cudaFree(c->retired[i]);
+        c->n_retired = 0;
+    }
+    c->retired[c->n_retired++] = p;
+    return ORBIT_OK;
+}
+
+// Scan descriptors; a fresh array is zeroed on `stream` (epoch 0 never matches a launch: epochs start at 1).
+static int ensure_status(orbit_ctx* c, size_t tiles, cudaStream_t stream) {
     if (tiles <= c->status_capacity) return ORBIT_OK;
     size_t cap = c->status_capacity ? c->status_capacity : 4096;
     while (cap < tiles) cap *= 2;
-    if (c->status) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->status)); c->status = nullptr; c->status_capacity = 0; }
+    int rc = retire(c, c->status);
+    if (rc != ORBIT_OK) return rc;
+    c->status = nullptr; c->status_capacity = 0;
     CK(cudaMalloc(&c->status, cap * sizeof(unsigned long long)));
-    CK(cudaMemset(c->status, 0, cap * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->status, 0, cap * sizeof(unsigned long long), stream));
     c->status_capacity = cap;
     return ORBIT_OK;
 }
@@ -80,14 +119,46 @@ static int ensure_tile_sums(orbit_ctx* c, size_t tiles) {
     if (tiles <= c->tile_sums_capacity) return ORBIT_OK;
     size_t cap = c->tile_sums_capacity ? c->tile_sums_capacity : 1024;
     while (cap < tiles) cap *= 2;
-    if (c->tile_sums) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->tile_sums)); c->tile_sums = nullptr; c->tile_sums_capacity = 0; }
+    int rc = retire(c, c->tile_sums);
+    if (rc != ORBIT_OK) return rc;
+    c->tile_sums = nullptr; c->tile_sums_capacity = 0;
     CK(cudaMalloc(&c->tile_sums, cap * sizeof(unsigned long long)));
     c->tile_sums_capacity = cap;
     return ORBIT_OK;
 }
 
+static int ensure_record_scratch(orbit_ctx* c, uint64_t max_records) {
+    if (max_records <= c->draw_mask_capacity) return ORBIT_OK;
+    int rc = retire(c, c->draw_masks);
+    if (rc == ORBIT_OK) rc = retire(c, c->cmd_side);
+    if (rc != ORBIT_OK) return rc;
+    c->draw_masks = nullptr; c->cmd_side = nullptr; c->draw_mask_capacity = 0;
+    size_t cap = 65536; while (cap < max_records) cap *= 2;
+    CK(cudaMalloc(&c->draw_masks, cap * sizeof(uint4)));
+    CK(cudaMalloc(&c->cmd_side, cap * 32u * sizeof(uint4)));
+    c->draw_mask_capacity = cap;
+    return ORBIT_OK;
+}
+
+static int ensure_lights(orbit_ctx* c, uint64_t n_lights) {
+    if (n_lights <= c->light_capacity) return ORBIT_OK;
+    int rc = retire(c, c->light_view);
+    if (rc != ORBIT_OK) return rc;
+    c->light_view = nullptr; c->light_capacity = 0;
+    size_t cap = 1024; while (cap < n_lights) cap *= 2;
+    CK(cudaMalloc(&c->light_view, cap * sizeof(float4)));
+    c->light_capacity = cap;
+    return ORBIT_OK;
+}
+
+// block of the timeline buffer for the next kernel launch (development builds), else nullptr
+static unsigned long long* next_trace(orbit_ctx* c) {
+    if (!c->trace) return nullptr;
+    return c->trace + (size_t)(c->trace_seq++ % 16u) * 1024u * 16u;
+}
+
 static ScanState next_scan(orbit_ctx* c) {
-    return ScanState{c->status, c->counters + 0, c->counters + 1, c->counters + 3};
+    return ScanState{next_trace(c), c->status, c->counters + 0, c->counters + 1, c->counters + 3};
 }
 
 static HizDevice hiz_device(const orbit_hiz* h) {
@@ -126,35 +197,45 @@ int orbit_ctx_create(int device, orbit_ctx** out) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) { g_last_cuda_error = (int)e; return ORBIT_ERR_NO_DEVICE; }
     if (device < 0 || device >= n) return ORBIT_ERR_INVALID_ARGUMENT;
-    CK(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (!guard.ok) { g_last_cuda_error = (int)cudaGetLastError(); return ORBIT_ERR_CUDA; }
     orbit_ctx* c = new (std::nothrow) orbit_ctx();
     if (!c) return ORBIT_ERR_OUT_OF_MEMORY;
     c->device = device;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    CK(cudaMalloc(&c->counters, 16 * sizeof(unsigned int)));
-    CK(cudaMemset(c->counters, 0, 16 * sizeof(unsigned int)));
+    CK(cudaMalloc(&c->counters, 32 * sizeof(unsigned int)));
+    CK(cudaMemset(c->counters, 0, 32 * sizeof(unsigned int)));
     { const unsigned int one = 1u; CK(cudaMemcpy(c->counters + 3, &one, sizeof(one), cudaMemcpyHostToDevice)); }
-    CK(cudaMalloc(&c->chunk_counts, 2 * 2048 * sizeof(uint32_t)));
-    CK(cudaMemset(c->chunk_counts, 0, 2 * 2048 * sizeof(uint32_t)));
+    CK(cudaMalloc(&c->chunk_counts, 4 * 2048 * sizeof(uint32_t)));   // two parities for orbit_meshlet_cull + two (never read) for orbit_meshlet_test
+    CK(cudaMemset(c->chunk_counts, 0, 4 * 2048 * sizeof(uint32_t)));
     CK(cudaHostAlloc(&c->status_host, sizeof(OrbitStatus), cudaHostAllocMapped));
     std::memset(c->status_host, 0, sizeof(OrbitStatus));
     CK(cudaHostGetDevicePointer(&c->status_dev, c->status_host, 0));
-    int rc = ensure_status(c, 4096);
+    int rc = ensure_status(c, 4096, nullptr);
     if (rc != ORBIT_OK) return rc;
+    CK(cudaDeviceSynchronize());
     CK(meshlet_cull_configure_device());
+    CK(light_cluster_configure_device());
+#ifdef ORBIT_TRACE
+    CK(cudaMalloc(&c->trace, 16u * 1024u * 16u * sizeof(unsigned long long)));
+    CK(cudaMemset(c->trace, 0, 16u * 1024u * 16u * sizeof(unsigned long long)));
+#endif
     if (const char* s = std::getenv("ORBIT_DEBUG_SKIP")) c->debug_skip = std::atoi(s);
     if (const char* s = std::getenv("ORBIT_MC_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->mc_ctas_per_sm = v; }
+    if (const char* s = std::getenv("ORBIT_EMIT_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->emit_ctas_per_sm = v; }
     *out = c;
     return ORBIT_OK;
 }
 
 void orbit_ctx_destroy(orbit_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->draw_masks); cudaFree(c->chunk_counts); cudaFree(c->tile_sums);
+    for (int i = 0; i < c->n_retired; ++i) cudaFree(c->retired[i]);
+    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->draw_masks); cudaFree(c->cmd_side); cudaFree(c->chunk_counts); cudaFree(c->tile_sums);
+    cudaFree(c->trace);
     cudaFreeHost(c->status_host);
     delete c;
 }
@@ -167,6 +248,31 @@ int orbit_ctx_poll_status(orbit_ctx* c, OrbitStatus* out) {
 }
 
 uint64_t orbit_ctx_launch_count(const orbit_ctx* c) { return c ? c->launches.load() : 0; }
+
+int orbit_ctx_reserve(orbit_ctx* c, uint64_t entity_draws, uint64_t capacity_records, uint64_t n_lights, uint64_t n_clusters, uint64_t n_entities) {
+    if (!c) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (capacity_records > 0xFFFFFFFFull) capacity_records = 0xFFFFFFFFull;
+    GUARD(c);
+    size_t tiles = (size_t)(entity_draws + 255u) / 256u + 1u;
+    if ((size_t)n_clusters + 1u > tiles) tiles = (size_t)n_clusters + 1u;
+    int rc = ensure_status(c, tiles, nullptr);
+    if (rc == ORBIT_OK && capacity_records) rc = ensure_record_scratch(c, capacity_records);
+    if (rc == ORBIT_OK && n_lights) rc = ensure_lights(c, n_lights);
+    if (rc == ORBIT_OK && n_entities) rc = ensure_tile_sums(c, ((size_t)n_entities + 255u) / 256u);
+    if (rc != ORBIT_OK) return rc;
+    CK(cudaDeviceSynchronize());   // the one place that may synchronise: after this, stage calls within these sizes never allocate
+    return ORBIT_OK;
+}
+
+#ifdef ORBIT_TRACE
+// development builds only: device pointer and size of the timeline buffer (see scan.cuh)
+int orbit_debug_trace(orbit_ctx* c, void** ptr, uint64_t* bytes) {
+    if (!c || !ptr || !bytes) return ORBIT_ERR_INVALID_ARGUMENT;
+    *ptr = c->trace; *bytes = 16ull * 1024ull * 16ull * sizeof(unsigned long long);
+    c->trace_seq = 0;   // the next launch stamps block 0 again
+    return ORBIT_OK;
+}
+#endif
 
 // ---- depth pyramid -------------------------------------------------------------------------------------
 int orbit_hiz_geometry(uint32_t dw, uint32_t dh, OrbitHizInfo* out) {
@@ -195,7 +301,8 @@ static int hiz_make(orbit_ctx* c, uint32_t dw, uint32_t dh, float* texels, bool 
     if (rc != ORBIT_OK) { delete h; return rc; }
     h->depth_w = dw; h->depth_h = dh; h->owns = owns; h->device = c->device;
     if (owns) {
-        cudaError_t e = cudaSetDevice(c->device);
+        DeviceGuard guard(c->device);
+        cudaError_t e = guard.ok ? cudaSuccess : cudaErrorInvalidDevice;
         if (e == cudaSuccess) e = cudaMalloc(&texels, (size_t)h->info.total_texels * sizeof(float));
         if (e != cudaSuccess) { g_last_cuda_error = (int)e; delete h; return e == cudaErrorMemoryAllocation ? ORBIT_ERR_OUT_OF_MEMORY : ORBIT_ERR_CUDA; }
     } else if (!texels || ((uintptr_t)texels & 15u)) {
@@ -211,7 +318,7 @@ int orbit_hiz_wrap(orbit_ctx* c, uint32_t dw, uint32_t dh, float* texels, orbit_
 
 void orbit_hiz_destroy(orbit_hiz* h) {
     if (!h) return;
-    if (h->owns) { cudaSetDevice(h->device); cudaFree(h->info.texels); }
+    if (h->owns) { DeviceGuard guard(h->device); cudaFree(h->info.texels); }
     delete h;
 }
 
@@ -223,11 +330,13 @@ int orbit_hiz_info(const orbit_hiz* h, OrbitHizInfo* out) {
 
 int orbit_hiz_build(orbit_ctx* c, orbit_hiz* h, const float* depth, uint32_t dw, uint32_t dh, void* stream) {
     if (!c || !h || !depth || dw != h->depth_w || dh != h->depth_h) return ORBIT_ERR_INVALID_ARGUMENT;
+    GUARD(c);
     HizBuildParams p{};
     p.depth = depth; p.texels = h->info.texels; p.depth_w = dw; p.depth_h = dh;
     p.width = h->info.width; p.height = h->info.height; p.levels = h->info.levels;
     for (int i = 0; i < ORBIT_HIZ_MAX_LEVELS; ++i) p.level_offset[i] = h->info.level_offset[i];
     p.ticket = c->counters + 2;
+    p.trace = next_trace(c);
     CK(launch_hiz_build(p, (cudaStream_t)stream));
     c->launches += 1;
     return ORBIT_OK;
@@ -265,7 +374,8 @@ int orbit_entity_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneB
     if (end > scene->entity_draw_count) end = scene->entity_draw_count;
     if (begin > end) return ORBIT_ERR_INVALID_ARGUMENT;
     const uint32_t n = end - begin;
-    rc = ensure_status(c, (size_t)(n + 255u) / 256u + 1u);
+    GUARD(c);
+    rc = ensure_status(c, (size_t)(n + 255u) / 256u + 1u, (cudaStream_t)stream);
     if (rc != ORBIT_OK) return rc;
     EntityCullParams p{};
     p.cull = *cull; p.hiz = hiz_device(hiz);
@@ -285,22 +395,24 @@ int orbit_entity_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneB
 }
 
 // ---- meshlet stage ---------------------------------------------------------------------------------------
-int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
-                       const void* meshlet_dispatch_buffer, uint64_t capacity_records, void* draw_command_buffer,
-                       uint64_t capacity_draws, void* task_payloads, void* stream) {
-    if (!c || !meshlet_dispatch_buffer || !draw_command_buffer) return ORBIT_ERR_INVALID_ARGUMENT;
-    if (((uintptr_t)meshlet_dispatch_buffer & 3u) || ((uintptr_t)draw_command_buffer & 3u) || ((uintptr_t)task_payloads & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
+// mode 0: test + emit (orbit_meshlet_cull); mode 1: test only, record entries into `record_masks` (orbit_meshlet_test)
+static int meshlet_stage(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
+                         const void* meshlet_dispatch_buffer, uint64_t capacity_records, void* draw_command_buffer,
+                         uint64_t capacity_draws, void* task_payloads, void* record_masks, void* stream) {
+    const bool test_only = record_masks != nullptr;
+    if (!c || !meshlet_dispatch_buffer || (!test_only && !draw_command_buffer)) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)meshlet_dispatch_buffer & 3u) || ((uintptr_t)draw_command_buffer & 3u) || ((uintptr_t)task_payloads & 3u) ||
+        ((uintptr_t)record_masks & 15u)) return ORBIT_ERR_INVALID_ARGUMENT;
     if (capacity_records > 0xFFFFFFFFull) capacity_records = 0xFFFFFFFFull;
     int rc = check_cull(cull, scene, hiz, true);
     if (rc != ORBIT_OK) return rc;
     // The record count lives on the device (the reference's dispatch_indirect); scratch and grid are sized for
     // the dispatch buffer's capacity and the kernel clamps the device-side count to it.
     const uint64_t max_records = capacity_records;
-    if (max_records > c->draw_mask_capacity) {
-        if (c->draw_masks) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->draw_masks)); c->draw_masks = nullptr; c->draw_mask_capacity = 0; }
-        size_t cap = 65536; while (cap < max_records) cap *= 2;
-        CK(cudaMalloc(&c->draw_masks, cap * sizeof(uint4)));
-        c->draw_mask_capacity = cap;
+    GUARD(c);
+    if (!test_only) {
+        rc = ensure_record_scratch(c, max_records);
+        if (rc != ORBIT_OK) return rc;
     }
     MeshletCullParams p{};
     p.cull = *cull; p.hiz = hiz_device(hiz);
@@ -312,12 +424,25 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     p.draw_words = (uint32_t*)draw_command_buffer;
     p.task_payloads = (uint32_t*)task_payloads;
     p.overflow_flag = &c->status_dev->draw_overflow;
-    p.draw_masks = c->draw_masks;
-    p.draw_total = c->counters + 4;     // [4],[5]
-    p.chunk_parity = c->counters + 6;   // [6] word A, [7] word B
-    p.chunk_counts = c->chunk_counts;
+    if (!test_only) {
+        p.draw_masks = c->draw_masks;
+        p.cmd_side = c->cmd_side;
+        p.draw_total = c->counters + 4;     // [4],[5]
+        p.chunk_parity = c->counters + 6;   // [6] word A, [7] word B
+        p.chunk_counts = c->chunk_counts;
+    } else {
+        // the survivor counters of a test-only call are never read: they go to a second set of scratch words, so that
+        // they cannot leak into a later orbit_meshlet_cull / orbit_draws_from_masks of this context
+        p.draw_masks = (uint4*)record_masks;
+        p.cmd_side = nullptr;               // entries carry flag 1: whoever emits reads the meshlet itself
+        p.draw_total = c->counters + 10;    // [10],[11]
+        p.chunk_parity = c->counters + 12;  // [12],[13]
+        p.chunk_counts = c->chunk_counts + 2 * 2048;
+    }
     p.capacity_records = max_records;
     p.capacity_draws = capacity_draws;
+    p.scan.trace = next_trace(c);
+    p.trace_emit = next_trace(c);
     p.pk_one = make_float2(1.0f, 1.0f); p.pk_mone = make_float2(-1.0f, -1.0f);
     for (uint32_t j = 0; j < 6u; ++j) {
         const uint32_t n = cull->cull_plane_count;
@@ -334,10 +459,64 @@ int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     // emit kernel: two CTAs per SM (every CTA repeats the 2048-entry chunk scan; more CTAs only add to that)
     if (c->emit_occupancy <= 0) c->emit_occupancy = meshlet_emit_max_ctas_per_sm();
     int emit_per_sm = c->emit_occupancy < 2 ? (c->emit_occupancy > 0 ? c->emit_occupancy : 1) : 2;
-    if (const char* s = std::getenv("ORBIT_EMIT_CTAS_PER_SM")) { const int v = std::atoi(s); if (v >= 1 && v <= c->emit_occupancy) emit_per_sm = v; }   // tuning knob
+    if (c->emit_ctas_per_sm >= 1 && c->emit_ctas_per_sm <= c->emit_occupancy) emit_per_sm = c->emit_ctas_per_sm;   // tuning knob
     const uint64_t emit_grid = (uint64_t)c->sm_count * (uint64_t)emit_per_sm;
-    CK(launch_meshlet_cull(p, c->debug_skip == 2 ? 0 : (int)grid, c->debug_skip == 1 ? 0 : (int)emit_grid, (cudaStream_t)stream));
-    c->launches += 2;   // test kernel + emit kernel
+    const bool skip_emit = test_only || c->debug_skip == 1;
+    CK(launch_meshlet_cull(p, c->debug_skip == 2 ? 0 : (int)grid, skip_emit ? 0 : (int)emit_grid, (cudaStream_t)stream));
+    c->launches += test_only ? 1 : 2;   // test kernel (+ emit kernel)
+    return ORBIT_OK;
+}
+
+int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
+                       const void* meshlet_dispatch_buffer, uint64_t capacity_records, void* draw_command_buffer,
+                       uint64_t capacity_draws, void* task_payloads, void* stream) {
+    return meshlet_stage(c, cull, scene, hiz, meshlet_dispatch_buffer, capacity_records, draw_command_buffer, capacity_draws, task_payloads,
+                         nullptr, stream);
+}
+
+int orbit_meshlet_test(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
+                       const void* meshlet_dispatch_buffer, uint64_t capacity_records, void* record_masks, void* stream) {
+    if (!record_masks) return ORBIT_ERR_INVALID_ARGUMENT;
+    return meshlet_stage(c, cull, scene, hiz, meshlet_dispatch_buffer, capacity_records, nullptr, 0, nullptr, record_masks, stream);
+}
+
+int orbit_record_masks_scatter_ranked(orbit_ctx* c, const void* src_record_masks, uint64_t src_capacity_records, void* dst_record_masks,
+                                      const uint32_t* rank_record_counts, uint32_t rank, uint32_t world, uint64_t dst_capacity_records,
+                                      void* stream) {
+    if (!c || !src_record_masks || !dst_record_masks || !rank_record_counts || world == 0u || rank >= world) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)src_record_masks | (uintptr_t)dst_record_masks) & 15u) return ORBIT_ERR_INVALID_ARGUMENT;
+    GUARD(c);
+    CK(launch_record_masks_scatter((const uint4*)src_record_masks, (uint4*)dst_record_masks, rank_record_counts, rank, world,
+                                   src_capacity_records, dst_capacity_records, c->sm_count * 8, (cudaStream_t)stream));
+    c->launches += 1;
+    return ORBIT_OK;
+}
+
+int orbit_draws_from_masks(orbit_ctx* c, const OrbitSceneBuffers* scene, const void* record_masks, uint64_t capacity_records,
+                           const uint32_t* rank_record_counts, uint32_t world, uint64_t rank_capacity_records,
+                           void* draw_command_buffer, uint64_t capacity_draws, void* stream) {
+    if (!c || !scene || !scene->meshlets || !record_masks || !rank_record_counts || world == 0u || !draw_command_buffer) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)record_masks & 15u) || ((uintptr_t)draw_command_buffer & 3u) || ((uintptr_t)scene->meshlets & 15u)) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (capacity_records > 0xFFFFFFFFull) capacity_records = 0xFFFFFFFFull;
+    GUARD(c);
+    MeshletCullParams p{};
+    p.meshlets = (const uint4*)scene->meshlets;
+    p.draw_words = (uint32_t*)draw_command_buffer;
+    p.overflow_flag = &c->status_dev->draw_overflow;
+    p.draw_masks = (uint4*)record_masks;      // read only on this path
+    p.cmd_side = nullptr;
+    p.draw_total = c->counters + 4;
+    p.chunk_parity = c->counters + 6;
+    p.chunk_counts = c->chunk_counts;
+    p.capacity_records = capacity_records;
+    p.capacity_draws = capacity_draws;
+    p.dispatch_words = c->counters + 16;      // a 3-word dispatch header written by the recount kernel
+    p.trace_emit = next_trace(c);
+    if (c->emit_occupancy <= 0) c->emit_occupancy = meshlet_emit_max_ctas_per_sm();
+    const int emit_per_sm = c->emit_occupancy < 2 ? (c->emit_occupancy > 0 ? c->emit_occupancy : 1) : 2;
+    CK(launch_draws_from_masks(p, rank_record_counts, world, rank_capacity_records, c->counters + 16, c->sm_count * 4,
+                               c->sm_count * emit_per_sm, (cudaStream_t)stream));
+    c->launches += 2;
     return ORBIT_OK;
 }
 
@@ -358,13 +537,10 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
     if (L != 0 && (!lights || ((uintptr_t)lights & 15u))) return ORBIT_ERR_INVALID_ARGUMENT;
     cudaStream_t s = (cudaStream_t)stream;
     const uint64_t clusters = cx * cy * cz;
-    if (L > c->light_capacity) {
-        if (c->light_view) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->light_view)); c->light_view = nullptr; c->light_capacity = 0; }
-        size_t cap = 1024; while (cap < L) cap *= 2;
-        CK(cudaMalloc(&c->light_view, cap * sizeof(float4)));
-        c->light_capacity = cap;
-    }
-    int rc = ensure_status(c, (size_t)clusters + 1u);   // light culling scans one tile per active cluster
+    GUARD(c);
+    int rc = ensure_lights(c, L);
+    if (rc != ORBIT_OK) return rc;
+    rc = ensure_status(c, (size_t)clusters + 1u, s);   // light culling scans one tile per active cluster
     if (rc != ORBIT_OK) return rc;
     ClusterParams p{};
     p.info = ci; p.z_scale = params->z_scale; p.z_bias = params->z_bias;
@@ -394,19 +570,21 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
     return ORBIT_OK;
 }
 
-int orbit_draws_scatter(orbit_ctx* c, const void* src, void* dst, uint32_t dst_first, uint32_t total_count,
+int orbit_draws_scatter(orbit_ctx* c, const void* src, uint64_t src_capacity_draws, void* dst, uint32_t dst_first, uint32_t total_count,
                         uint64_t dst_capacity_draws, void* stream) {
     if (!c || !src || !dst) return ORBIT_ERR_INVALID_ARGUMENT;
-    CK(launch_draws_scatter((const uint32_t*)src, (uint32_t*)dst, dst_first, total_count, dst_capacity_draws,
+    GUARD(c);
+    CK(launch_draws_scatter((const uint32_t*)src, src_capacity_draws, (uint32_t*)dst, dst_first, total_count, dst_capacity_draws,
                             c->sm_count * 16, (cudaStream_t)stream, nullptr, 0u, 0u));
     c->launches += 1;
     return ORBIT_OK;
 }
 
-int orbit_draws_scatter_ranked(orbit_ctx* c, const void* src, void* dst, const uint32_t* rank_counts, uint32_t rank, uint32_t world,
+int orbit_draws_scatter_ranked(orbit_ctx* c, const void* src, uint64_t src_capacity_draws, void* dst, const uint32_t* rank_counts, uint32_t rank, uint32_t world,
                                uint64_t dst_capacity_draws, void* stream) {
     if (!c || !src || !dst || !rank_counts || world == 0u || rank >= world) return ORBIT_ERR_INVALID_ARGUMENT;
-    CK(launch_draws_scatter((const uint32_t*)src, (uint32_t*)dst, 0u, 0u, dst_capacity_draws, c->sm_count * 16, (cudaStream_t)stream,
+    GUARD(c);
+    CK(launch_draws_scatter((const uint32_t*)src, src_capacity_draws, (uint32_t*)dst, 0u, 0u, dst_capacity_draws, c->sm_count * 16, (cudaStream_t)stream,
                             rank_counts, rank, world));
     c->launches += 1;
     return ORBIT_OK;
@@ -415,6 +593,7 @@ int orbit_draws_scatter_ranked(orbit_ctx* c, const void* src, void* dst, const u
 int orbit_scene_update(orbit_ctx* c, const OrbitSceneUpdate* u, void* stream) {
     if (!c || !u) return ORBIT_ERR_INVALID_ARGUMENT;
     if (!u->entity_draws) return ORBIT_ERR_INVALID_ARGUMENT;
+    GUARD(c);
     if (u->n_entities == 0u) {   // empty scene: only the count header is produced
         CK(cudaMemsetAsync(u->entity_draws, 0, 4, (cudaStream_t)stream));
         return ORBIT_OK;
@@ -439,7 +618,7 @@ int orbit_scene_update(orbit_ctx* c, const OrbitSceneUpdate* u, void* stream) {
 
 int orbit_peer_alloc(orbit_ctx* c, uint64_t bytes, void** out_ptr, void* out_handle) {
     if (!c || !out_ptr || !out_handle || bytes == 0) return ORBIT_ERR_INVALID_ARGUMENT;
-    CK(cudaSetDevice(c->device));
+    GUARD(c);
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return e == cudaErrorMemoryAllocation ? ORBIT_ERR_OUT_OF_MEMORY : ORBIT_ERR_CUDA; }
@@ -454,7 +633,7 @@ int orbit_peer_alloc(orbit_ctx* c, uint64_t bytes, void** out_ptr, void* out_han
 
 int orbit_peer_open(orbit_ctx* c, const void* handle, void** out_ptr) {
     if (!c || !handle || !out_ptr) return ORBIT_ERR_INVALID_ARGUMENT;
-    CK(cudaSetDevice(c->device));
+    GUARD(c);
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle, sizeof(h));
     CK(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -463,14 +642,14 @@ int orbit_peer_open(orbit_ctx* c, const void* handle, void** out_ptr) {
 
 int orbit_peer_close(orbit_ctx* c, void* mapped_ptr) {
     if (!c || !mapped_ptr) return ORBIT_ERR_INVALID_ARGUMENT;
-    CK(cudaSetDevice(c->device));
+    GUARD(c);
     CK(cudaIpcCloseMemHandle(mapped_ptr));
     return ORBIT_OK;
 }
 
 void orbit_peer_free(orbit_ctx* c, void* ptr) {
     if (!c || !ptr) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     cudaFree(ptr);
 }
 
@@ -489,16 +668,20 @@ namespace orbit {
 // each assembled from four 4-byte loads of the local source; up to 3 head and 3 tail words go out as 4-byte stores.
 // rank_counts != nullptr: dst_first and total_count come from the device (the all-gathered per-rank survivor counts):
 // dst_first = sum of the counts of ranks below `rank`, total = sum over all `world` ranks — no host round trip.
-__global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+// A count header may exceed its buffer's capacity after an overflow (the emit kernel stores the exact survivor count and
+// drops the commands beyond capacity): every count read here — the source's own and the other ranks' — is clamped to
+// src_capacity (the ranks of a sharded view use equal capacities), so nothing is read past a source buffer and the
+// rank-major list has no gaps.
+__global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __restrict__ src, uint64_t src_capacity, uint32_t* __restrict__ dst,
                                                             uint32_t dst_first, uint32_t total_count, uint64_t dst_capacity,
                                                             const uint32_t* __restrict__ rank_counts, uint32_t rank, uint32_t world) {
     if (rank_counts) {
         uint32_t first = 0u, total = 0u;
-        for (uint32_t r = 0; r < world; ++r) { const uint32_t c = __ldcg(rank_counts + r); if (r < rank) first += c; total += c; }
+        for (uint32_t r = 0; r < world; ++r) { const uint32_t c = (uint32_t)min((uint64_t)__ldcg(rank_counts + r), src_capacity); if (r < rank) first += c; total += c; }
         dst_first = first; total_count = total;
     }
     const uint32_t n = __ldcg(src);
-    uint64_t m = n;
+    uint64_t m = min((uint64_t)n, src_capacity);
     if ((uint64_t)dst_first >= dst_capacity) m = 0; else if ((uint64_t)dst_first + m > dst_capacity) m = dst_capacity - dst_first;
     const uint64_t words = m * 7u;
     const uint32_t* s = src + 1;
@@ -531,9 +714,9 @@ __global__ void __launch_bounds__(256) draws_scatter_kernel(const uint32_t* __re
     if (gtid < words - done) d[done + gtid] = __ldcg(s + done + gtid);
     if (blockIdx.x == 0 && threadIdx.x == 0 && total_count != 0xFFFFFFFFu) dst[0] = total_count;
 }
-cudaError_t launch_draws_scatter(const uint32_t* src, uint32_t* dst, uint32_t dst_first, uint32_t total_count,
+cudaError_t launch_draws_scatter(const uint32_t* src, uint64_t src_capacity, uint32_t* dst, uint32_t dst_first, uint32_t total_count,
                                  uint64_t dst_capacity, int grid, cudaStream_t s, const uint32_t* rank_counts, uint32_t rank, uint32_t world) {
-    draws_scatter_kernel<<<grid, 256, 0, s>>>(src, dst, dst_first, total_count, dst_capacity, rank_counts, rank, world);
+    draws_scatter_kernel<<<grid, 256, 0, s>>>(src, src_capacity, dst, dst_first, total_count, dst_capacity, rank_counts, rank, world);
     return cudaGetLastError();
 }
 }  // namespace orbit

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const OrbitCullInfo& ci = p.cull;
     pdl_wait();
+    ORBIT_TRACE_STAMP(p.scan.trace, 0, 0);
     const unsigned int epoch = scan_epoch(p.scan);
     uint32_t tile = blockIdx.x;
     if (!kFlat) {
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
         vis_offset = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 2u);
     }
     const uint32_t count = min(__ldg(p.entity_draw_words), p.draw_end);
+    ORBIT_TRACE_STAMP(p.scan.trace, 0, 1 + 0 * (count + epoch));
     const uint32_t pass = ci.occlusion_pass;
     const bool mocc = ci.meshlet_visibility_buffer != ORBIT_NO_BUFFER;
 
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
         for (int k = 0; k < 4; ++k) mcol[k] = as_float4(ld_v4_ordered(p.entities + (size_t)entity_index * 8u + k));
         const bool vib = ((vword >> (gid & 31u)) & 1u) != 0u;
         visible = (pass == 1u) ? vib : true;
+        ORBIT_TRACE_STAMP(p.scan.trace, 0, 2 + 0 * (uint32_t)(mcol[3].w != 0.0f) + 0 * (lods[0].x & sph.x != 0.0f));
 
         // view * model (entity_cull.comp:131-133)
         ModelView mv;
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
     }
     // pass 2: visibility word of these 32 draws (lanes past `count` contribute 0)
     const uint32_t vis_mask = __ballot_sync(0xFFFFFFFFu, visible);
+    ORBIT_TRACE_STAMP(p.scan.trace, 0, 3 + 0 * (vis_mask & 1u));
     if (pass == 2u && lane == 0u && gid < count) p.entity_visibility[gid >> 5] = vis_mask;
 
     // ---- CTA exclusive scan of chunk counts
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
     }
     s_excl[tid] = warp_base + incl - chunks;
     if (tid == 0) s_excl[kEcThreads] = tile_total;
+    ORBIT_TRACE_STAMP(p.scan.trace, 0, 4 + 0 * (tile_total & 1u));
     if (warp == 0u) {
         uint32_t base;
         if (kFlat) {
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
         } else {
             base = lookback_exclusive(p.scan, epoch, tile, tile_total);
         }
+        ORBIT_TRACE_STAMP(p.scan.trace, 0, 5 + 0 * (base & 1u));
         if (lane == 0u) {
             s_base = base;
             if (tile == ntiles - 1u) {
@@ -176,7 +182,9 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
             rec[3] = s_vo[lo] + k;   // every earlier chunk of this draw is full, so += count/32 adds exactly 1 each
         }
     }
+    ORBIT_TRACE_STAMP(p.scan.trace, 0, 6);
     if (tid == 0) scan_cta_exit(p.scan, epoch);
+    ORBIT_TRACE_STAMP(p.scan.trace, 0, 7);
 }
 
 cudaError_t launch_entity_cull(const EntityCullParams& p, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t stream) {

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) hiz_build_kernel(const __grid_constant__ 
     const uint32_t tiles_x = p.width >> 6;
     const uint32_t tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     pdl_wait();
+    ORBIT_TRACE_STAMP(p.trace, 4, 0);
 
     // ---- level 0: lane owns columns 2*lane, 2*lane+1 of rows warp*8 .. warp*8+7 of the tile
     const uint32_t x_a = tx * 64u + 2u * lane;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(256) hiz_build_kernel(const __grid_constant__ 
         va[r] = fminf(fminf(__ldg(r0 + xa0), __ldg(r0 + xa1)), fminf(__ldg(r1 + xa0), __ldg(r1 + xa1)));
         vb[r] = fminf(fminf(__ldg(r0 + xb0), __ldg(r0 + xb1)), fminf(__ldg(r1 + xb0), __ldg(r1 + xb1)));
     }
+    ORBIT_TRACE_STAMP(p.trace, 4, 1 + 0 * (uint32_t)(va[7] + vb[7] > 2.0f));
     {
         float* l0 = p.texels + p.level_offset[0];
 #pragma unroll
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(256) hiz_build_kernel(const __grid_constant__ 
         v6 = fminf(v6, __shfl_xor_sync(0xFFFFFFFFu, v6, 8));
         if (lane == 0u) p.texels[p.level_offset[6] + (size_t)ty * (p.width >> 6) + tx] = v6;
     }
+    ORBIT_TRACE_STAMP(p.trace, 4, 2);
     pdl_launch_dependents();
     if (p.levels <= 7u) return;
     // ---- remaining small levels: last CTA to arrive
@@ -173,10 +176,12 @@ __global__ void __launch_bounds__(256) hiz_build_kernel(const __grid_constant__ 
         if (s_last) *p.ticket = 0u;
     }
     __syncthreads();
+    ORBIT_TRACE_STAMP(p.trace, 4, 3);
     if (!s_last) return;
     __threadfence();
     if ((p.width >> 6) * (p.height >> 6) <= 4096u) hiz_tail_smem(p, 7u, s_top_a, s_top_b);
     else hiz_tail(p, 7u);
+    ORBIT_TRACE_STAMP(p.trace, 4, 4);
 }
 
 cudaError_t launch_hiz_build(const HizBuildParams& p, cudaStream_t stream) {

@@ -337,15 +337,15 @@ cudaError_t launch_light_view(const ClusterParams& p, cudaStream_t s) {
     light_view_kernel<<<(L + 255u) / 256u, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
+static constexpr size_t light_culling_smem_bytes() { return (size_t)kLcWarps * ORBIT_MAX_LIGHTS_PER_CLUSTER * sizeof(uint32_t); }
+
+// More than 48 KB of dynamic shared memory: opt in once per DEVICE (called from orbit_ctx_create with the context's device current).
+cudaError_t light_cluster_configure_device() {
+    return cudaFuncSetAttribute(light_culling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)light_culling_smem_bytes());
+}
+
 cudaError_t launch_light_culling(const ClusterParams& p, int grid, cudaStream_t s) {
-    const size_t smem = (size_t)kLcWarps * ORBIT_MAX_LIGHTS_PER_CLUSTER * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(light_culling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    light_culling_kernel<<<grid, kLcWarps * 32, smem, s>>>(p);
+    light_culling_kernel<<<grid, kLcWarps * 32, light_culling_smem_bytes(), s>>>(p);
     return cudaGetLastError();
 }
 

@@ -470,9 +470,13 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
     const OrbitCullInfo& ci = p.cull;
     const PkConsts k = {p.pk_one, p.pk_mone};
     pdl_wait();
+    ORBIT_TRACE_STAMP(p.scan.trace, 1, 0);
     if (threadIdx.x == 0) *s_next_tile = kMcWarps;
     __syncthreads();
-    // ---- this CTA's tiles: local index j -> tile blockIdx.x + j * gridDim.x; j = warp first, then from the counter
+    // ---- this CTA's tiles: local index j -> tile blockIdx.x + j * gridDim.x; j = warp first, then from the counter.
+    // (Device-wide dynamic hand-out was measured twice and lost twice: a ticket per tile serialises ~13 k same-address atomics
+    // in one L2 slice; batches of 8 tiles claimed per CTA need only ~1.5 k, but the claiming warp then sits out one L2 atomic
+    // round trip per batch with its next tile's loads not yet issued — late pass 34.4 us vs 27.7 us; profiles/r2_meshlet_test_history.txt.)
     auto fetch_tile = [&]() -> uint32_t {
         uint32_t j = 0u;
         if (lane == 0u) j = atomicAdd(s_next_tile, 1u);
@@ -492,6 +496,7 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
     uint32_t cur_word = load_words(t_cur, p.capacity_records), next_word = load_words(t_next, p.capacity_records);
     uint32_t nrec = __ldcg(p.dispatch_words);  // workgroup_count_x written by the entity stage
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
+    ORBIT_TRACE_STAMP(p.scan.trace, 1, 1 + 0 * (nrec & 1u));
     const uint32_t chunk_shift = chunk_shift_of(nrec);
     // Scratch is double-buffered by a parity that lives in device memory (CUDA-graph replays must see fresh state).
     // Word A is read by test kernels and written by emit kernels; word B the other way round: a kernel never writes
@@ -547,6 +552,9 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
         if (!(lane < 4u * R && (uint64_t)t_next * R + (lane >> 2) < (uint64_t)nrec)) next_word = 0u;
     }
     uint32_t warp_total = 0u;   // survivors found by this warp (lets the emit kernel skip everything when zero)
+#ifdef ORBIT_TRACE
+    bool trace_first = true;
+#endif
     uint32_t qhead = 0u, qn = 0u;   // ring-buffer read position and fill (entries [qhead, qhead+qn) mod 128 are pending)
     if (t_cur < tiles_total) issue_tma(cur_word);
     // One extra, empty iteration after the last tile flushes what is left in the ring through the same drain code.
@@ -572,7 +580,7 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
                     vw = ws.vis[lane];
                     p.meshlet_visibility[my_vo] = 0u;
                 }
-                if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(0u, ent, mof, 0u);
+                if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(0u, ent, mof, 1u);   // .w = 1: no side-array entries, the emit kernel reads the meshlet
             } else {
                 cp_async_wait_all();
                 __syncwarp();
@@ -580,6 +588,9 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
             tile_model_view<R>(&ws.rows[0][0], mv_base, my_word, lane, v0, v1, v2, v3);
             mbar_wait(bar, parity);
             parity ^= 1u;
+#ifdef ORBIT_TRACE
+            if (p.scan.trace != nullptr && threadIdx.x == 0 && trace_first) { trace_first = false; ORBIT_TRACE_STAMP(p.scan.trace, 1, 2); }
+#endif
         }
         // The record loop is deliberately NOT unrolled (instruction cache). The extra, empty iteration after a warp's last
         // tile (final_pass) only runs the drain below, on whatever is left in the ring.
@@ -602,8 +613,13 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
                 const bool pre = in_rec && t.pre_visible;
                 if (!kPass2) {
                     // should_draw = visible && alpha passes the filter (meshlet_cull.comp:207)
-                    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pre && (shl1(alpha) & ci.alpha_mode_flags) != 0u);
+                    const bool draw = pre && (shl1(alpha) & ci.alpha_mode_flags) != 0u;
+                    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, draw);
                     if (lane == r) my_mask = mask;
+                    // the command words of a survivor travel to the emit kernel through a side array (L2-resident at the sizes
+                    // where the emit kernel is latency-bound; at C5 scale it replaces a second 32-byte read of every surviving meshlet)
+                    const uint32_t ent_r = __shfl_sync(0xFFFFFFFFu, my_word, r * 4u);
+                    if (draw && p.cmd_side != nullptr) p.cmd_side[(size_t)(rec0 + r) * 32u + lane] = make_uint4(b.y, b.z, b.w, ent_r);
                 } else {
                     // queue the survivors for the Hi-Z test
                     const uint32_t pre_mask = __ballot_sync(0xFFFFFFFFu, pre);
@@ -640,7 +656,7 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
             // load per record and never touches the dispatch buffer); survivors counted per chunk
             const uint32_t ent = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 0u) & 31u);
             const uint32_t mof = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 1u) & 31u);
-            if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(my_mask, ent, mof, 0u);
+            if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(my_mask, ent, mof, p.cmd_side != nullptr ? 0u : 1u);
             const uint32_t tile_total = __reduce_add_sync(0xFFFFFFFFu, __popc(my_mask));
             if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + (rec0 >> chunk_shift), tile_total);   // a tile never straddles a chunk
             warp_total += tile_total;
@@ -649,20 +665,35 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
         t_next2 = t_next2 < tiles_total ? fetch_tile() : 0x7FFFFFFFu;
         final_pass = t_cur >= tiles_total;
     }
+    ORBIT_TRACE_STAMP(p.scan.trace, 1, 3);
     pdl_launch_dependents();
     if (lane == 0u && warp_total != 0u) atomicAdd(draw_total, warp_total);
+#ifdef ORBIT_TRACE
+    __syncthreads();
+    ORBIT_TRACE_STAMP(p.scan.trace, 1, 4);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Packed mode: pass 1 with a meshlet visibility buffer. Only lanes whose visibility bit is set can be visible
-// (visible = visible_in_buffer, meshlet_cull.comp:137), so they are packed across the tile's records and only
-// those meshlets are loaded and tested. Latency-bound (little work per tile): small shared-memory footprint so
-// that many warps are resident, and the visibility words and model matrices are fetched in parallel.
+// (visible = visible_in_buffer, meshlet_cull.comp:137), so only those meshlets are loaded and tested.
+//
+// The kernel is latency-bound, and the candidates are badly distributed: most tiles of R records hold none (occluded
+// entities), a tile inside the visible part of the scene up to 32 R. A warp that tests its own tile's candidates 32 at a
+// time sets the kernel's duration by the heaviest tile (measured on C2: warps without candidates done after 2.6 us, the
+// heaviest after 9.7 us; profiles/r2_frame_timeline.txt). So the candidates of a CTA's eight tiles go into ONE
+// shared-memory queue and all eight warps drain it, two batches of 32 per step with both batches' meshlet gathers in
+// flight and their arithmetic interleaved; and the tiles of a CTA are taken gridDim.x apart (tile = (round * 8 + warp) *
+// gridDim.x + blockIdx.x), so every CTA gets the same mix of empty and full tiles. The dependent loads of a tile (record
+// words -> visibility word + model matrix -> meshlets) are software-pipelined across rounds: round k+1's chain is started
+// before round k's queue is drained, and the first two rounds' record words are requested before the record count is known.
 template <int R>
-struct __align__(16) PackedSmem {
-    float mv[2][R][kMvStride];     // double-buffered: the next tile's matrices are built while this tile is tested
-    uint32_t items[R * 32];
-    uint32_t mask[R];
+struct __align__(16) PackedCtaSmem {
+    float mv[kMcWarps][R][kMvStride];      // view*model + scale per record of the round's tiles
+    uint32_t words[kMcWarps][R * 4];       // the tiles' record words
+    uint32_t mask[kMcWarps][R];            // draw masks being accumulated
+    uint32_t queue[kMcWarps * R * 32];     // candidates: warp << 8 | record << 5 | lane
+    uint32_t qcount[2];                    // queue fill, double-buffered by round parity
 };
 
 // Loads of one tile that depend only on its record words, kept in registers until the tile's turn comes:
@@ -706,105 +737,153 @@ __device__ __forceinline__ void packed_finish_model_view(const PackedPrefetch<R>
     __syncwarp();
 }
 
+#ifndef ORBIT_PACKED_MIN_CTAS
+#define ORBIT_PACKED_MIN_CTAS 4
+#endif
 template <int R>
-__global__ void __launch_bounds__(kMcThreads, 4) meshlet_test_packed_kernel(const __grid_constant__ MeshletCullParams p) {
-    __shared__ PackedSmem<R> s_all[kMcWarps];
+__global__ void __launch_bounds__(kMcThreads, ORBIT_PACKED_MIN_CTAS) meshlet_test_packed_kernel(const __grid_constant__ MeshletCullParams p) {
+    static_assert(R == 2 || R == 4 || R == 8, "records per warp tile");
+    __shared__ PackedCtaSmem<R> sm;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    PackedSmem<R>& ws = s_all[warp];
     const OrbitCullInfo& ci = p.cull;
     pdl_wait();
-    const uint32_t w_stride = gridDim.x * kMcWarps;
-    const uint32_t tile0 = blockIdx.x * kMcWarps + warp;
-    // Latency-bound kernel (a warp sees one or two tiles, each a chain of dependent loads: record words -> visibility
-    // word + model matrices -> meshlets -> material): the chain of tile t+1 is started before tile t is tested, and
-    // the first two tiles' record words are requested before the record count is known (bounded by the buffer's
-    // capacity, masked afterwards).
-    auto spec_words = [&](uint32_t tile) -> uint32_t {
-        const uint64_t rec = (uint64_t)tile * R + (lane >> 2);
-        return (lane < 4u * R && rec < p.capacity_records) ? __ldcg(p.dispatch_words + 3u + (size_t)tile * R * 4u + lane) : 0u;
+    ORBIT_TRACE_STAMP(p.scan.trace, 2, 0);
+    if (threadIdx.x < 2u) sm.qcount[threadIdx.x] = 0u;
+    // tile of (round, warp): CTAs interleave at tile granularity, a CTA's own tiles lie gridDim.x apart
+    const uint64_t round_stride = (uint64_t)kMcWarps * gridDim.x;
+    const uint64_t tile_first = (uint64_t)warp * gridDim.x + blockIdx.x;
+    auto spec_words = [&](uint64_t tile, uint64_t bound) -> uint32_t {
+        const uint64_t rec = tile * R + (lane >> 2);
+        return (lane < 4u * R && rec < bound) ? __ldcg(p.dispatch_words + 3u + (size_t)tile * R * 4u + lane) : 0u;
     };
-    uint32_t cur_word = spec_words(tile0), next_word = spec_words(tile0 + w_stride);
+    uint32_t cur_word = spec_words(tile_first, p.capacity_records), next_word = spec_words(tile_first + round_stride, p.capacity_records);
     uint32_t nrec = __ldcg(p.dispatch_words);
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
+    ORBIT_TRACE_STAMP_AFTER(p.scan.trace, 2, 1, nrec + cur_word);
     const uint32_t chunk_rec = 1u << chunk_shift_of(nrec);
-    const uint32_t half = __ldcg(p.chunk_parity) & 1u;   // see meshlet_test_stream_kernel
+    const uint32_t half = __ldcg(p.chunk_parity) & 1u;   // see meshlet_test_direct_kernel
     if (blockIdx.x == 0 && threadIdx.x == 0) p.chunk_parity[1] = half;
     uint32_t* const chunk_counts = p.chunk_counts + half * kMaxChunks;
     uint32_t* const draw_total = p.draw_total + half;
-    const uint32_t tiles_total = (nrec + R - 1) / R;
-    if (!(lane < 4u * R && (uint64_t)tile0 * R + (lane >> 2) < nrec)) cur_word = 0u;
-    if (!(lane < 4u * R && (uint64_t)(tile0 + w_stride) * R + (lane >> 2) < nrec)) next_word = 0u;
+    const uint64_t tiles_total = ((uint64_t)nrec + R - 1) / R;
+    if (!(lane < 4u * R && tile_first * R + (lane >> 2) < nrec)) cur_word = 0u;
+    if (!(lane < 4u * R && (tile_first + round_stride) * R + (lane >> 2) < nrec)) next_word = 0u;
     const uint32_t vrow_i = lane & 3u;
     const float v0 = ci.view_matrix.m[0][vrow_i], v1 = ci.view_matrix.m[1][vrow_i];
     const float v2 = ci.view_matrix.m[2][vrow_i], v3 = ci.view_matrix.m[3][vrow_i];
-    uint32_t warp_total = 0u, buf = 0u;
+    uint32_t warp_total = 0u;
     PackedPrefetch<R> cur = packed_issue_loads<R>(p, cur_word, lane);
-    // A tile none of whose records had a visible meshlet last frame (most of the list: occluded entities) needs neither
-    // matrices nor packing — that arithmetic, not memory, was what the kernel spent its issue slots on.
-    if (tile0 < tiles_total && __ballot_sync(0xFFFFFFFFu, cur.vw != 0u) != 0u)
-        packed_finish_model_view<R>(cur, &ws.mv[0][0][0], lane, v0, v1, v2, v3);
-    for (uint32_t tile = tile0; tile < tiles_total; tile += w_stride) {
-        const uint32_t rec0 = tile * R;
+    __syncthreads();                                                        // qcount zeroed
+    for (uint32_t round = 0; (uint64_t)round * round_stride + blockIdx.x < tiles_total; ++round) {   // CTA-uniform
+        const uint64_t tile = tile_first + (uint64_t)round * round_stride;
+        const uint32_t rec0 = (uint32_t)min(tile * R, (uint64_t)0xFFFFFFFFu);
         const uint32_t my_word = cur_word;
-        float* const mv_base = &ws.mv[buf][0][0];
         const uint32_t vw = cur.vw;
-        // ---- start the next tile's chain (its words arrived while the previous tile was tested)
-        const bool has_next = tile + w_stride < tiles_total;
-        PackedPrefetch<R> nxt = packed_issue_loads<R>(p, next_word, lane);
-        uint32_t next2_word = 0u;
-        {
-            const uint32_t t2 = tile + 2u * w_stride;
-            if (t2 < tiles_total && lane < 4u * R && t2 * R + (lane >> 2) < nrec) next2_word = __ldcg(p.dispatch_words + 3u + (size_t)t2 * R * 4u + lane);
-        }
-        // ---- this tile: pack the lanes whose visibility bit is set, test them
-        uint32_t my_draw_mask = 0u;
-        if (__ballot_sync(0xFFFFFFFFu, vw != 0u) != 0u) {      // warp-uniform
+        const uint32_t qpar = round & 1u;
+        // ---- A. this warp's tile: record words and matrices into shared memory, candidates into the CTA's queue
+        if (lane < 4u * R) sm.words[warp][lane] = my_word;
+        if (lane < (uint32_t)R) sm.mask[warp][lane] = 0u;
+        const uint32_t any_vw = __ballot_sync(0xFFFFFFFFu, vw != 0u);
+#ifdef ORBIT_TRACE
+        if (round == 0u) ORBIT_TRACE_STAMP_AFTER(p.scan.trace, 2, 5, any_vw);
+#endif
+        if (any_vw != 0u) {                                                 // warp-uniform: tiles without candidates skip the matrix math
+            packed_finish_model_view<R>(cur, &sm.mv[warp][0][0], lane, v0, v1, v2, v3);
             uint32_t n_items = 0u;
+#pragma unroll
+            for (int r = 0; r < R; ++r) n_items += __popc(__shfl_sync(0xFFFFFFFFu, vw, r));
+            uint32_t base = 0u;
+            if (lane == 0u) base = atomicAdd(&sm.qcount[qpar], n_items);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const uint32_t m = __shfl_sync(0xFFFFFFFFu, vw, r);
-                if ((m >> lane) & 1u) ws.items[n_items + __popc(m & lt)] = ((uint32_t)r << 5) | lane;
-                n_items += __popc(m);
+                if ((m >> lane) & 1u) sm.queue[base + __popc(m & lt)] = (warp << 8) | ((uint32_t)r << 5) | lane;
+                base += __popc(m);
             }
-            if (lane < (uint32_t)R) ws.mask[lane] = 0u;
-            __syncwarp();
-            for (uint32_t k = 0; k * 32u < n_items; ++k) {
-                const uint32_t i = k * 32u + lane;
-                const uint32_t id = i < n_items ? ws.items[i] : 0u;
-                const uint32_t moff = __shfl_sync(0xFFFFFFFFu, my_word, (id >> 5) * 4u + 1u);
-                if (i < n_items) {
-                    const uint32_t r = id >> 5, j = id & 31u;
-                    const uint4* m = p.meshlets + 2u * ((size_t)moff + j);
-                    const uint4 a = __ldg(m), b = __ldg(m + 1);
-                    const float* mvr = mv_base + r * kMvStride;
-                    const ItemTest t = test_item<-1>(ci, *reinterpret_cast<const float4*>(mvr), *reinterpret_cast<const float4*>(mvr + 4),
-                                                     *reinterpret_cast<const float4*>(mvr + 8), *reinterpret_cast<const float4*>(mvr + 12), mvr[16],
-                                                     __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w), b.x);
-                    if (draw_rule(ci, p, t.pre_visible, true, false, b.w)) atomicOr(&ws.mask[r], 1u << j);
+        }
+        // ---- start the next round's chain (its record words arrived while the previous round was tested)
+        PackedPrefetch<R> nxt = packed_issue_loads<R>(p, next_word, lane);
+        uint32_t next2_word = 0u;
+        {
+            const uint64_t t2 = tile + 2u * round_stride;
+            if (t2 < tiles_total && lane < 4u * R && t2 * R + (lane >> 2) < nrec) next2_word = __ldcg(p.dispatch_words + 3u + (size_t)t2 * R * 4u + lane);
+        }
+        __syncthreads();
+        // ---- C. all warps drain the queue: batches warp, warp + 8, ...; two batches per step
+        const uint32_t total = sm.qcount[qpar];
+        if (threadIdx.x == 0) sm.qcount[qpar ^ 1u] = 0u;                    // the next round's counter (last read two barriers ago)
+#ifdef ORBIT_TRACE
+        if (round == 0u) { ORBIT_TRACE_STAMP(p.scan.trace, 2, 6); ORBIT_TRACE_VALUE(p.scan.trace, 8, total); }
+#endif
+        for (uint32_t b0 = warp * 32u; b0 < total; b0 += 2u * kMcWarps * 32u) {
+            uint32_t id[2]; uint4 ma[2], mb[2]; bool live[2]; uint32_t alpha[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t i = b0 + (uint32_t)u * kMcWarps * 32u + lane;
+                live[u] = i < total;
+                id[u] = sm.queue[live[u] ? i : 0u];                         // dead lanes redo candidate 0 and drop the result
+                const uint32_t moff = sm.words[id[u] >> 8][((id[u] >> 5) & 7u) * 4u + 1u];
+                const uint4* m = p.meshlets + 2u * ((size_t)moff + (id[u] & 31u));
+                ma[u] = __ldg(m); mb[u] = __ldg(m + 1);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                alpha[u] = __ldg(reinterpret_cast<const uint32_t*>(p.materials + (size_t)(mb[u].w & 0xFFFFu) * ORBIT_MATERIAL_STRIDE_BYTES + ORBIT_MATERIAL_ALPHA_MODE_OFFSET));
+#ifdef ORBIT_TRACE
+            if (round == 0u && b0 == warp * 32u) { ORBIT_TRACE_STAMP_AFTER(p.scan.trace, 2, 7, ma[0].x + ma[1].x); ORBIT_TRACE_STAMP_AFTER(p.scan.trace, 2, 9, alpha[0] + alpha[1]); }
+#endif
+            bool pre[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float* mvr = &sm.mv[id[u] >> 8][(id[u] >> 5) & 7u][0];
+                const ItemTest t = test_item<-1>(ci, *reinterpret_cast<const float4*>(mvr), *reinterpret_cast<const float4*>(mvr + 4),
+                                                 *reinterpret_cast<const float4*>(mvr + 8), *reinterpret_cast<const float4*>(mvr + 12), mvr[16],
+                                                 __uint_as_float(ma[u].x), __uint_as_float(ma[u].y), __uint_as_float(ma[u].z), __uint_as_float(ma[u].w), mb[u].x);
+                pre[u] = t.pre_visible;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                // should_draw = visible && alpha passes the filter (meshlet_cull.comp:207); pass 1: visible_last_frame holds for every candidate
+                if (live[u] && pre[u] && (shl1(alpha[u]) & ci.alpha_mode_flags) != 0u) {
+                    const uint32_t w = id[u] >> 8, r = (id[u] >> 5) & 7u, j = id[u] & 31u;
+                    atomicOr(&sm.mask[w][r], 1u << j);
+                    // the command words of a survivor travel to the emit kernel through an L2-resident side array
+                    const uint64_t rec = ((uint64_t)w * gridDim.x + blockIdx.x + (uint64_t)round * round_stride) * R + r;
+                    if (p.cmd_side != nullptr) p.cmd_side[rec * 32u + j] = make_uint4(mb[u].y, mb[u].z, mb[u].w, sm.words[w][r * 4u]);
                 }
             }
-            __syncwarp();
-            if (lane < (uint32_t)R) my_draw_mask = ws.mask[lane];
-            __syncwarp();
         }
+#ifdef ORBIT_TRACE
+        if (round == 0u) ORBIT_TRACE_STAMP(p.scan.trace, 2, 10);
+#endif
+        __syncthreads();
+#ifdef ORBIT_TRACE
+        if (round == 0u) ORBIT_TRACE_STAMP(p.scan.trace, 2, 11);
+#endif
+        // ---- E. this warp's tile: draw masks out, survivors counted per chunk
+        uint32_t my_draw_mask = 0u;
+        if (lane < (uint32_t)R) my_draw_mask = sm.mask[warp][lane];
         {
             const uint32_t ent = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 0u) & 31u);
             const uint32_t mof = __shfl_sync(0xFFFFFFFFu, my_word, (lane * 4u + 1u) & 31u);
-            if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(my_draw_mask, ent, mof, 0u);
+            if (lane < (uint32_t)R && (uint64_t)rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(my_draw_mask, ent, mof, p.cmd_side != nullptr ? 0u : 1u);
         }
         const uint32_t tile_total = __reduce_add_sync(0xFFFFFFFFu, __popc(my_draw_mask));
         if (lane == 0u && tile_total != 0u) atomicAdd(chunk_counts + rec0 / chunk_rec, tile_total);
         warp_total += tile_total;
-        // ---- the next tile's matrices into the other buffer; rotate
-        if (has_next && __ballot_sync(0xFFFFFFFFu, nxt.vw != 0u) != 0u) packed_finish_model_view<R>(nxt, &ws.mv[buf ^ 1u][0][0], lane, v0, v1, v2, v3);
-        buf ^= 1u;
         cur = nxt;
         cur_word = next_word;
         next_word = next2_word;
     }
+    ORBIT_TRACE_STAMP(p.scan.trace, 2, 3);
     pdl_launch_dependents();
     if (lane == 0u && warp_total != 0u) atomicAdd(draw_total, warp_total);
+#ifdef ORBIT_TRACE
+    __syncthreads();
+    ORBIT_TRACE_STAMP(p.scan.trace, 2, 4);
+#endif
 }
 
 // Position of the n-th (0-based) set bit of m (n < popc(m)): branch-free binary search on popcounts of halves.
@@ -841,6 +920,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const bool want_payload = p.task_payloads != nullptr;
     pdl_wait();
+    ORBIT_TRACE_STAMP(p.trace_emit, 3, 0);
     // both halves of the chunk counts are requested before the parity is known: one round trip instead of two
     uint32_t v0[8], v1[8];
     {
@@ -857,6 +937,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
     uint32_t nrec = __ldcg(p.dispatch_words);
     const uint32_t parity = __ldcg(p.chunk_parity + 1) & 1u;   // word B: the half the test kernel of this call used
     const uint32_t grand_total = parity ? t1 : t0;
+    ORBIT_TRACE_STAMP_AFTER(p.trace_emit, 3, 1, grand_total + v0[0] + v1[7]);
     if ((uint64_t)nrec > p.capacity_records) nrec = (uint32_t)p.capacity_records;
     // zero the other parity's counters for the next call (it runs after this kernel in stream order)
     for (uint32_t i = blockIdx.x * blockDim.x + tid; i < kMaxChunks; i += gridDim.x * blockDim.x) p.chunk_counts[(parity ^ 1u) * kMaxChunks + i] = 0u;
@@ -884,6 +965,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
         for (int k = 0; k < 8; ++k) { run += v[k]; s_prefix[tid * 8u + (uint32_t)k] = run; }
         __syncthreads();
         const uint32_t total = s_prefix[kMaxChunks - 1u];
+        ORBIT_TRACE_STAMP(p.trace_emit, 3, 2 + 0 * (total & 1u));
         if (blockIdx.x == 0 && tid == 0) {
             p.draw_words[0] = total;   // exact count even when it exceeds capacity
             if ((uint64_t)total > p.capacity_draws) *p.overflow_flag = 1u;
@@ -899,6 +981,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
                 const uint32_t mid = (lo + hi) >> 1;
                 if (s_prefix[mid] > o_begin) hi = mid; else lo = mid + 1u;
             }
+            ORBIT_TRACE_STAMP_AFTER(p.trace_emit, 3, 4, lo);
             uint32_t running = lo ? s_prefix[lo - 1u] : 0u;               // outputs before record `rec`
             uint32_t rec = lo * chunk_rec;
             // At a chunk boundary the prefix tells whether the chunk holds any survivor: empty chunks are stepped over
@@ -919,49 +1002,80 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
                 const uint32_t my = r + lane;
                 return my < nrec ? __ldcg(p.draw_masks + my) : make_uint4(0u, 0u, 0u, 0u);
             };
-            uint4 e = load_masks(rec);
-            while (running < o_end && rec < nrec) {
-                const uint32_t rec_next = advance();
-                const uint4 e_next = load_masks(rec_next);                // speculative: unused when this group ends the share
-                const uint32_t dm = e.x, entity = e.y, moff = e.z;
-                const uint32_t pc = __popc(dm);
-                uint32_t inc = pc;
+            // Four groups of 32 records in flight: a warp whose share of the outputs lies in a sparsely surviving stretch
+            // walks many groups for its ~30 outputs, one dependent L2 round trip each (that tail was half of this kernel's
+            // time on the C2 early pass; profiles/r2_frame_timeline.txt).
+            constexpr int kDepth = 4;
+            uint32_t recs[kDepth]; uint4 es[kDepth];
+            recs[0] = rec; es[0] = load_masks(rec);
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                    if (lane >= (uint32_t)d) inc += t;
-                }
-                const uint32_t step_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-                if (running + step_total > o_begin) {
-                    __syncwarp();
-                    sr[lane] = inc; sr[32 + lane] = dm; sr[64 + lane] = entity; sr[96 + lane] = moff;
-                    __syncwarp();
-                    const uint32_t l0 = o_begin > running ? o_begin - running : 0u;            // first local output of mine
-                    const uint32_t l1 = min(step_total, o_end - running);                      // one past my last local output
-                    for (uint32_t ol = l0 + lane; ol < l1; ol += 32u) {
-                        uint32_t a = 0u, b = 31u;
+            for (int u = 1; u < kDepth; ++u) { recs[u] = advance(); es[u] = load_masks(recs[u]); }
+#ifdef ORBIT_TRACE
+            bool trace_first_group = false; uint32_t trace_groups = 0u;
+#endif
+            bool more = true;
+            while (more) {
 #pragma unroll
-                        for (int it = 0; it < 5; ++it) {
-                            const uint32_t mid = (a + b) >> 1;
-                            if (sr[mid] > ol) b = mid; else a = mid + 1u;
-                        }
-                        const uint32_t r = a;
-                        const uint32_t excl = r ? sr[r - 1u] : 0u;
-                        const uint32_t j = select_set_bit(sr[32 + r], ol - excl);   // (ol-excl)-th survivor of the record
-                        const uint32_t midx = sr[96 + r] + j;
-                        const uint4 mb = __ldg(p.meshlets + 2u * (size_t)midx + 1);
-                        const uint64_t idx = (uint64_t)running + ol;
-                        if (idx < p.capacity_draws) store_command(p.draw_words + 1u + idx * 7u, mb.y, mb.z, mb.w, sr[64 + r], midx);
+                for (int u = 0; u < kDepth; ++u) {
+                    if (!(running < o_end && recs[u] < nrec)) { more = false; break; }
+                    const uint4 e = es[u];
+                    const uint32_t group_rec = recs[u];
+                    recs[u] = advance();
+                    es[u] = load_masks(recs[u]);                             // speculative: unused when the share ends first
+                    const uint32_t dm = e.x, entity = e.y, moff = e.z;
+                    const uint32_t pc = __popc(dm);
+                    uint32_t inc = pc;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                        if (lane >= (uint32_t)d) inc += t;
                     }
+                    const uint32_t step_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+#ifdef ORBIT_TRACE
+                    if (!trace_first_group) { trace_first_group = true; ORBIT_TRACE_STAMP_AFTER(p.trace_emit, 3, 5, step_total); }
+                    ++trace_groups;
+#endif
+                    if (running + step_total > o_begin) {
+                        __syncwarp();
+                        sr[lane] = inc; sr[32 + lane] = dm; sr[64 + lane] = entity; sr[96 + lane] = moff | (e.w << 31);
+                        __syncwarp();
+                        const uint32_t l0 = o_begin > running ? o_begin - running : 0u;            // first local output of mine
+                        const uint32_t l1 = min(step_total, o_end - running);                      // one past my last local output
+                        for (uint32_t ol = l0 + lane; ol < l1; ol += 32u) {
+                            uint32_t a = 0u, b = 31u;
+#pragma unroll
+                            for (int it = 0; it < 5; ++it) {
+                                const uint32_t mid = (a + b) >> 1;
+                                if (sr[mid] > ol) b = mid; else a = mid + 1u;
+                            }
+                            const uint32_t r = a;
+                            const uint32_t excl = r ? sr[r - 1u] : 0u;
+                            const uint32_t j = select_set_bit(sr[32 + r], ol - excl);   // (ol-excl)-th survivor of the record
+                            const uint32_t mo = sr[96 + r];
+                            const uint32_t midx = (mo & 0x7FFFFFFFu) + j;
+                            // command words: from the side array the test kernel filled (x,y,z = vertex_offset, data_offset, packed
+                            // counts), or — pass 2, whose candidates do not carry them — from the meshlet itself
+                            uint4 cw;
+                            if (mo >> 31) { const uint4 mb = __ldg(p.meshlets + 2u * (size_t)midx + 1); cw = make_uint4(mb.y, mb.z, mb.w, 0u); }
+                            else cw = __ldcg(p.cmd_side + (size_t)(group_rec + r) * 32u + j);
+                            const uint64_t idx = (uint64_t)running + ol;
+                            if (idx < p.capacity_draws) store_command(p.draw_words + 1u + idx * 7u, cw.x, cw.y, cw.z, sr[64 + r], midx);
+                        }
+                    }
+                    running += step_total;
                 }
-                running += step_total;
-                rec = rec_next;
-                e = e_next;
             }
+            ORBIT_TRACE_STAMP(p.trace_emit, 3, 6);
+            ORBIT_TRACE_VALUE(p.trace_emit, 8, trace_groups);
+            ORBIT_TRACE_VALUE(p.trace_emit, 9, o_end - o_begin);
         }
     } else if (blockIdx.x == 0 && tid == 0) {
         p.draw_words[0] = 0u;   // nothing survived (the steady-state late pass)
     }
+#ifdef ORBIT_TRACE
+    __syncthreads();
+    ORBIT_TRACE_STAMP(p.trace_emit, 3, 3);
+#endif
     pdl_launch_dependents();   // after the emission: an early trigger measured 20% slower when there is a lot to emit
     if (want_payload) {
         // MeshTaskPayload + emitted task count per record (indices ascending by lane — the task shader's atomicAdd
@@ -994,6 +1108,69 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Multi-GPU (meshlet ranges of one view): a rank that only TESTS its records ships the 16-byte
+// {draw mask, entity, meshlet offset, 1} entries instead of 28-byte draw commands (C3: 28 MB instead of 229 MB to the
+// rank that submits the draws); that rank lays the ranks' entries end to end — rank-major = canonical record order —
+// recounts the survivors per chunk and runs the ordinary emit kernel over the combined list.
+//
+// Copies this rank's entries [0, own count) to dst[first ...), first = sum of the lower ranks' (clamped) record counts.
+__global__ void __launch_bounds__(256) record_masks_scatter_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                                   const uint32_t* __restrict__ rank_counts, uint32_t rank, uint32_t world,
+                                                                   uint64_t src_capacity, uint64_t dst_capacity) {
+    uint64_t first = 0u;
+    for (uint32_t r = 0; r < rank; ++r) first += min((uint64_t)__ldcg(rank_counts + r), src_capacity);
+    uint64_t n = min((uint64_t)__ldcg(rank_counts + rank), src_capacity);
+    if (first >= dst_capacity) n = 0u; else if (first + n > dst_capacity) n = dst_capacity - first;
+    const uint64_t gsize = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3u * gsize < n; i += 4u * gsize) {                          // four independent 16-byte stores in flight (NVLink)
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldcg(src + i + (uint64_t)k * gsize);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) __stcg(dst + first + i + (uint64_t)k * gsize, v[k]);
+    }
+    for (; i < n; i += gsize) __stcg(dst + first + i, __ldcg(src + i));
+}
+
+// Survivors per chunk of the combined list (same double-buffered scratch protocol as the test kernels, so the emit kernel
+// that follows cannot tell the difference) and the combined record count as a dispatch-buffer header for it.
+__global__ void __launch_bounds__(256) record_masks_recount_kernel(const __grid_constant__ MeshletCullParams p, const uint32_t* __restrict__ rank_counts,
+                                                                   uint32_t world, uint64_t rank_capacity, uint32_t* __restrict__ header_out) {
+    uint64_t total = 0u;
+    for (uint32_t r = 0; r < world; ++r) total += min((uint64_t)__ldcg(rank_counts + r), rank_capacity);
+    const uint32_t nrec = (uint32_t)min(total, p.capacity_records);
+    const uint32_t chunk_shift = chunk_shift_of(nrec);
+    const uint32_t half = __ldcg(p.chunk_parity) & 1u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.chunk_parity[1] = half; header_out[0] = nrec; header_out[1] = 1u; header_out[2] = 1u; }
+    uint32_t* const chunk_counts = p.chunk_counts + half * kMaxChunks;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t mine = 0u;
+    // a warp covers 32 consecutive records = at most one chunk (chunks are >= 32 records and 32-aligned)
+    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < nrec; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = base + lane;
+        const uint32_t pc = r < nrec ? (uint32_t)__popc(__ldcg(reinterpret_cast<const uint32_t*>(p.draw_masks + r))) : 0u;
+        const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, pc);
+        if (lane == 0u && s != 0u) { atomicAdd(chunk_counts + (uint32_t)(base >> chunk_shift), s); mine += s; }
+    }
+    if (mine != 0u) atomicAdd(p.draw_total + half, mine);
+}
+
+cudaError_t launch_record_masks_scatter(const uint4* src, uint4* dst, const uint32_t* rank_counts, uint32_t rank, uint32_t world,
+                                        uint64_t src_capacity, uint64_t dst_capacity, int grid, cudaStream_t s) {
+    record_masks_scatter_kernel<<<grid, 256, 0, s>>>(src, dst, rank_counts, rank, world, src_capacity, dst_capacity);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_draws_from_masks(const MeshletCullParams& p, const uint32_t* rank_counts, uint32_t world, uint64_t rank_capacity,
+                                    uint32_t* header, int grid, int emit_grid, cudaStream_t s) {
+    record_masks_recount_kernel<<<grid, 256, 0, s>>>(p, rank_counts, world, rank_capacity, header);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_kernel(meshlet_emit_kernel, dim3(emit_grid), dim3(kEmitWarps * 32), 0, s, p);
+}
+
 // ---- launch plumbing ---------------------------------------------------------------------------------------
 struct TestVariant { bool packed; bool pass2; int proj; };
 static TestVariant variant_of(const OrbitCullInfo& ci) {
@@ -1009,6 +1186,10 @@ static TestVariant variant_of(const OrbitCullInfo& ci) {
 #define ORBIT_TILE_RECORDS 4
 #endif
 constexpr int kTileR = ORBIT_TILE_RECORDS;   // records per warp tile of the direct test kernel
+#ifndef ORBIT_PACKED_RECORDS
+#define ORBIT_PACKED_RECORDS 8
+#endif
+constexpr int kPackedR = ORBIT_PACKED_RECORDS;   // records per warp tile of the packed (pass 1) test kernel
 static constexpr size_t direct_smem_bytes() { return 128u + sizeof(WarpSmem<kTileR>) * kMcWarps; }
 
 template <bool kPass2, int kProj>
@@ -1036,8 +1217,8 @@ static cudaError_t launch_test(const MeshletCullParams& p, int grid, cudaStream_
     const TestVariant v = variant_of(p.cull);
     if (v.packed) {
         // the packed kernel fills its 32-lane test batches from a whole tile of 8 records (a 4-record tile's batch is 44 % full on C2)
-        if (occupancy) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_packed_kernel<8>, kMcThreads, 0); return cudaSuccess; }
-        return launch_kernel(meshlet_test_packed_kernel<8>, dim3(grid), dim3(kMcThreads), 0, stream, p);
+        if (occupancy) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_packed_kernel<kPackedR>, kMcThreads, 0); return cudaSuccess; }
+        return launch_kernel(meshlet_test_packed_kernel<kPackedR>, dim3(grid), dim3(kMcThreads), 0, stream, p);
     }
     if (v.pass2) {
         if (v.proj == 0) return launch_stream<true, 0>(p, grid, stream, occupancy);

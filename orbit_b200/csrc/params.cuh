@@ -31,7 +31,8 @@ struct MeshletCullParams {
     uint32_t* draw_words;             // MeshletDrawCommandBuffer as u32[]: count then 7 words per command
     uint32_t* task_payloads;          // nullable, 11 words per record
     uint32_t* overflow_flag;          // host-mapped status word
-    uint4* draw_masks;                // scratch: {draw mask, entity, meshlet offset, 0} per dispatch record (test -> emit kernel)
+    uint4* draw_masks;                // scratch: {draw mask, entity, meshlet offset, flag} per dispatch record (test -> emit kernel); flag 1 = no side entries
+    uint4* cmd_side;                  // scratch: {vertex_offset, data_offset, packed counts, entity} per (record, lane) of a survivor (test -> emit kernel)
     uint32_t* draw_total;             // scratch[2]: survivors counted by the test kernel, per parity (re-zeroed by the emit kernel)
     uint32_t* chunk_counts;           // scratch: 2 x 2048 per-chunk survivor counts (double-buffered by parity)
     uint32_t* chunk_parity;           // scratch[2]: word A (read by test, written by emit), word B (written by test, read by emit)
@@ -39,7 +40,8 @@ struct MeshletCullParams {
     uint64_t capacity_draws;
     float2 pk_one, pk_mone;           // (1, 1) and (-1, -1): operands of the packed add / subtract (see PkConsts in meshlet_cull.cu)
     float2 planes_t[6][4];            // cull planes paired for the packed test: [j][c] = (planes[2j][c], planes[2j+1][c]); an odd last plane is repeated
-    ScanState scan;
+    ScanState scan;                   // only .trace is used (development timeline of the test kernel)
+    unsigned long long* trace_emit;   // development timeline of the emit kernel
 };
 
 struct EntityCullParams {
@@ -77,6 +79,7 @@ struct HizBuildParams {
     uint32_t width, height, levels;
     uint32_t level_offset[ORBIT_HIZ_MAX_LEVELS];
     unsigned int* ticket;  // zero on entry, re-zeroed by the last CTA
+    unsigned long long* trace;
 };
 
 struct ClusterParams {
@@ -100,6 +103,11 @@ int meshlet_emit_max_ctas_per_sm();
 int meshlet_cull_max_ctas_per_sm(const MeshletCullParams&);
 int meshlet_cull_variant_index(const OrbitCullInfo&);
 cudaError_t meshlet_cull_configure_device();
+cudaError_t light_cluster_configure_device();
+cudaError_t launch_record_masks_scatter(const uint4* src, uint4* dst, const uint32_t* rank_counts, uint32_t rank, uint32_t world,
+                                        uint64_t src_capacity, uint64_t dst_capacity, int grid, cudaStream_t s);
+cudaError_t launch_draws_from_masks(const MeshletCullParams& p, const uint32_t* rank_counts, uint32_t world, uint64_t rank_capacity,
+                                    uint32_t* header, int grid, int emit_grid, cudaStream_t s);
 cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t);
 int entity_cull_max_ctas_per_sm();
 cudaError_t launch_hiz_build(const HizBuildParams&, cudaStream_t);
@@ -108,7 +116,7 @@ cudaError_t launch_mark_active(const ClusterParams&, int grid, cudaStream_t);
 cudaError_t launch_compact_clusters(const ClusterParams&, cudaStream_t);
 cudaError_t launch_light_view(const ClusterParams&, cudaStream_t);
 cudaError_t launch_light_culling(const ClusterParams&, int grid, cudaStream_t);
-cudaError_t launch_draws_scatter(const uint32_t* src, uint32_t* dst, uint32_t dst_first, uint32_t total_count,
+cudaError_t launch_draws_scatter(const uint32_t* src, uint64_t src_capacity, uint32_t* dst, uint32_t dst_first, uint32_t total_count,
                                  uint64_t dst_capacity, int grid, cudaStream_t s, const uint32_t* rank_counts, uint32_t rank, uint32_t world);
 
 }  // namespace orbit

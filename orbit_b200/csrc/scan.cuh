@@ -19,7 +19,31 @@ namespace orbit {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Development aid (never in the shipped library): -DORBIT_TRACE makes thread 0 of every CTA write %globaltimer stamps at
+// named points of a kernel into a buffer owned by the context (orbit_debug_trace): every LAUNCH gets its own block of
+// 1024 CTAs x 16 slots (16 blocks, handed out round robin by the host); slot 15 of CTA 0 holds the kernel id.
+// tools/trace_frame.py turns the blocks into a timeline of the frame. Without the flag the macro expands to nothing.
+#ifdef ORBIT_TRACE
+__device__ __forceinline__ unsigned long long trace_time() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ORBIT_TRACE_STAMP(trace, kernel_id, slot) \
+    do { if ((trace) != nullptr && threadIdx.x == 0) { \
+        (trace)[(size_t)min(blockIdx.x, 1023u) * 16u + (slot)] = orbit::trace_time(); \
+        if (blockIdx.x == 0) (trace)[15] = 1000ull + (kernel_id); } } while (0)
+// stamp taken only once the 32-bit value `dep` has arrived (the asm reads it, so the warp stalls on its scoreboard first)
+__device__ __forceinline__ unsigned long long trace_time_after(unsigned int dep) {
+    unsigned long long t; asm volatile("{ .reg .b32 tmp; mov.b32 tmp, %1; mov.u64 %0, %%globaltimer; }" : "=l"(t) : "r"(dep)); return t; }
+#define ORBIT_TRACE_STAMP_AFTER(trace, kernel_id, slot, dep) \
+    do { if ((trace) != nullptr && threadIdx.x == 0) (trace)[(size_t)min(blockIdx.x, 1023u) * 16u + (slot)] = orbit::trace_time_after((unsigned int)(dep)); } while (0)
+#define ORBIT_TRACE_VALUE(trace, slot, value) \
+    do { if ((trace) != nullptr && threadIdx.x == 0) (trace)[(size_t)min(blockIdx.x, 1023u) * 16u + (slot)] = (unsigned long long)(value); } while (0)
+#else
+#define ORBIT_TRACE_STAMP(trace, kernel_id, slot) do { } while (0)
+#define ORBIT_TRACE_STAMP_AFTER(trace, kernel_id, slot, dep) do { } while (0)
+#define ORBIT_TRACE_VALUE(trace, slot, value) do { } while (0)
+#endif
+
 struct ScanState {
+    unsigned long long* trace;   // development timeline buffer (nullptr unless built with -DORBIT_TRACE)
     unsigned long long* status;  // one descriptor per tile
     unsigned int* ticket;        // next tile to hand out
     unsigned int* done;          // CTAs that finished (the last one resets ticket/done for the next launch)
@@ -97,7 +121,15 @@ __device__ __forceinline__ unsigned int gather_lower_aggregates(const ScanState&
             w[k] = 0ull;
             if (i < n) { w[k] = peek(st.status + i); pending |= 1u << k; }
         }
+#ifdef ORBIT_TRACE
+        unsigned int trace_iters = 0u;
+#endif
         while (pending) {
+#ifdef ORBIT_TRACE
+            if (trace_iters == 0u) ORBIT_TRACE_STAMP(st.trace, 0, 9);
+            ++trace_iters;
+            ORBIT_TRACE_VALUE(st.trace, 8, trace_iters);
+#endif
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if ((pending >> k) & 1u) {

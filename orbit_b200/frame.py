@@ -175,17 +175,49 @@ class PreparedFrame:
         if rc:
             raise RuntimeError("orbit_meshlet_cull: %d" % rc)
 
+    def meshlet_test(self, late, record_masks, s=None):
+        """The test half of the meshlet stage (orbit_meshlet_test): visibility words + one 16-byte entry per dispatch record into
+        `record_masks`; used by the sharded view, whose draw commands are emitted on the rank that submits them."""
+        C, lib, p = self._C, self._lib, self._ptr
+        s = s or self._stream()
+        g, sb, disp = (self.g_late, self.sb_late, self.late_dispatch) if late else (self.g_early, self.sb_early, self.early_dispatch)
+        rc = lib.orbit_meshlet_test(self.context._h, C.byref(g), C.byref(sb), self.vstate.depth_pyramid._h if late else None,
+                                    p(disp), self.rcap, p(record_masks), s)
+        if rc:
+            raise RuntimeError("orbit_meshlet_test: %d" % rc)
+
     def hiz(self, s=None):
         s = s or self._stream()
         rc = self._lib.orbit_hiz_build(self.context._h, self.vstate.depth_pyramid._h, self._ptr(self.depth), self._hw[0], self._hw[1], s)
         if rc:
             raise RuntimeError("orbit_hiz_build: %d" % rc)
 
-    def launch(self):
+    def launch(self, overlap_main_entity=False):
+        """The frame's stage calls in dependency order. `overlap_main_entity`: the MAIN pass's entity stage depends only on the
+        entity visibility bits the LATE entity stage wrote, not on the late MESHLET stage, so it may be forked onto a side stream
+        beside the late meshlet test (the entity and meshlet stages use disjoint context scratch: orbit_cuda.h, "Threading").
+        Measured on C2 (profiles/r2_frame_timeline.txt): the entity kernel is hidden, but the late test kernel — persistent CTAs
+        with a static tile split — ends 7 us later when 40 SMs start a third of their CTAs late, so the frame gains nothing
+        (104.5 vs 104.2 us); off by default, kept because it is bit-identical and pays off when the late pass is small."""
         s = self._stream()
-        self.entity(False, s); self.meshlet(False, s); self.hiz(s); self.entity(True, s); self.meshlet(True, s)
-        if self.main_pass:
-            self.entity("main", s); self.meshlet("main", s)
+        self.entity(False, s); self.meshlet(False, s); self.hiz(s); self.entity(True, s)
+        if not self.main_pass:
+            self.meshlet(True, s)
+            return
+        if not overlap_main_entity:
+            self.meshlet(True, s); self.entity("main", s); self.meshlet("main", s)
+            return
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.context.device, priority=-1)   # high priority: its 40 CTAs must get their SM
+            # slots before the persistent CTAs of the late meshlet test fill every SM (kernel-node priority is captured with the stream's)
+        fork = torch.cuda.Event(); fork.record(main)
+        self._side.wait_event(fork)
+        self.entity("main", self._C.c_void_p(self._side.cuda_stream))
+        join = torch.cuda.Event(); join.record(self._side)
+        self.meshlet(True, s)
+        main.wait_event(join)
+        self.meshlet("main", s)
 
     def capture(self):
         self.launch()  # warm: scratch growth / occupancy queries must not happen during capture

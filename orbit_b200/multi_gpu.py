@@ -59,7 +59,8 @@ def exchange_survivors(local_draw_buffer: torch.Tensor, out_buffer: torch.Tensor
         return local_draw_buffer[:4 + DRAW_BYTES * n], [n]
     counts = torch.zeros(world, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(counts, count, group=group)
-    counts_h = [int(v) for v in counts.cpu().tolist()]
+    cap = (local_draw_buffer.numel() - 4) // DRAW_BYTES
+    counts_h = [min(int(v), cap) for v in counts.cpu().tolist()]      # an overflowed rank holds only `capacity` commands (equal capacities)
     total, mx = sum(counts_h), max(counts_h)
     rank = dist.get_rank(group)
     # NCCL has no all-gather-v: pad every rank's list to the longest one
@@ -117,14 +118,14 @@ class PeerExchange:
         whose draws are submitted by one GPU needs; each rank then stores its commands once instead of world times."""
         C = self.C
         dist.all_gather_into_tensor(self.counts, local_draw_buffer[:4].view(torch.int32), group=self.group)
-        counts = [int(v) for v in self.counts.cpu().tolist()]
+        counts = [min(int(v), self.capacity) for v in self.counts.cpu().tolist()]     # an overflowed rank stored only `capacity` commands
         total, first = sum(counts), sum(counts[:self.rank])
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for k in range(self.world):
             r = (self.rank + k) % self.world       # staggered destinations: no rank is everybody's first target
             if root is not None and r != root:
                 continue
-            rc = self.lib.orbit_draws_scatter(self.context._h, C.c_void_p(local_draw_buffer.data_ptr()), C.c_void_p(self.peer_ptrs[r]),
+            rc = self.lib.orbit_draws_scatter(self.context._h, C.c_void_p(local_draw_buffer.data_ptr()), self.capacity, C.c_void_p(self.peer_ptrs[r]),
                                               first, total, self.capacity, stream)
             if rc:
                 raise RuntimeError("orbit_draws_scatter: %d" % rc)
@@ -149,7 +150,7 @@ class PeerExchange:
             r = (self.rank + k) % self.world
             if root is not None and r != root:
                 continue
-            rc = self.lib.orbit_draws_scatter_ranked(self.context._h, C.c_void_p(local_draw_buffer.data_ptr()), C.c_void_p(self.peer_ptrs[r]),
+            rc = self.lib.orbit_draws_scatter_ranked(self.context._h, C.c_void_p(local_draw_buffer.data_ptr()), self.capacity, C.c_void_p(self.peer_ptrs[r]),
                                                      C.c_void_p(self.counts.data_ptr()), self.rank, self.world, self.capacity, stream)
             if rc:
                 raise RuntimeError("orbit_draws_scatter_ranked: %d" % rc)
@@ -175,6 +176,68 @@ class PeerExchange:
         for r, q in enumerate(self.peer_ptrs):
             if r != self.rank:
                 self.lib.orbit_peer_close(self.context._h, self.C.c_void_p(q))
+        self.lib.orbit_peer_free(self.context._h, self.C.c_void_p(self.local_ptr))
+
+
+class MaskExchange:
+    """Survivor exchange of a sharded view in its compact form: every rank ships one 16-byte entry per dispatch record
+    ({draw mask, entity, meshlet offset, 1}, written by orbit_meshlet_test) to the ROOT rank — the GPU that submits the draws —
+    by NVLink peer stores at the record offset of its range (rank-major = canonical record order); the root recounts and
+    emits the 28-byte commands itself (orbit_draws_from_masks). C3: 28 MB cross the switch instead of 229 MB, and the
+    emission (a local HBM-bound kernel) no longer waits for a single GPU's NVLink ingress. Device-side counts throughout:
+    the all-gathered dispatch headers are the only collective besides the closing 4-byte fence."""
+
+    def __init__(self, context, capacity_records_rank, capacity_records_total, root=0, group=None):
+        import ctypes as C
+        from . import _lib
+        self.C, self.lib, self.context, self.group, self.root = C, _lib.lib(), context, group, root
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        cap = torch.tensor([int(capacity_records_rank)], dtype=torch.int64, device=context.device)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)          # one capacity for every rank: counts are clamped to it
+        self.rank_capacity = int(cap.item())
+        self.total_capacity = int(capacity_records_total)
+        self.local_masks = torch.zeros(16 * max(self.rank_capacity, 1), dtype=torch.uint8, device=context.device)
+        nbytes = 16 * max(self.total_capacity, 1) if self.rank == root else 256
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(self.lib.orbit_peer_alloc(context._h, nbytes, C.byref(ptr), handle), "orbit_peer_alloc")
+        self.local_ptr = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        if self.rank == root:
+            self.root_ptr = self.local_ptr
+        else:
+            q = C.c_void_p()
+            _lib.check(self.lib.orbit_peer_open(context._h, handles[root], C.byref(q)), "orbit_peer_open")
+            self.root_ptr = q.value
+        self.counts = torch.zeros(self.world, dtype=torch.int32, device=context.device)
+        self._fence = torch.zeros(1, dtype=torch.int32, device=context.device)
+        dist.barrier(group=group)
+
+    def exchange(self, dispatch_buffer):
+        """Enqueued on the current stream: all-gather of the record counts, this rank's entries -> root, closing fence."""
+        C = self.C
+        dist.all_gather_into_tensor(self.counts, dispatch_buffer[:4].view(torch.int32), group=self.group)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = self.lib.orbit_record_masks_scatter_ranked(self.context._h, C.c_void_p(self.local_masks.data_ptr()), self.rank_capacity,
+                                                        C.c_void_p(self.root_ptr), C.c_void_p(self.counts.data_ptr()), self.rank, self.world,
+                                                        self.total_capacity, stream)
+        if rc:
+            raise RuntimeError("orbit_record_masks_scatter_ranked: %d" % rc)
+        dist.all_reduce(self._fence, group=self.group)     # completes on the root only after every rank's stores were issued and flushed
+
+    def expand(self, scene_buffers, draw_buffer, capacity_draws):
+        """Root only, after exchange(): the combined entries -> MeshletDrawCommandBuffer."""
+        C = self.C
+        rc = self.lib.orbit_draws_from_masks(self.context._h, C.byref(scene_buffers), C.c_void_p(self.local_ptr), self.total_capacity,
+                                             C.c_void_p(self.counts.data_ptr()), self.world, self.rank_capacity,
+                                             C.c_void_p(draw_buffer.data_ptr()), int(capacity_draws),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc:
+            raise RuntimeError("orbit_draws_from_masks: %d" % rc)
+
+    def close(self):
+        if self.rank != self.root:
+            self.lib.orbit_peer_close(self.context._h, self.C.c_void_p(self.root_ptr))
         self.lib.orbit_peer_free(self.context._h, self.C.c_void_p(self.local_ptr))
 
 
@@ -260,25 +323,61 @@ class ShardedView:
         late, _ = exchange_survivors(pf.late_draws)
         return early, late
 
-    # ---- what bench.py times as "the sharded frame including the exchange" ------------------------------------------
+    # ---- the sharded frame with the compact exchange (what bench.py times as "including the exchange") --------------------
+    def enable_mask_exchange(self, capacity_records_total, capacity_draws_total):
+        """Record-entry exchange (MaskExchange) for both lists; the early list's exchange gets its own process group (its own
+        NCCL stream), so it overlaps the pyramid broadcast and the late pass instead of queueing behind them."""
+        self.side_group = dist.new_group()
+        rcap = self.prepared.rcap
+        self.mx_early = MaskExchange(self.context, rcap, capacity_records_total, root=0, group=self.side_group)
+        self.mx_late = MaskExchange(self.context, rcap, capacity_records_total, root=0)
+        self.total_dcap = int(capacity_draws_total)
+        if self.rank == 0:
+            self.gathered_early = torch.zeros(4 + DRAW_BYTES * self.total_dcap, dtype=torch.uint8, device=self.context.device)
+            self.gathered_late = torch.zeros(4 + DRAW_BYTES * self.total_dcap, dtype=torch.uint8, device=self.context.device)
+        self._side = torch.cuda.Stream()
+
     def best_exchange_name(self):
-        return ("survivor lists gathered on rank 0 by NVLink peer stores (device-side counts, no host round trip), the early "
-                "list's exchange overlapped with Hi-Z + late pass, one closing fence")
+        return ("16-byte record entries {draw mask, entity, meshlet offset} to rank 0 by NVLink peer stores (device-side counts), "
+                "rank 0 emits the commands of the combined list; the early list's exchange + emission overlap Hi-Z, its broadcast and the late pass")
 
     def step_best(self):
-        return self.step_overlapped(0)
+        """early cull (test only) -> [side stream: entries -> rank 0, rank 0 emits the early list] || Hi-Z on rank 0 + broadcast ->
+        late cull (test only) -> entries -> rank 0, rank 0 emits the late list."""
+        pf = self.prepared
+        main = torch.cuda.current_stream()
+        if not self.empty:
+            pf.entity(False); pf.meshlet_test(False, self.mx_early.local_masks)
+        else:
+            pf.early_dispatch[:4].zero_()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self.mx_early.exchange(pf.early_dispatch)
+            if self.rank == 0:
+                self.mx_early.expand(pf.sb_early, self.gathered_early, self.total_dcap)
+        if self.rank == 0:
+            pf.hiz()
+        broadcast_pyramid(self.vstate.depth_pyramid.texels, src=0)
+        if not self.empty:
+            pf.entity(True); pf.meshlet_test(True, self.mx_late.local_masks)
+        else:
+            pf.late_dispatch[:4].zero_()
+        self.mx_late.exchange(pf.late_dispatch)
+        if self.rank == 0:
+            self.mx_late.expand(pf.sb_late, self.gathered_late, self.total_dcap)
+        main.wait_stream(self._side)
 
     def clear_gathered(self):
-        self.peer_early.clear(); self.peer_late.clear()
+        if self.rank == 0:
+            self.gathered_early.zero_(); self.gathered_late.zero_()
+        torch.cuda.synchronize()
 
-    def gathered_lists(self, result):
-        """The two assembled MeshletDrawCommandBuffers on this rank after step_best() (meaningful on rank 0)."""
-        c_e, c_l = result
-        return self.peer_early.read(int(c_e.sum())), self.peer_late.read(int(c_l.sum()))
+    def gathered_lists(self):
+        """The two assembled MeshletDrawCommandBuffers (rank 0) after step_best()."""
+        return self.gathered_early, self.gathered_late
 
     def close(self):
-        for name in ("peer_early", "peer_late"):
+        for name in ("peer_early", "peer_late", "mx_early", "mx_late"):
             if hasattr(self, name):
                 getattr(self, name).close()
                 delattr(self, name)
-

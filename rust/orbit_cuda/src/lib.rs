@@ -116,6 +116,7 @@ extern "C" {
     pub fn orbit_ctx_destroy(ctx: *mut orbit_ctx);
     pub fn orbit_ctx_poll_status(ctx: *mut orbit_ctx, out: *mut OrbitStatus) -> i32;
     pub fn orbit_ctx_launch_count(ctx: *const orbit_ctx) -> u64;
+    pub fn orbit_ctx_reserve(ctx: *mut orbit_ctx, entity_draws: u64, capacity_records: u64, n_lights: u64, n_clusters: u64, n_entities: u64) -> i32;
     pub fn orbit_hiz_geometry(depth_width: u32, depth_height: u32, out: *mut OrbitHizInfo) -> i32;
     pub fn orbit_hiz_create(ctx: *mut orbit_ctx, depth_width: u32, depth_height: u32, out: *mut *mut orbit_hiz) -> i32;
     pub fn orbit_hiz_wrap(ctx: *mut orbit_ctx, depth_width: u32, depth_height: u32, texels: *mut f32, out: *mut *mut orbit_hiz) -> i32;
@@ -130,11 +131,19 @@ extern "C" {
     pub fn orbit_light_cluster(ctx: *mut orbit_ctx, params: *const OrbitClusterParams, depth: *const f32, lights: *const c_void,
                                tile_masks: *mut c_void, depth_bounds: *mut c_void, unique_clusters: *mut c_void,
                                offset_count_image: *mut c_void, light_index_list: *mut c_void, capacity_indices: u64, stream: *mut c_void) -> i32;
-    pub fn orbit_draws_scatter_ranked(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, dst_draw_buffer: *mut c_void, rank_counts: *const u32,
-                                      rank: u32, world: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_draws_scatter_ranked(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, src_capacity_draws: u64, dst_draw_buffer: *mut c_void,
+                                      rank_counts: *const u32, rank: u32, world: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_meshlet_test(ctx: *mut orbit_ctx, cull: *const OrbitCullInfo, scene: *const OrbitSceneBuffers, hiz: *const orbit_hiz,
+                              meshlet_dispatch_buffer: *const c_void, capacity_records: u64, record_masks: *mut c_void, stream: *mut c_void) -> i32;
+    pub fn orbit_record_masks_scatter_ranked(ctx: *mut orbit_ctx, src_record_masks: *const c_void, src_capacity_records: u64,
+                                             dst_record_masks: *mut c_void, rank_record_counts: *const u32, rank: u32, world: u32,
+                                             dst_capacity_records: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_draws_from_masks(ctx: *mut orbit_ctx, scene: *const OrbitSceneBuffers, record_masks: *const c_void, capacity_records: u64,
+                                  rank_record_counts: *const u32, world: u32, rank_capacity_records: u64,
+                                  draw_command_buffer: *mut c_void, capacity_draws: u64, stream: *mut c_void) -> i32;
     pub fn orbit_scene_update(ctx: *mut orbit_ctx, update: *const OrbitSceneUpdate, stream: *mut c_void) -> i32;
-    pub fn orbit_draws_scatter(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, dst_draw_buffer: *mut c_void, dst_first: u32,
-                               total_count: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_draws_scatter(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, src_capacity_draws: u64, dst_draw_buffer: *mut c_void,
+                               dst_first: u32, total_count: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
 }
 
 /// Safe-ish wrappers shaped like the reference entry points (draw_gen.rs:327-389, 456-566).

@@ -1,3 +1,7 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-python tools/kbench.py sweep > gpurun_out/r2_kb1.txt 2>&1; cat gpurun_out/r2_kb1.txt | tail -4
-ncu --set full --clock-control none --import-source on -k regex:meshlet_test_direct -s 6 -c 4 -o gpurun_out/r2_prof1 python bench.py --steps 2 --warmup 1 --step-only --no-cpu-baseline > gpurun_out/r2_ncu1.log 2>&1; tail -3 gpurun_out/r2_ncu1.log
+echo "== production lib"; timeout 300 python tools/kbench.py default 2>&1 | tail -1
+for f in _variants/lib_ec128.so _variants/lib_ec64.so; do
+  echo "== $f"; ORBIT_B200_LIB=$PWD/$f timeout 300 python tools/kbench.py default 2>&1 | tail -1
+done
+for f in lib_trace lib_trace_ec128; do
+ORBIT_B200_LIB=$PWD/_variants/$f.so timeout 300 python tools/trace_frame.py > gpurun_out/r2_trace9_$f.txt 2>&1; grep -A200 "run 1" gpurun_out/r2_trace9_$f.txt | grep -E "^\s+\[|frame:|tiles done|cta done" | cut -c1-170
+done

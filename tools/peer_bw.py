@@ -31,7 +31,7 @@ def main():
             dist.barrier(); torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            pe.lib.orbit_draws_scatter(ctx._h, C.c_void_p(src.data_ptr()), C.c_void_p(pe.peer_ptrs[dst_rank]), rank * n, world * n, pe.capacity, stream)
+            pe.lib.orbit_draws_scatter(ctx._h, C.c_void_p(src.data_ptr()), pe.capacity, C.c_void_p(pe.peer_ptrs[dst_rank]), rank * n, world * n, pe.capacity, stream)
             b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b) * 1e3)
         us = sorted(ts[1:])[len(ts[1:]) // 2]
