@@ -70,6 +70,9 @@ typedef struct OrbitStatus {
     uint32_t light_index_overflow;/* light lists exceeded capacity_indices (extra dropped)                    */
     uint32_t visibility_overflow; /* scene update needed more visibility words than the buffer holds (the reference
                                      panics here: scene.rs:427 `.unwrap()`)                                   */
+    uint32_t asset_error;         /* orbit_meshlet_bounds met a meshlet with more than 128 triangles (left untouched);
+                                     orbit_ctx_poll_status then returns ORBIT_ERR_INVALID_ARGUMENT              */
+    uint32_t reserved[3];
 } OrbitStatus;
 
 /* Device pointers to the long-lived scene / asset arrays the culling path reads.
@@ -190,6 +193,21 @@ typedef struct OrbitSceneUpdate {
     void*           entity_draws;            /* out: EntityDrawBuffer (u32 count @0, OrbitEntityDraw[] @4)       */
 } OrbitSceneUpdate;
 int orbit_scene_update(orbit_ctx* ctx, const OrbitSceneUpdate* update, void* stream);
+
+/* ---- asset-side producers of the culling path's inputs --------------------------------- */
+/* The bounds part of compute_meshlets (assets/mesh.rs:292-338): for every OrbitMeshlet m of `meshlets` (vertex_offset,
+ * data_offset, vertex_count, triangle_count filled in by the meshlet builder) computes what meshopt::compute_meshlet_bounds
+ * returns — bounding_sphere, cone_axis (snorm8 x 3), cone_cutoff (snorm8) — and stores it into the meshlet in place.
+ * Geometry: vertex v of the meshlet = vertices[vertex_offset + meshlet_data[data_offset + v]] (position = 3 x f32 at the start
+ * of a `vertex_stride`-byte element: GpuMeshVertex, assets/mesh.rs:12-20, stride 32); triangle t = the three bytes at
+ * ((u8*)&meshlet_data[data_offset + vertex_count])[3t..3t+3] (the layout compute_meshlets writes, mesh.rs:308-316).
+ * Meshlets with more than 128 triangles are left untouched and flagged (OrbitStatus.asset_error). */
+int orbit_meshlet_bounds(orbit_ctx* ctx, const void* vertices, uint32_t vertex_stride, const uint32_t* meshlet_data,
+                         void* meshlets, uint32_t n_meshlets, void* stream);
+/* MeshData::compute_bounds (assets/mesh.rs:192-215) for n_meshes meshes: vertex_ranges[2m] = first vertex, [2m+1] = vertex
+ * count; writes OrbitMeshInfo[m].bounding_sphere (centre = AABB middle, radius = largest vertex distance) and .aabb. */
+int orbit_mesh_bounds(orbit_ctx* ctx, const void* vertices, uint32_t vertex_stride, const uint32_t* vertex_ranges,
+                      void* mesh_infos, uint32_t n_meshes, void* stream);
 
 /* ---- multi-GPU helper (no reference counterpart) --------------------------------------------- */
 /* Appends `count` draw commands read from src (a MeshletDrawCommandBuffer, device-side count honoured) into

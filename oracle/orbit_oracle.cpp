@@ -750,4 +750,142 @@ int oracle_scene_update(const float* transforms, const uint32_t* mesh_slots, uin
     return overflow;
 }
 
+// ---- asset-side producers --------------------------------------------------------------------------
+// meshlet bounds: the bounds part of compute_meshlets (src/assets/mesh.rs:292-338) = meshopt::compute_meshlet_bounds.
+// meshopt 0.2.0 (Cargo.toml:40) is NOT vendored in the reference tree; this restates meshoptimizer's published
+// meshopt_computeMeshletBounds / computeBoundingSphere (clusterizer.cpp). PARITY UNPINNED against the reference (no
+// executable meshopt here); the CUDA kernel (csrc/asset_bounds.cu) is held to this restatement bit for bit.
+static void ref_bounding_sphere(float result[4], const float (*points)[3], size_t count) {
+    size_t pmin[3] = {0, 0, 0}, pmax[3] = {0, 0, 0};
+    for (size_t i = 0; i < count; ++i) {
+        const float* p = points[i];
+        for (int axis = 0; axis < 3; ++axis) {
+            pmin[axis] = (p[axis] < points[pmin[axis]][axis]) ? i : pmin[axis];
+            pmax[axis] = (p[axis] > points[pmax[axis]][axis]) ? i : pmax[axis];
+        }
+    }
+    float paxisd2 = 0;
+    int paxis = 0;
+    for (int axis = 0; axis < 3; ++axis) {
+        const float* p1 = points[pmin[axis]];
+        const float* p2 = points[pmax[axis]];
+        const float dx = p2[0] - p1[0], dy = p2[1] - p1[1], dz = p2[2] - p1[2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 > paxisd2) { paxisd2 = d2; paxis = axis; }
+    }
+    const float* p1 = points[pmin[paxis]];
+    const float* p2 = points[pmax[paxis]];
+    float center[3] = {(p1[0] + p2[0]) / 2, (p1[1] + p2[1]) / 2, (p1[2] + p2[2]) / 2};
+    float radius = std::sqrt(paxisd2) / 2;
+    for (size_t i = 0; i < count; ++i) {
+        const float* p = points[i];
+        const float dx = p[0] - center[0], dy = p[1] - center[1], dz = p[2] - center[2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 > radius * radius) {
+            const float d = std::sqrt(d2);
+            const float k = 0.5f + (radius / d) / 2;
+            const float k1 = 1 - k;
+            center[0] = center[0] * k + p[0] * k1;
+            center[1] = center[1] * k + p[1] * k1;
+            center[2] = center[2] * k + p[2] * k1;
+            radius = (radius + d) / 2;
+        }
+    }
+    result[0] = center[0]; result[1] = center[1]; result[2] = center[2]; result[3] = radius;
+}
+
+static int ref_quantize_snorm8(float v) {
+    const float round = (v >= 0 ? 0.5f : -0.5f);
+    v = (v >= -1) ? v : -1;
+    v = (v <= +1) ? v : +1;
+    return int(v * 127.0f + round);
+}
+
+// meshlets: OrbitMeshlet[n] in / out. Returns the number of meshlets skipped because they hold more than 128 triangles.
+int oracle_meshlet_bounds(const void* vertices_, uint32_t vertex_stride, const uint32_t* meshlet_data, void* meshlets_, uint32_t n_meshlets) {
+    const uint8_t* vertices = (const uint8_t*)vertices_;
+    OrbitMeshlet* meshlets = (OrbitMeshlet*)meshlets_;
+    int skipped = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : skipped)
+    for (int64_t m = 0; m < (int64_t)n_meshlets; ++m) {
+        OrbitMeshlet& ml = meshlets[m];
+        const uint32_t tcount = ml.triangle_count;
+        if (tcount > 128u) { ++skipped; continue; }
+        const uint32_t* vidx = meshlet_data + ml.data_offset;
+        const uint8_t* tris = (const uint8_t*)(vidx + ml.vertex_count);
+        float normals[128][3];
+        float corners[128 * 3][3];
+        size_t triangles = 0;
+        for (uint32_t t = 0; t < tcount; ++t) {
+            const float* pc[3];
+            for (int k = 0; k < 3; ++k) pc[k] = (const float*)(vertices + (size_t)(ml.vertex_offset + vidx[tris[3 * t + k]]) * vertex_stride);
+            const float p10[3] = {pc[1][0] - pc[0][0], pc[1][1] - pc[0][1], pc[1][2] - pc[0][2]};
+            const float p20[3] = {pc[2][0] - pc[0][0], pc[2][1] - pc[0][1], pc[2][2] - pc[0][2]};
+            const float nx = p10[1] * p20[2] - p10[2] * p20[1];
+            const float ny = p10[2] * p20[0] - p10[0] * p20[2];
+            const float nz = p10[0] * p20[1] - p10[1] * p20[0];
+            const float area = std::sqrt(nx * nx + ny * ny + nz * nz);
+            if (area == 0.f) continue;                       // degenerate triangles are invisible anyway
+            normals[triangles][0] = nx / area; normals[triangles][1] = ny / area; normals[triangles][2] = nz / area;
+            for (int k = 0; k < 3; ++k) std::memcpy(corners[3 * triangles + k], pc[k], 12);
+            ++triangles;
+        }
+        if (triangles == 0) {                                // degenerate cluster: zeroed bounds
+            ml.bounding_sphere[0] = ml.bounding_sphere[1] = ml.bounding_sphere[2] = ml.bounding_sphere[3] = 0.f;
+            ml.cone_axis[0] = ml.cone_axis[1] = ml.cone_axis[2] = 0; ml.cone_cutoff = 0;
+            continue;
+        }
+        float psphere[4], nsphere[4];
+        ref_bounding_sphere(psphere, corners, triangles * 3);
+        ref_bounding_sphere(nsphere, normals, triangles);
+        float axis[3] = {nsphere[0], nsphere[1], nsphere[2]};
+        const float axislength = std::sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+        const float invaxislength = axislength == 0.f ? 0.f : 1.f / axislength;
+        axis[0] *= invaxislength; axis[1] *= invaxislength; axis[2] *= invaxislength;
+        float mindp = 1.f;
+        for (size_t i = 0; i < triangles; ++i) {
+            const float dp = normals[i][0] * axis[0] + normals[i][1] * axis[1] + normals[i][2] * axis[2];
+            mindp = (dp < mindp) ? dp : mindp;
+        }
+        for (int k = 0; k < 4; ++k) ml.bounding_sphere[k] = psphere[k];
+        if (mindp <= 0.1f) {                                 // normal cone ~168 degrees or wider: trivial accept
+            ml.cone_axis[0] = ml.cone_axis[1] = ml.cone_axis[2] = 0; ml.cone_cutoff = 127;
+            continue;
+        }
+        const float cutoff = std::sqrt(1 - mindp * mindp);
+        const int q0 = ref_quantize_snorm8(axis[0]), q1 = ref_quantize_snorm8(axis[1]), q2 = ref_quantize_snorm8(axis[2]);
+        const float e0 = std::fabs((signed char)q0 / 127.f - axis[0]);
+        const float e1 = std::fabs((signed char)q1 / 127.f - axis[1]);
+        const float e2 = std::fabs((signed char)q2 / 127.f - axis[2]);
+        const int qc = int(127 * (cutoff + e0 + e1 + e2) + 1);
+        ml.cone_axis[0] = (int8_t)q0; ml.cone_axis[1] = (int8_t)q1; ml.cone_axis[2] = (int8_t)q2;
+        ml.cone_cutoff = (qc > 127) ? (int8_t)127 : (int8_t)qc;
+    }
+    return skipped;
+}
+
+// MeshData::compute_bounds (src/assets/mesh.rs:192-215): vertex_ranges[2m] = first vertex, [2m+1] = count.
+void oracle_mesh_bounds(const void* vertices_, uint32_t vertex_stride, const uint32_t* vertex_ranges, void* mesh_infos_, uint32_t n_meshes) {
+    const uint8_t* vertices = (const uint8_t*)vertices_;
+    uint8_t* mesh_infos = (uint8_t*)mesh_infos_;
+    for (uint32_t m = 0; m < n_meshes; ++m) {
+        const uint32_t first = vertex_ranges[2 * m], count = vertex_ranges[2 * m + 1];
+        if (count == 0) continue;
+        auto pos = [&](uint32_t i) { return (const float*)(vertices + (size_t)(first + i) * vertex_stride); };
+        float lo[3] = {pos(0)[0], pos(0)[1], pos(0)[2]}, hi[3] = {lo[0], lo[1], lo[2]};
+        for (uint32_t i = 0; i < count; ++i)
+            for (int k = 0; k < 3; ++k) { lo[k] = std::fmin(lo[k], pos(i)[k]); hi[k] = std::fmax(hi[k], pos(i)[k]); }
+        const float c[3] = {(hi[0] + lo[0]) * 0.5f, (hi[1] + lo[1]) * 0.5f, (hi[2] + lo[2]) * 0.5f};
+        float r2 = 0.0f;
+        for (uint32_t i = 0; i < count; ++i) {
+            const float dx = pos(i)[0] - c[0], dy = pos(i)[1] - c[1], dz = pos(i)[2] - c[2];
+            r2 = std::fmax(r2, dx * dx + dy * dy + dz * dz);
+        }
+        float* mi = (float*)(mesh_infos + (size_t)m * 128);
+        mi[0] = c[0]; mi[1] = c[1]; mi[2] = c[2]; mi[3] = std::sqrt(r2);
+        mi[4] = lo[0]; mi[5] = lo[1]; mi[6] = lo[2]; mi[7] = 0.0f;
+        mi[8] = hi[0]; mi[9] = hi[1]; mi[10] = hi[2]; mi[11] = 0.0f;
+    }
+}
+
 }  // extern "C"

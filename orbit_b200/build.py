@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liborbit_b200.so")
-SOURCES = ["api.cu", "hiz_build.cu", "entity_cull.cu", "meshlet_cull.cu", "light_cluster.cu", "scene_update.cu"]
+SOURCES = ["api.cu", "hiz_build.cu", "entity_cull.cu", "meshlet_cull.cu", "light_cluster.cu", "scene_update.cu", "asset_bounds.cu"]
 HOST_LIB_PATH = os.path.join(LIB_DIR, "liborbit_host.so")   # compiled host-side frame driver above the C ABI
 HOST_SOURCES = [os.path.join(HERE, "host", "frame_driver.cpp")]
 HEADERS = ["orbit_device.cuh", "scan.cuh", "params.cuh", "../../include/orbit_cuda.h", "../../include/orbit_layouts.h"]

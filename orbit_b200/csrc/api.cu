@@ -65,6 +65,9 @@ struct orbit_ctx {
     // light scratch
     float4* light_view = nullptr;
     size_t light_capacity = 0;
+    uint64_t light_hits_budget = 0;   // bytes the bit matrix may take (ORBIT_LIGHT_HITS_BUDGET_MB, default 256)
+    uint32_t* light_hits = nullptr;   // bit matrix [active cluster][light / 32] of the light-parallel culling path
+    size_t light_hits_words = 0;
     // tuning (ORBIT_MC_CTAS_PER_SM environment override, read once)
     int mc_ctas_per_sm = 0;
     int emit_occupancy = 0;
@@ -137,6 +140,24 @@ static int ensure_record_scratch(orbit_ctx* c, uint64_t max_records) {
     CK(cudaMalloc(&c->draw_masks, cap * sizeof(uint4)));
     CK(cudaMalloc(&c->cmd_side, cap * 32u * sizeof(uint4)));
     c->draw_mask_capacity = cap;
+    return ORBIT_OK;
+}
+
+// The light-parallel culling path keeps one hit bit per (cluster, light); grids whose matrix would exceed this budget (the
+// reference's default 8-pixel tiles: ~10^6 clusters) take the CTA-per-cluster kernel instead.
+static constexpr uint64_t kLightHitsBudgetBytes = 256ull << 20;
+static uint64_t light_hits_words_needed(uint64_t clusters, uint64_t n_lights) {   // bit matrix + per-(cluster, light block) counts
+    return clusters * ((uint64_t)light_hits_blocks((uint32_t)n_lights) * 17u + 8u);   // 16 words of bits + 1 count per (cluster, light block), 8 words of box per cluster
+}
+
+static int ensure_light_hits(orbit_ctx* c, uint64_t words) {
+    if (words <= c->light_hits_words) return ORBIT_OK;
+    int rc = retire(c, c->light_hits);
+    if (rc != ORBIT_OK) return rc;
+    c->light_hits = nullptr; c->light_hits_words = 0;
+    size_t cap = 1u << 16; while (cap < words) cap *= 2;
+    CK(cudaMalloc(&c->light_hits, cap * sizeof(uint32_t)));
+    c->light_hits_words = cap;
     return ORBIT_OK;
 }
 
@@ -224,6 +245,8 @@ int orbit_ctx_create(int device, orbit_ctx** out) {
 #endif
     if (const char* s = std::getenv("ORBIT_DEBUG_SKIP")) c->debug_skip = std::atoi(s);
     if (const char* s = std::getenv("ORBIT_MC_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->mc_ctas_per_sm = v; }
+    c->light_hits_budget = kLightHitsBudgetBytes;
+    if (const char* s = std::getenv("ORBIT_LIGHT_HITS_BUDGET_MB")) { const long v = std::atol(s); if (v >= 0) c->light_hits_budget = (uint64_t)v << 20; }
     if (const char* s = std::getenv("ORBIT_EMIT_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->emit_ctas_per_sm = v; }
     *out = c;
     return ORBIT_OK;
@@ -234,7 +257,7 @@ void orbit_ctx_destroy(orbit_ctx* c) {
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < c->n_retired; ++i) cudaFree(c->retired[i]);
-    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->draw_masks); cudaFree(c->cmd_side); cudaFree(c->chunk_counts); cudaFree(c->tile_sums);
+    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->light_hits); cudaFree(c->draw_masks); cudaFree(c->cmd_side); cudaFree(c->chunk_counts); cudaFree(c->tile_sums);
     cudaFree(c->trace);
     cudaFreeHost(c->status_host);
     delete c;
@@ -244,6 +267,7 @@ int orbit_ctx_poll_status(orbit_ctx* c, OrbitStatus* out) {
     if (!c || !out) return ORBIT_ERR_INVALID_ARGUMENT;
     *out = *c->status_host;
     std::memset(c->status_host, 0, sizeof(OrbitStatus));
+    if (out->asset_error) return ORBIT_ERR_INVALID_ARGUMENT;
     return (out->dispatch_overflow || out->draw_overflow || out->light_index_overflow || out->visibility_overflow) ? ORBIT_ERR_CAPACITY : ORBIT_OK;
 }
 
@@ -538,7 +562,9 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
     cudaStream_t s = (cudaStream_t)stream;
     const uint64_t clusters = cx * cy * cz;
     GUARD(c);
-    int rc = ensure_lights(c, L);
+    const uint64_t hit_words = light_hits_words_needed(clusters, L);
+    const bool light_parallel = L != 0u && hit_words * 4u <= c->light_hits_budget;
+    int rc = light_parallel ? ensure_light_hits(c, hit_words) : ensure_lights(c, L);
     if (rc != ORBIT_OK) return rc;
     rc = ensure_status(c, (size_t)clusters + 1u, s);   // light culling scans one tile per active cluster
     if (rc != ORBIT_OK) return rc;
@@ -549,6 +575,8 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
     p.unique_clusters = (uint32_t*)unique_clusters; p.offset_count_image = (uint32_t*)offset_count_image;
     p.light_index_words = (uint32_t*)light_index_list; p.overflow_flag = &c->status_dev->light_index_overflow;
     p.capacity_indices = capacity_indices;
+    // scratch of the light-parallel path: [boxes: 8 words per cluster][bit matrix][block counts]
+    p.cluster_boxes = light_parallel ? reinterpret_cast<float4*>(c->light_hits) : nullptr;
     // fill_buffer(.., 0) of masks and bounds: cluster.rs:447-450; inactive image texels are zeroed (unspecified in the reference)
     CK(cudaMemsetAsync(tile_masks, 0, cx * cy * 4u, s));
     CK(cudaMemsetAsync(depth_bounds, 0, clusters * 8u, s));
@@ -560,13 +588,26 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
     CK(launch_mark_active(p, (int)grid, s));
     p.scan = next_scan(c);
     CK(launch_compact_clusters(p, s));
-    CK(launch_light_view(p, s));
-    p.scan = next_scan(c);
-    uint64_t lgrid = clusters;                       // one CTA per active cluster, persistent: at most 2 x 1024 threads per SM
-    const uint64_t lcap = (uint64_t)c->sm_count * 2u;
-    if (lgrid > lcap) lgrid = lcap;
-    CK(launch_light_culling(p, (int)lgrid, s));
-    c->launches += (L ? 4 : 3);
+    if (light_parallel) {
+        const uint32_t wpc = light_hits_blocks(L) * 16u;   // row stride of the bit matrix (64-byte aligned rows)
+        uint32_t* const hit_rows = c->light_hits + clusters * 8u;
+        uint32_t* const block_counts = hit_rows + clusters * wpc;
+        CK(launch_light_hits(p, hit_rows, block_counts, wpc, (uint32_t)clusters, s));
+        p.scan = next_scan(c);
+        uint64_t lgrid = (clusters + 31u) / 32u;     // a warp per active cluster, 32 per CTA, persistent over tiles
+        const uint64_t lcap = (uint64_t)c->sm_count * 2u;
+        if (lgrid > lcap) lgrid = lcap;
+        CK(launch_light_lists(p, hit_rows, block_counts, wpc, (int)lgrid, s));
+        c->launches += 4;
+    } else {
+        CK(launch_light_view(p, s));
+        p.scan = next_scan(c);
+        uint64_t lgrid = clusters;                   // one CTA per active cluster, persistent: at most 2 x 1024 threads per SM
+        const uint64_t lcap = (uint64_t)c->sm_count * 2u;
+        if (lgrid > lcap) lgrid = lcap;
+        CK(launch_light_culling(p, (int)lgrid, s));
+        c->launches += (L ? 4 : 3);
+    }
     return ORBIT_OK;
 }
 
@@ -613,6 +654,40 @@ int orbit_scene_update(orbit_ctx* c, const OrbitSceneUpdate* u, void* stream) {
     p.n_entities = u->n_entities; p.visibility_capacity_words = u->visibility_capacity_words;
     CK(launch_scene_update(p, (cudaStream_t)stream));
     c->launches += 2;
+    return ORBIT_OK;
+}
+
+int orbit_meshlet_bounds(orbit_ctx* c, const void* vertices, uint32_t vertex_stride, const uint32_t* meshlet_data, void* meshlets,
+                         uint32_t n_meshlets, void* stream) {
+    if (!c || !vertices || !meshlet_data || !meshlets || vertex_stride < 12u || (vertex_stride & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)vertices & 3u) || ((uintptr_t)meshlet_data & 3u) || ((uintptr_t)meshlets & 15u)) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (n_meshlets == 0u) return ORBIT_OK;
+    GUARD(c);
+    MeshletBoundsParams p{};
+    p.vertices = (const uint8_t*)vertices; p.vertex_stride = vertex_stride; p.meshlet_data = meshlet_data;
+    p.meshlets = (uint8_t*)meshlets; p.n_meshlets = n_meshlets; p.error_flag = &c->status_dev->asset_error;
+    uint64_t grid = ((uint64_t)n_meshlets + 3u) / 4u;
+    const uint64_t cap = (uint64_t)c->sm_count * 16u;
+    if (grid > cap) grid = cap;
+    CK(launch_meshlet_bounds(p, (int)grid, (cudaStream_t)stream));
+    c->launches += 1;
+    return ORBIT_OK;
+}
+
+int orbit_mesh_bounds(orbit_ctx* c, const void* vertices, uint32_t vertex_stride, const uint32_t* vertex_ranges, void* mesh_infos,
+                      uint32_t n_meshes, void* stream) {
+    if (!c || !vertices || !vertex_ranges || !mesh_infos || vertex_stride < 12u || (vertex_stride & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)vertices & 3u) || ((uintptr_t)vertex_ranges & 3u) || ((uintptr_t)mesh_infos & 15u)) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (n_meshes == 0u) return ORBIT_OK;
+    GUARD(c);
+    MeshBoundsParams p{};
+    p.vertices = (const uint8_t*)vertices; p.vertex_stride = vertex_stride; p.vertex_ranges = vertex_ranges;
+    p.mesh_infos = (uint8_t*)mesh_infos; p.n_meshes = n_meshes;
+    uint64_t grid = n_meshes;
+    const uint64_t cap = (uint64_t)c->sm_count * 8u;
+    if (grid > cap) grid = cap;
+    CK(launch_mesh_bounds(p, (int)grid, (cudaStream_t)stream));
+    c->launches += 1;
     return ORBIT_OK;
 }
 

@@ -122,68 +122,6 @@ __global__ void __launch_bounds__(256) mark_active_kernel(const __grid_constant_
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) compact_clusters_kernel(const __grid_constant__ ClusterParams p) {
-    __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_tile, s_base;
-    const OrbitClusterCullInfo& ci = p.info;
-    const uint32_t cx = ci.cluster_count[0], cy = ci.cluster_count[1], cz = ci.cluster_count[2];
-    const uint32_t total = cx * cy * cz;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const unsigned int epoch = scan_epoch(p.scan);
-    if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t idx = tile * 256u + tid;
-    bool active = false;
-    if (idx < total) {
-        const uint32_t z = idx / (cx * cy);
-        const uint32_t t = idx - z * cx * cy;   // tile index = x + y*cx
-        active = (__ldcg(p.tile_masks + t) & shl1(z)) != 0u;
-    }
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, active);
-    if (lane == 0u) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t warp_base = 0u, tile_total = 0u;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { const uint32_t v = s_warp[w]; if ((uint32_t)w < warp) warp_base += v; tile_total += v; }
-    if (warp == 0u) {
-        const uint32_t base = lookback_exclusive(p.scan, epoch, tile, tile_total);
-        if (lane == 0u) {
-            s_base = base;
-            if (tile == gridDim.x - 1u) {
-                const uint32_t n = base + tile_total;
-                p.unique_clusters[0] = (n + 255u) / 256u;   // div_ceil(cluster_count, 256)
-                p.unique_clusters[1] = 1u;
-                p.unique_clusters[2] = 1u;
-                p.unique_clusters[3] = n;
-            }
-        }
-    }
-    __syncthreads();
-    if (active) p.unique_clusters[4u + s_base + warp_base + __popc(bal & ((1u << lane) - 1u))] = idx;
-    if (tid == 0) scan_cta_exit(p.scan, epoch);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) light_view_kernel(const __grid_constant__ ClusterParams p) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p.info.global_light_count) return;
-    const uint8_t* l = p.lights + (size_t)j * 64u;
-    const uint32_t type = __ldg(reinterpret_cast<const uint32_t*>(l));
-    const float4 pos = __ldg(reinterpret_cast<const float4*>(l + 32));      // position xyz, inner_radius
-    const float radius = __ldg(reinterpret_cast<const float*>(l + 60));
-    const float* m = &p.info.world_to_view_matrix.m[0][0];
-    float4 o;
-    o.x = add(add(add(mul(m[0], pos.x), mul(m[4], pos.y)), mul(m[8], pos.z)), mul(m[12], 1.0f));
-    o.y = add(add(add(mul(m[1], pos.x), mul(m[5], pos.y)), mul(m[9], pos.z)), mul(m[13], 1.0f));
-    o.z = add(add(add(mul(m[2], pos.x), mul(m[6], pos.y)), mul(m[10], pos.z)), mul(m[14], 1.0f));
-    o.w = (type == ORBIT_LIGHT_POINT) ? radius : __uint_as_float(0x7F800000u);  // non-point lights always hit
-    p.light_view[j] = o;
-}
-
-constexpr int kLcWarps = 32;
-
 struct Aabb3 { float lo[3], hi[3]; };
 
 __device__ __forceinline__ void unproject(const OrbitClusterCullInfo& ci, float px, float py, float* out) {
@@ -229,6 +167,78 @@ __device__ __forceinline__ Aabb3 cluster_volume(const ClusterParams& p, uint32_t
     }
     return a;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) compact_clusters_kernel(const __grid_constant__ ClusterParams p) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_tile, s_base;
+    const OrbitClusterCullInfo& ci = p.info;
+    const uint32_t cx = ci.cluster_count[0], cy = ci.cluster_count[1], cz = ci.cluster_count[2];
+    const uint32_t total = cx * cy * cz;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned int epoch = scan_epoch(p.scan);
+    if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t idx = tile * 256u + tid;
+    bool active = false;
+    if (idx < total) {
+        const uint32_t z = idx / (cx * cy);
+        const uint32_t t = idx - z * cx * cy;   // tile index = x + y*cx
+        active = (__ldcg(p.tile_masks + t) & shl1(z)) != 0u;
+    }
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, active);
+    if (lane == 0u) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t warp_base = 0u, tile_total = 0u;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t v = s_warp[w]; if ((uint32_t)w < warp) warp_base += v; tile_total += v; }
+    if (warp == 0u) {
+        const uint32_t base = lookback_exclusive(p.scan, epoch, tile, tile_total);
+        if (lane == 0u) {
+            s_base = base;
+            if (tile == gridDim.x - 1u) {
+                const uint32_t n = base + tile_total;
+                p.unique_clusters[0] = (n + 255u) / 256u;   // div_ceil(cluster_count, 256)
+                p.unique_clusters[1] = 1u;
+                p.unique_clusters[2] = 1u;
+                p.unique_clusters[3] = n;
+            }
+        }
+    }
+    __syncthreads();
+    if (active) {
+        const uint32_t slot = s_base + warp_base + __popc(bal & ((1u << lane) - 1u));
+        p.unique_clusters[4u + slot] = idx;
+        // the light-parallel culling path reads every active cluster's view-space box from many CTAs: computed once, here
+        // (ten IEEE divisions per cluster, light_culling.comp:68-119), 32 bytes per compacted-list slot
+        if (p.cluster_boxes != nullptr) {
+            const Aabb3 b = cluster_volume(p, idx);
+            p.cluster_boxes[2u * (size_t)slot] = make_float4(b.lo[0], b.lo[1], b.lo[2], 0.0f);
+            p.cluster_boxes[2u * (size_t)slot + 1u] = make_float4(b.hi[0], b.hi[1], b.hi[2], 0.0f);
+        }
+    }
+    if (tid == 0) scan_cta_exit(p.scan, epoch);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) light_view_kernel(const __grid_constant__ ClusterParams p) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.info.global_light_count) return;
+    const uint8_t* l = p.lights + (size_t)j * 64u;
+    const uint32_t type = __ldg(reinterpret_cast<const uint32_t*>(l));
+    const float4 pos = __ldg(reinterpret_cast<const float4*>(l + 32));      // position xyz, inner_radius
+    const float radius = __ldg(reinterpret_cast<const float*>(l + 60));
+    const float* m = &p.info.world_to_view_matrix.m[0][0];
+    float4 o;
+    o.x = add(add(add(mul(m[0], pos.x), mul(m[4], pos.y)), mul(m[8], pos.z)), mul(m[12], 1.0f));
+    o.y = add(add(add(mul(m[1], pos.x), mul(m[5], pos.y)), mul(m[9], pos.z)), mul(m[13], 1.0f));
+    o.z = add(add(add(mul(m[2], pos.x), mul(m[6], pos.y)), mul(m[10], pos.z)), mul(m[14], 1.0f));
+    o.w = (type == ORBIT_LIGHT_POINT) ? radius : __uint_as_float(0x7F800000u);  // non-point lights always hit
+    p.light_view[j] = o;
+}
+
+constexpr int kLcWarps = 32;
 
 // One CTA of kLcWarps warps per active cluster (persistent over clusters through a ticket). The light list is cut
 // into kLcWarps contiguous stripes, one per warp; a warp tests 32 lights per step and ballot-compacts its hits
@@ -320,6 +330,206 @@ __global__ void __launch_bounds__(kLcWarps * 32) light_culling_kernel(const __gr
         }
     }
     if (tid == 0) scan_cta_exit(p.scan, epoch);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Light-parallel formulation of light_culling.comp:121-151 (the path taken whenever its bit matrix fits the scratch budget;
+// the CTA-per-cluster kernel above remains for grids with ~10^6 clusters). The CTA-per-cluster kernel re-streams the whole
+// light array once per active cluster and occupies one SM per cluster (C4: 99 clusters -> 99 of 148 SMs, 232 G tests/s).
+// Here the work is cut the other way:
+//   1. light_hits_kernel: a CTA owns 512 consecutive lights (two per thread, view-space sphere computed in registers —
+//      no light_view pass) and a chunk of 32 active clusters whose view-space boxes sit in shared memory; every
+//      (light, cluster) test is one broadcast shared-memory read of the box + ~17 FP32 instructions, a ballot per
+//      (warp, cluster) yields 32 hit bits, and the CTA leaves a 16-word row per cluster in a bit matrix
+//      [active cluster][light / 32] (coalesced 64-byte stores). Grid = light blocks x cluster chunks: every SM busy.
+//   2. light_lists_kernel: a warp per active cluster reads its row of the matrix (2049 words at C4), counts, caps at 256
+//      (the reference keeps the FIRST 256 hits in ascending light order: light_culling.comp:121-132), the clusters' ranges
+//      are packed in compacted-list order by the look-back scan, and the warp expands its row's first 256 set bits into
+//      ascending light indices. Same arithmetic per test as the kernel above, so the lists are bit-identical.
+constexpr uint32_t kLhLightsPerCta = 512u, kLhClusterChunk = 32u, kLhWordsPerCta = kLhLightsPerCta / 32u;
+
+// hits:   [active cluster][words_per_cluster]   one bit per light; words_per_cluster = 16 x light blocks (rows are 64-byte aligned)
+// counts: [active cluster][light_blocks]        hits of the cluster among the 512 lights of one light block
+__global__ void __launch_bounds__(256) light_hits_kernel(const __grid_constant__ ClusterParams p, uint32_t* __restrict__ hits,
+                                                         uint32_t* __restrict__ counts, uint32_t words_per_cluster) {
+    __shared__ float s_box[kLhClusterChunk][8];                  // lo xyz, hi xyz (padded to 32 bytes: two 16-byte broadcast reads)
+    __shared__ uint32_t s_out[kLhClusterChunk][kLhWordsPerCta];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t nactive = __ldcg(p.unique_clusters + 3);
+    if (blockIdx.y * kLhClusterChunk >= nactive) return;        // chunk rows beyond the active clusters: nothing to do, before any load
+    const uint32_t L = p.info.global_light_count;
+    const uint32_t light0 = blockIdx.x * kLhLightsPerCta;
+    // this thread's two lights: light0 + tid and light0 + 256 + tid (word = block * 16 + k * 8 + warp, bit = lane)
+    float lx[2], ly[2], lz[2], lr2[2];
+    bool live[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t j = light0 + (uint32_t)k * 256u + tid;
+        live[k] = j < L;
+        lx[k] = ly[k] = lz[k] = 0.0f; lr2[k] = -1.0f;
+        if (live[k]) {
+            const uint8_t* l = p.lights + (size_t)j * 64u;
+            const uint32_t type = __ldg(reinterpret_cast<const uint32_t*>(l));
+            const float4 pos = __ldg(reinterpret_cast<const float4*>(l + 32));      // position xyz, inner_radius
+            const float radius = __ldg(reinterpret_cast<const float*>(l + 60));
+            const float* m = &p.info.world_to_view_matrix.m[0][0];
+            lx[k] = add(add(add(mul(m[0], pos.x), mul(m[4], pos.y)), mul(m[8], pos.z)), mul(m[12], 1.0f));
+            ly[k] = add(add(add(mul(m[1], pos.x), mul(m[5], pos.y)), mul(m[9], pos.z)), mul(m[13], 1.0f));
+            lz[k] = add(add(add(mul(m[2], pos.x), mul(m[6], pos.y)), mul(m[10], pos.z)), mul(m[14], 1.0f));
+            const float w = (type == ORBIT_LIGHT_POINT) ? radius : __uint_as_float(0x7F800000u);   // non-point lights always hit
+            lr2[k] = mul(w, w);
+        }
+    }
+    for (uint32_t chunk0 = blockIdx.y * kLhClusterChunk; chunk0 < nactive; chunk0 += gridDim.y * kLhClusterChunk) {
+        const uint32_t nc = min(kLhClusterChunk, nactive - chunk0);
+        __syncthreads();                                         // previous chunk's boxes and rows are no longer read
+        if (tid < 2u * nc) *reinterpret_cast<float4*>(&s_box[tid >> 1][(tid & 1u) * 4u]) = __ldcg(p.cluster_boxes + 2u * (size_t)chunk0 + tid);
+        __syncthreads();
+        for (uint32_t c = 0; c < nc; ++c) {
+            const float4 lo = *reinterpret_cast<const float4*>(&s_box[c][0]);
+            const float4 hi = *reinterpret_cast<const float4*>(&s_box[c][4]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                // per axis: v < lo adds (lo-v)^2, v > hi adds (v-hi)^2 (light_culling.comp:52-66); lo <= hi, so at most one
+                // applies and d is that term's base (or 0, and fma(0,0,acc) == acc): same value, no divergence
+                float acc = 0.0f;
+                float d = fmaxf(fmaxf(sub(lo.x, lx[k]), sub(lx[k], hi.x)), 0.0f); acc = fma_(d, d, acc);
+                d = fmaxf(fmaxf(sub(lo.y, ly[k]), sub(ly[k], hi.y)), 0.0f); acc = fma_(d, d, acc);
+                d = fmaxf(fmaxf(sub(lo.z, lz[k]), sub(lz[k], hi.z)), 0.0f); acc = fma_(d, d, acc);
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, live[k] && acc <= lr2[k]);
+                if (lane == 0u) s_out[c][(uint32_t)k * 8u + warp] = bal;
+            }
+        }
+        __syncthreads();
+        // rows out: 16 consecutive words per cluster + their popcount (16 lanes per cluster: half-warp reduction)
+        for (uint32_t i0 = 0; i0 < kLhClusterChunk * kLhWordsPerCta; i0 += 256u) {
+            const uint32_t i = i0 + tid, c = i >> 4, w = i & 15u;
+            const uint32_t v = c < nc ? s_out[c][w] : 0u;
+            const uint32_t word = blockIdx.x * kLhWordsPerCta + w;
+            if (c < nc) hits[(size_t)(chunk0 + c) * words_per_cluster + word] = v;
+            uint32_t n = (uint32_t)__popc(v);
+            n += __shfl_xor_sync(0xFFFFFFFFu, n, 1); n += __shfl_xor_sync(0xFFFFFFFFu, n, 2);
+            n += __shfl_xor_sync(0xFFFFFFFFu, n, 4); n += __shfl_xor_sync(0xFFFFFFFFu, n, 8);
+            if (c < nc && w == 0u) counts[(size_t)(chunk0 + c) * gridDim.x + blockIdx.x] = n;
+        }
+    }
+}
+
+// One warp per active cluster, 32 clusters per CTA (a tile of the look-back scan: with ~100 active clusters the chain is four
+// tiles long). The cluster's hits per light block are scanned (ascending light order = ascending block order), the total is
+// capped at the reference's 256, the tile's range comes from the look-back over tiles in compacted-list order, and every lane
+// expands the blocks it owns at their ranks — only blocks that hold a hit are ever read from the bit matrix.
+constexpr int kLlWarps = 32;
+__global__ void __launch_bounds__(kLlWarps * 32) light_lists_kernel(const __grid_constant__ ClusterParams p, const uint32_t* __restrict__ hits,
+                                                                    const uint32_t* __restrict__ counts, uint32_t words_per_cluster, uint32_t light_blocks) {
+    __shared__ uint32_t s_cnt[kLlWarps];
+    __shared__ uint32_t s_tile, s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned int epoch = scan_epoch(p.scan);
+    const uint32_t nactive = __ldcg(p.unique_clusters + 3);
+    const uint32_t ntiles = (nactive + kLlWarps - 1u) / kLlWarps;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) {
+            if (tile == 0u && tid == 0) p.light_index_words[0] = 0u;      // no active cluster at all
+            break;
+        }
+        const uint32_t t = tile * kLlWarps + warp;                         // this warp's active cluster (compacted-list position)
+        const bool have = t < nactive;
+        const uint32_t* crow = counts + (size_t)t * light_blocks;
+        // ---- 1. hits of the cluster, capped at the reference's 256
+        uint32_t count = 0u;
+        constexpr int kKeep = 8;                                          // block counts kept in registers: 8 x 32 blocks = 131 072 lights
+        uint32_t kept[kKeep];
+#pragma unroll
+        for (int k = 0; k < kKeep; ++k) {
+            const uint32_t b = (uint32_t)k * 32u + lane;
+            kept[k] = (have && b < light_blocks) ? __ldcg(crow + b) : 0u;
+            count += kept[k];
+        }
+        if (have) for (uint32_t b = (uint32_t)kKeep * 32u + lane; b < light_blocks; b += 32u) count += __ldcg(crow + b);
+        count = min(__reduce_add_sync(0xFFFFFFFFu, count), (uint32_t)ORBIT_MAX_LIGHTS_PER_CLUSTER);
+        if (lane == 0u) s_cnt[warp] = count;
+        __syncthreads();
+        uint32_t before = 0u, total = 0u;
+#pragma unroll
+        for (int w = 0; w < kLlWarps; ++w) { const uint32_t v = s_cnt[w]; if ((uint32_t)w < warp) before += v; total += v; }
+        // ---- 2. the tile's range in the global list: look-back over tiles in compacted-list order
+        if (warp == 0u) {
+            const uint32_t off = lookback_exclusive(p.scan, epoch, tile, total);
+            if (lane == 0u) {
+                s_base = off;
+                if (tile == ntiles - 1u) {
+                    p.light_index_words[0] = off + total;
+                    if ((uint64_t)off + total > p.capacity_indices) *p.overflow_flag = 1u;
+                }
+            }
+        }
+        __syncthreads();
+        if (have) {
+            const uint32_t off = s_base + before;
+            const uint32_t idx = __ldcg(p.unique_clusters + 4u + t);
+            if (lane == 0u) { p.offset_count_image[2u * (size_t)idx] = off; p.offset_count_image[2u * (size_t)idx + 1u] = count; }
+            // ---- 3. blocks in ascending order, 32 per step: rank of a block's first hit = hits of all earlier blocks
+            const uint32_t* row = hits + (size_t)t * words_per_cluster;
+            uint32_t running = 0u;
+#pragma unroll 1
+            for (uint32_t b0 = 0u; b0 < light_blocks && running < count; b0 += 32u) {
+                const uint32_t b = b0 + lane;
+                uint32_t n = 0u;
+                if (b0 < (uint32_t)kKeep * 32u) {
+#pragma unroll
+                    for (int k = 0; k < kKeep; ++k) if (b0 == (uint32_t)k * 32u) n = kept[k];
+                } else if (b < light_blocks) {
+                    n = __ldcg(crow + b);
+                }
+                uint32_t inc = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= (uint32_t)d) inc += v;
+                }
+                uint32_t pos = running + inc - n;
+                if (n != 0u && pos < count) {
+                    // the block's 16 words in four 16-byte loads, all in flight at once (one word at a time made every hit block
+                    // a chain of 16 dependent L2 round trips: 32 us for the 99 clusters of C4)
+                    const uint4* r4 = reinterpret_cast<const uint4*>(row + (size_t)b * kLhWordsPerCta);
+                    const uint4 v0 = __ldcg(r4), v1 = __ldcg(r4 + 1), v2 = __ldcg(r4 + 2), v3 = __ldcg(r4 + 3);
+                    const uint32_t words[kLhWordsPerCta] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+                    for (uint32_t w = 0; w < kLhWordsPerCta; ++w) {
+                        uint32_t word = words[w];
+                        while (word != 0u && pos < count) {
+                            const uint32_t bit = (uint32_t)__ffs((int)word) - 1u;
+                            if ((uint64_t)off + pos < p.capacity_indices) p.light_index_words[1u + off + pos] = (b * kLhWordsPerCta + w) * 32u + bit;
+                            word &= word - 1u;
+                            ++pos;
+                        }
+                    }
+                }
+                running += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
+        }
+    }
+    if (tid == 0) scan_cta_exit(p.scan, epoch);
+}
+
+uint32_t light_hits_blocks(uint32_t n_lights) { return (n_lights + kLhLightsPerCta - 1u) / kLhLightsPerCta; }
+
+cudaError_t launch_light_hits(const ClusterParams& p, uint32_t* hits, uint32_t* counts, uint32_t words_per_cluster, uint32_t max_clusters, cudaStream_t s) {
+    const uint32_t gx = light_hits_blocks(p.info.global_light_count);
+    uint32_t gy = (max_clusters + kLhClusterChunk - 1u) / kLhClusterChunk;
+    if (gy > 16u) gy = 16u;                                      // chunks beyond that are strided over by the same CTAs
+    if (gx == 0u) return cudaSuccess;
+    light_hits_kernel<<<dim3(gx, gy ? gy : 1u), 256, 0, s>>>(p, hits, counts, words_per_cluster);
+    return cudaGetLastError();
+}
+cudaError_t launch_light_lists(const ClusterParams& p, const uint32_t* hits, const uint32_t* counts, uint32_t words_per_cluster, int grid, cudaStream_t s) {
+    light_lists_kernel<<<grid, kLlWarps * 32, 0, s>>>(p, hits, counts, words_per_cluster, light_hits_blocks(p.info.global_light_count));
+    return cudaGetLastError();
 }
 
 cudaError_t launch_mark_active(const ClusterParams& p, int grid, cudaStream_t s) {

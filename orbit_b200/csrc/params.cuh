@@ -72,6 +72,23 @@ struct SceneUpdateParams {
     uint32_t n_entities, visibility_capacity_words;
 };
 
+struct MeshletBoundsParams {
+    const uint8_t* vertices;             // vertex array, position = 3 x f32 at the start of each element
+    uint32_t vertex_stride;              // bytes (GpuMeshVertex: 32)
+    const uint32_t* meshlet_data;        // per meshlet at data_offset: vertex_count indices, then triangle_count x 3 bytes
+    uint8_t* meshlets;                   // OrbitMeshlet[]: counts / offsets in, bounding_sphere + cone out
+    uint32_t n_meshlets;
+    uint32_t* error_flag;                // host-mapped status word (a meshlet with more triangles than the kernel stages)
+};
+
+struct MeshBoundsParams {
+    const uint8_t* vertices;
+    uint32_t vertex_stride;
+    const uint32_t* vertex_ranges;       // per mesh: first vertex, vertex count
+    uint8_t* mesh_infos;                 // OrbitMeshInfo[]: bounding_sphere @0, aabb.min @16, aabb.max @32 written
+    uint32_t n_meshes;
+};
+
 struct HizBuildParams {
     const float* depth;
     float* texels;
@@ -88,6 +105,7 @@ struct ClusterParams {
     const float* depth;
     const uint8_t* lights;            // OrbitLightData[]
     float4* light_view;               // scratch: (view xyz, outer_radius or +inf for non-point lights)
+    float4* cluster_boxes;            // scratch (light-parallel path, else nullptr): view-space box lo / hi per compacted-list slot
     uint32_t* tile_masks;
     uint32_t* depth_bounds;           // 2 words per cluster
     uint32_t* unique_clusters;        // 4-word header + indices
@@ -111,11 +129,16 @@ cudaError_t launch_draws_from_masks(const MeshletCullParams& p, const uint32_t* 
 cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t);
 int entity_cull_max_ctas_per_sm();
 cudaError_t launch_hiz_build(const HizBuildParams&, cudaStream_t);
+cudaError_t launch_meshlet_bounds(const MeshletBoundsParams&, int grid, cudaStream_t);
+cudaError_t launch_mesh_bounds(const MeshBoundsParams&, int grid, cudaStream_t);
 cudaError_t launch_scene_update(const SceneUpdateParams&, cudaStream_t);
 cudaError_t launch_mark_active(const ClusterParams&, int grid, cudaStream_t);
 cudaError_t launch_compact_clusters(const ClusterParams&, cudaStream_t);
 cudaError_t launch_light_view(const ClusterParams&, cudaStream_t);
 cudaError_t launch_light_culling(const ClusterParams&, int grid, cudaStream_t);
+uint32_t light_hits_blocks(uint32_t n_lights);
+cudaError_t launch_light_hits(const ClusterParams&, uint32_t* hits, uint32_t* counts, uint32_t words_per_cluster, uint32_t max_clusters, cudaStream_t);
+cudaError_t launch_light_lists(const ClusterParams&, const uint32_t* hits, const uint32_t* counts, uint32_t words_per_cluster, int grid, cudaStream_t);
 cudaError_t launch_draws_scatter(const uint32_t* src, uint64_t src_capacity, uint32_t* dst, uint32_t dst_first, uint32_t total_count,
                                  uint64_t dst_capacity, int grid, cudaStream_t s, const uint32_t* rank_counts, uint32_t rank, uint32_t world);
 

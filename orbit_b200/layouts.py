@@ -122,7 +122,7 @@ class ClusterParams(C.Structure):
 
 class Status(C.Structure):
     _fields_ = [("dispatch_overflow", C.c_uint32), ("draw_overflow", C.c_uint32), ("light_index_overflow", C.c_uint32),
-                ("visibility_overflow", C.c_uint32)]
+                ("visibility_overflow", C.c_uint32), ("asset_error", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class SceneUpdate(C.Structure):

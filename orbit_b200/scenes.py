@@ -339,6 +339,81 @@ def orthographic_view(eye, direction, width, height, half_width, near, far, up=(
                 projection_type=L.PROJ_ORTHOGRAPHIC, near=near, far=far, half_width=half_width)
 
 
+def _quat_from_rotation_arc(a, b):
+    """glam Quat::from_rotation_arc for unit vectors (general branch): (cross(a,b), 1 + dot(a,b)) normalised; (x,y,z,w)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    q = np.concatenate([np.cross(a, b), [1.0 + float(np.dot(a, b))]])
+    return q / np.linalg.norm(q)
+
+
+def frustum_split(near, far, lam, ratio):
+    """math.rs:64-69."""
+    uniform = near + (far - near) * ratio
+    log = near * (far / near) ** ratio
+    return log * lam + (1.0 - lam) * uniform
+
+
+def perspective_corners(fovy, aspect, near, far):
+    """math.rs:149-168: the 8 view-space corners of a sub-frustum."""
+    th, tv = np.tan(fovy / 2.0) * aspect, np.tan(fovy / 2.0)
+    xn, yn, xf, yf = near * th, near * tv, far * th, far * tv
+    return np.array([[-xn, -yn, -near, 1.0], [xn, -yn, -near, 1.0], [xn, yn, -near, 1.0], [-xn, yn, -near, 1.0],
+                     [-xf, -yf, -far, 1.0], [xf, -yf, -far, 1.0], [xf, yf, -far, 1.0], [-xf, yf, -far, 1.0]])
+
+
+SUN_ORIENTATION = _quat_from_rotation_arc((0.0, 0.0, 1.0), np.array([-1.0, 1.0, 1.0]) / np.sqrt(3.0))   # app.rs:593
+
+
+def cascade_views(camera, n_cascades=4, lam=0.8, max_shadow_distance=32.0, resolution=2048, orientation=SUN_ORIENTATION,
+                  min_mesh_lod=0, max_mesh_lod=7):
+    """The orthographic shadow-cascade views of ShadowRenderer::render_cascaded_shadow (shadow_renderer.rs:466-712) for a
+    perspective `camera` View, restated step by step (host-side data generation: evaluated in float64, rounded to f32 where
+    the CullInfo is packed): split distances (lambda 0.8, max distance 32, :469-476), sub-frustum corners in light space
+    (:478-486), bounding sphere of the corners (:488-505), forward offset (:510-524), texel snapping (:526-532), light matrix =
+    translate(-centre') * rotate(inverse orientation) (:540), near = -radius - 80 / far = radius (:542-543), cull planes = the 6
+    planes of the NON-reversed orthographic matrix (:622-630) followed by those of the first 5 camera planes, taken in light
+    space, whose normal has z >= 0 (:632-640) — 6 to 11 planes; pass 0, LOD range min..max+1 for cascades 0-1 and 2..max+1 for
+    cascades 2-3 (:697-700), LOD target = light_matrix * camera position (:703)."""
+    assert camera.projection_type == L.PROJ_PERSPECTIVE
+    qi = np.array([-orientation[0], -orientation[1], -orientation[2], orientation[3]])    # direction.inverse() of a unit quaternion
+    light_rot = np.eye(4); light_rot[:3, :3] = _quat_to_mat(qi[None])[0]
+    view_to_world = np.linalg.inv(camera.view)
+    cam_pos = view_to_world[:3, 3]
+    view_to_light = light_rot @ view_to_world
+    cam_vp = camera.projection_matrix @ camera.view
+    out = []
+    for i in range(n_cascades):
+        near = frustum_split(camera.near, max_shadow_distance, lam, i / n_cascades)
+        far = frustum_split(camera.near, max_shadow_distance, lam, (i + 1) / n_cascades)
+        corners = (view_to_light @ perspective_corners(camera.fov, camera.aspect, near, far).T).T
+        corners = corners / corners[:, 3:4]
+        centre = corners.sum(axis=0) / 8.0
+        cmin, cmax = corners[:, :3].min(axis=0), corners[:, :3].max(axis=0)
+        radius = float(np.sqrt(max(np.sum((corners[:, :3] - centre[:3]) ** 2, axis=1))))
+        fwd = view_to_light[:3, 2]                                           # z_axis of view_to_light
+        fa = (fwd + 1.0) / 2.0
+        lo, hi = cmin - centre[:3], cmax - centre[:3]
+        offset = lo + (hi - lo) * fa - radius * fwd                          # lerp_element_wise(min, max, a) - radius * sign
+        texel = radius * 2.0 / resolution
+        centre2 = np.floor((centre[:3] + offset) / texel) * texel
+        T = np.eye(4); T[:3, 3] = -centre2
+        light_matrix = T @ light_rot
+        near_clip, far_clip = -radius - 80.0, radius
+        P = orthographic_rh(-radius, radius, -radius, radius, far_clip, near_clip)          # reverse z (:545-552)
+        light_planes = [normalize_plane(pl) for pl in frustum_planes_from_matrix(
+            orthographic_rh(-radius, radius, -radius, radius, near_clip, far_clip))]         # non-reversed on purpose (:622-630)
+        clip_to_light = cam_vp @ np.linalg.inv(light_matrix)
+        cam_planes = [normalize_plane(pl) for pl in frustum_planes_from_matrix(clip_to_light)[:5]]
+        cam_planes = [pl for pl in cam_planes if pl[2] >= 0.0]                               # dot(plane.xyz, Z) >= 0 (:636)
+        planes = np.array(light_planes + cam_planes)
+        lod_range = (min_mesh_lod, max_mesh_lod + 1) if i < 2 else (2, max_mesh_lod + 1)
+        target = (light_matrix @ np.append(cam_pos, 1.0))[:3]
+        out.append(View(width=resolution, height=resolution, view=light_matrix, projection_matrix=P, planes=planes,
+                        projection_type=L.PROJ_ORTHOGRAPHIC, near=near_clip, far=far_clip, half_width=radius,
+                        lod_target_view=tuple(float(v) for v in target), lod_range=lod_range))
+    return out
+
+
 def make_depth(scene, view, max_entities=None):
     """Reverse-Z depth buffer: every entity in front of the camera is splatted as a screen-space disc at its
     centre depth (max-blend = nearest wins), sky = 0.0. Deterministic; generated once per (scene, view)."""

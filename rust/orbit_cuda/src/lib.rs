@@ -106,7 +106,7 @@ pub struct OrbitClusterParams { pub info: OrbitClusterCullInfo, pub z_scale: f32
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
-pub struct OrbitStatus { pub dispatch_overflow: u32, pub draw_overflow: u32, pub light_index_overflow: u32, pub visibility_overflow: u32 }
+pub struct OrbitStatus { pub dispatch_overflow: u32, pub draw_overflow: u32, pub light_index_overflow: u32, pub visibility_overflow: u32, pub asset_error: u32, pub reserved: [u32; 3] }
 
 extern "C" {
     pub fn orbit_abi_version() -> i32;
@@ -142,6 +142,10 @@ extern "C" {
                                   rank_record_counts: *const u32, world: u32, rank_capacity_records: u64,
                                   draw_command_buffer: *mut c_void, capacity_draws: u64, stream: *mut c_void) -> i32;
     pub fn orbit_scene_update(ctx: *mut orbit_ctx, update: *const OrbitSceneUpdate, stream: *mut c_void) -> i32;
+    pub fn orbit_meshlet_bounds(ctx: *mut orbit_ctx, vertices: *const c_void, vertex_stride: u32, meshlet_data: *const u32, meshlets: *mut c_void,
+                                n_meshlets: u32, stream: *mut c_void) -> i32;
+    pub fn orbit_mesh_bounds(ctx: *mut orbit_ctx, vertices: *const c_void, vertex_stride: u32, vertex_ranges: *const u32, mesh_infos: *mut c_void,
+                             n_meshes: u32, stream: *mut c_void) -> i32;
     pub fn orbit_draws_scatter(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, src_capacity_draws: u64, dst_draw_buffer: *mut c_void,
                                dst_first: u32, total_count: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
 }

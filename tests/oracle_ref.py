@@ -54,6 +54,8 @@ def lib():
         h.oracle_entity_cull.argtypes = [C.POINTER(L.CullInfo), C.POINTER(L.SceneBuffers), vp, u32, u32, vp, u64, C.POINTER(Stats)]
         h.oracle_meshlet_cull.restype = u64
         h.oracle_meshlet_cull.argtypes = [C.POINTER(L.CullInfo), C.POINTER(L.SceneBuffers), vp, u32, u32, vp, vp, u64, vp, C.POINTER(Stats)]
+        h.oracle_meshlet_bounds.restype = C.c_int; h.oracle_meshlet_bounds.argtypes = [vp, u32, vp, vp, u32]
+        h.oracle_mesh_bounds.restype = None; h.oracle_mesh_bounds.argtypes = [vp, u32, vp, vp, u32]
         h.oracle_mark_active.argtypes = [C.POINTER(L.ClusterParams), vp, vp, vp]
         h.oracle_compact_clusters.restype = u32; h.oracle_compact_clusters.argtypes = [C.POINTER(L.ClusterParams), vp, vp]
         h.oracle_light_culling.restype = u64
@@ -112,6 +114,11 @@ class HostScene:
         sb.entity_draw_count = s.n_entities
         sb.draw_begin, sb.draw_end = self.draw_begin, self.draw_end
         return sb
+
+    def reset_visibility(self):
+        """Frame 0 of another view: both bitmasks back to zero (the harness's definition of the never-initialised masks)."""
+        self.entity_visibility[:] = 0
+        self.meshlet_visibility[:] = 0
 
     def update_pyramid(self, depth):
         self.hiz_info, self.hiz_texels = hiz_build(depth)
@@ -203,3 +210,14 @@ def scene_update(transforms, mesh_slots, visibility_offsets, mesh_infos, cursor,
                                     _p(entity_data), _p(draws))
     count = int(draws[:4].view(np.uint32)[0])
     return entity_data[:count], draws[:4 + 12 * count], int(ovf)
+
+
+def asset_bounds(vertices, meshlet_data, meshlets, mesh_infos, vertex_ranges):
+    """compute_meshlets' bounds (mesh.rs:321-338 = meshopt::compute_meshlet_bounds) + MeshData::compute_bounds (mesh.rs:192-215)
+    on copies of `meshlets` / `mesh_infos`. Returns (meshlets, mesh_infos, meshlets skipped for > 128 triangles)."""
+    ml, mi = np.ascontiguousarray(meshlets).copy(), np.ascontiguousarray(mesh_infos).copy()
+    v, d, r = np.ascontiguousarray(vertices), np.ascontiguousarray(meshlet_data, dtype=np.uint32), np.ascontiguousarray(vertex_ranges, dtype=np.uint32)
+    skipped = lib().oracle_meshlet_bounds(v.ctypes.data, v.dtype.itemsize, d.ctypes.data, ml.ctypes.data, len(ml))
+    lib().oracle_mesh_bounds(v.ctypes.data, v.dtype.itemsize, r.ctypes.data, mi.ctypes.data, len(mi))
+    return ml, mi, int(skipped)
+

@@ -67,3 +67,19 @@ def test_clusters_no_lights_and_sky_only(gpu_context, oracle):
     st = ClusterSettings(screen_resolution=(256, 128))
     na, total = _run(gpu_context, oracle, sc, view, depth, lights, st)
     assert na == 0 and total == 0
+
+
+def test_clusters_cta_per_cluster_fallback(oracle, monkeypatch):
+    """Grids whose (cluster, light) bit matrix exceeds the scratch budget take the CTA-per-cluster kernel; forced here with a
+    zero budget on a context of its own — same lists as the light-parallel path and the oracle."""
+    from orbit_b200.passes import ClusterSettings, Context
+    monkeypatch.setenv("ORBIT_LIGHT_HITS_BUDGET_MB", "0")
+    ctx = Context(0)
+    monkeypatch.delenv("ORBIT_LIGHT_HITS_BUDGET_MB")
+    sc, view = scenes.config_c4(scale=0.02)
+    depth = scenes.make_depth(sc, view)
+    lights = scenes.make_lights(scenes.SEEDS["C4"], 4096, sc.aabb_min, sc.aabb_max)
+    st = ClusterSettings(screen_resolution=(1920, 1080), z_slice_count=24, tile_size_px=120)
+    na, total = _run(ctx, oracle, sc, view, depth, lights, st)
+    assert na > 0 and total > 0
+    ctx.close()
