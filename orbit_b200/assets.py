@@ -146,11 +146,11 @@ class AssetBuilder:
         vertices, data, meshlets, infos, ranges = self.arrays()
         d_v, d_d, d_m = context.upload(vertices), context.upload(data), context.upload(meshlets)
         d_i, d_r = context.upload(infos), context.upload(ranges)
-        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        s = C.c_void_p(torch.cuda.current_stream(context.device).cuda_stream)
         p = lambda t: C.c_void_p(t.data_ptr())
         _lib.check(lib.orbit_meshlet_bounds(context._h, p(d_v), vertex_dtype.itemsize, p(d_d), p(d_m), len(meshlets), s), "orbit_meshlet_bounds")
         _lib.check(lib.orbit_mesh_bounds(context._h, p(d_v), vertex_dtype.itemsize, p(d_r), p(d_i), len(infos), s), "orbit_mesh_bounds")
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(context.device)
         return (vertices, data, d_m.cpu().numpy().view(L.meshlet_dtype).reshape(-1).copy(),
                 d_i.cpu().numpy().view(L.mesh_info_dtype).reshape(-1).copy(), ranges)
 

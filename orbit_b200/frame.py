@@ -147,7 +147,7 @@ class PreparedFrame:
         self._hw = (w, h)
 
     def _stream(self):
-        return self._C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return self._C.c_void_p(torch.cuda.current_stream(self.context.device).cuda_stream)
 
     def entity(self, late, s=None):
         C, lib, p = self._C, self._lib, self._ptr
@@ -207,7 +207,7 @@ class PreparedFrame:
         if not overlap_main_entity:
             self.meshlet(True, s); self.entity("main", s); self.meshlet("main", s)
             return
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.context.device)
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=self.context.device, priority=-1)   # high priority: its 40 CTAs must get their SM
             # slots before the persistent CTAs of the late meshlet test fill every SM (kernel-node priority is captured with the stream's)

@@ -124,8 +124,9 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(context=None):
+    """torch's current stream ON THE CONTEXT'S DEVICE (the thread's current device may be another one)."""
+    return C.c_void_p(torch.cuda.current_stream(context.device if context is not None else None).cuda_stream)
 
 
 class Context:
@@ -135,8 +136,7 @@ class Context:
     def __init__(self, device=0):
         if not torch.cuda.is_available():
             raise RuntimeError("orbit_b200 needs a CUDA device (no CPU fallback)")
-        self.device = torch.device("cuda", device)
-        torch.cuda.set_device(self.device)
+        self.device = torch.device("cuda", device)     # the caller's current device is left alone: the C ABI switches per call
         self._h = C.c_void_p()
         _lib.check(_lib.lib().orbit_ctx_create(device, C.byref(self._h)), "orbit_ctx_create")
         self._transients = {}
@@ -248,7 +248,7 @@ class DepthPyramid:
         """depth_buffer: float32 device tensor [H, W] (reverse-Z)."""
         h, w = depth_buffer.shape
         assert (w, h) == self.size and depth_buffer.dtype == torch.float32 and depth_buffer.is_contiguous()
-        _lib.check(_lib.lib().orbit_hiz_build(self.context._h, self._h, _ptr(depth_buffer), w, h, _stream()), "orbit_hiz_build")
+        _lib.check(_lib.lib().orbit_hiz_build(self.context._h, self._h, _ptr(depth_buffer), w, h, _stream(self.context)), "orbit_hiz_build")
         self.usable = True
 
     def get_current(self):
@@ -276,7 +276,7 @@ def create_meshlet_dispatch_command(context, name, assets, scene, cull_info):
     sb = _scene_buffers(assets, scene, cull_info)
     pyr = cull_info.occlusion_culling.depth_pyramid
     _lib.check(_lib.lib().orbit_entity_cull(context._h, C.byref(g), C.byref(sb), pyr._h if pyr is not None else None,
-                                            _ptr(buf), cap, _stream()), "orbit_entity_cull")
+                                            _ptr(buf), cap, _stream(context)), "orbit_entity_cull")
     return g, buf
 
 
@@ -291,7 +291,7 @@ def create_meshlet_draw_commands(context, name, assets, scene, cull_info, meshle
     pyr = cull_info.occlusion_culling.depth_pyramid
     _lib.check(_lib.lib().orbit_meshlet_cull(context._h, C.byref(g), C.byref(sb), pyr._h if pyr is not None else None,
                                              _ptr(meshlet_dispatch_buffer), rcap, _ptr(buf), dcap,
-                                             _ptr(task_payloads), _stream()), "orbit_meshlet_cull")
+                                             _ptr(task_payloads), _stream(context)), "orbit_meshlet_cull")
     return buf
 
 
@@ -367,5 +367,5 @@ def compute_clusters(context, settings, view_matrix, projection_matrix, near, de
     index = context.create_transient(name + "_light_index_buffer", 4 + 4 * cap)
     _lib.check(_lib.lib().orbit_light_cluster(context._h, C.byref(p), _ptr(depth_buffer), _ptr(scene.light_data_buffer),
                                               _ptr(masks), _ptr(bounds), _ptr(unique), _ptr(image), _ptr(index), cap,
-                                              _stream()), "orbit_light_cluster")
+                                              _stream(context)), "orbit_light_cluster")
     return GraphClusterInfo(image, index, masks, bounds, unique, (cx, cy), cz, p.z_scale, p.z_bias, settings.tile_px_size()), p

@@ -57,17 +57,34 @@ def test_context_from_worker_threads(oracle):
     assert not errors, errors
 
 
-def test_stage_call_with_another_device_current(gpu_context, oracle):
-    """The caller's current device is not the context's: the entry points switch and restore (needs 2 GPUs)."""
+def test_stage_call_with_another_device_current(oracle):
+    """The caller's current device is not the context's: every entry point makes the context's device current for the call and
+    restores the caller's (needs 2 GPUs). Driven through the raw C ABI from a worker thread whose current device stays 0."""
     if torch.cuda.device_count() < 2:
         pytest.skip("one GPU")
     errors = []
 
     def worker():
-        torch.cuda.set_device(0)          # thread-current device 0, context on device 1
-        _run_two_frames(1, oracle, errors, "dev1-from-dev0")
-        if torch.cuda.current_device() != 0:
-            errors.append(("restore", "current device changed to %d" % torch.cuda.current_device()))
+        try:
+            from orbit_b200 import _lib
+            from orbit_b200.passes import Context, DepthPyramid
+            torch.cuda.set_device(0)
+            ctx = Context(1)                                   # orbit_ctx_create(1) while device 0 is current
+            depth = np.random.default_rng(5).random((270, 480), dtype=np.float32)
+            d_depth = torch.from_numpy(depth).to(ctx.device)
+            pyr = DepthPyramid(ctx, "guard", (480, 270))
+            stream = torch.cuda.Stream(device=1)
+            stream.wait_stream(torch.cuda.current_stream(ctx.device))
+            rc = _lib.lib().orbit_hiz_build(ctx._h, pyr._h, C.c_void_p(d_depth.data_ptr()), 480, 270, C.c_void_p(stream.cuda_stream))
+            assert rc == 0, rc
+            stream.synchronize()
+            _, ref = oracle.hiz_build(depth)
+            assert np.array_equal(pyr.texels.cpu().numpy().view(np.uint32), ref.view(np.uint32)), "pyramid built on device 1"
+            assert torch.cuda.current_device() == 0, "current device changed to %d" % torch.cuda.current_device()
+            ctx.close()
+            assert torch.cuda.current_device() == 0
+        except BaseException as e:      # noqa: BLE001
+            errors.append(repr(e))
     t = threading.Thread(target=worker); t.start(); t.join()
     assert not errors, errors
 
