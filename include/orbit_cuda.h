@@ -229,18 +229,18 @@ int orbit_draws_scatter_ranked(orbit_ctx* ctx, const void* src_draw_buffer, uint
  * that submits the draws). orbit_meshlet_test = the test half of orbit_meshlet_cull: visibility words are written as usual,
  * and for every dispatch record r < count one entry {u32 draw mask, u32 entity, u32 meshlet offset, u32 1} goes to
  * record_masks[r] (16-byte aligned, capacity_records entries); no draw commands are produced.
- * orbit_record_masks_scatter_ranked stores this rank's entries into dst (usually peer-mapped) at entry index
- * sum(rank_record_counts[0..rank)) — rank_record_counts = the all-gathered dispatch-buffer headers, read on the device.
- * orbit_draws_from_masks runs on the receiving rank: recounts the survivors of the combined list and emits the
- * MeshletDrawCommandBuffer in canonical order (command words are read from scene->meshlets). Counts above
- * rank_capacity_records are clamped to it. */
+ * orbit_record_masks_put stores this rank's entries (count = the dispatch buffer's header, read on the device, clamped to
+ * capacity_records) into dst_region and the count into *dst_count — both usually peer-mapped memory of the receiving rank,
+ * which keeps one region of `region_stride_records` entries and one count word per rank; no rank needs another rank's count,
+ * so the exchange needs no collective besides a closing fence.
+ * orbit_draws_from_masks runs on the receiving rank: reads the regions in rank order (rank-major = canonical record order),
+ * recounts the survivors and emits the MeshletDrawCommandBuffer (command words are read from scene->meshlets). */
 int orbit_meshlet_test(orbit_ctx* ctx, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
                        const void* meshlet_dispatch_buffer, uint64_t capacity_records, void* record_masks, void* stream);
-int orbit_record_masks_scatter_ranked(orbit_ctx* ctx, const void* src_record_masks, uint64_t src_capacity_records,
-                                      void* dst_record_masks, const uint32_t* rank_record_counts, uint32_t rank, uint32_t world,
-                                      uint64_t dst_capacity_records, void* stream);
-int orbit_draws_from_masks(orbit_ctx* ctx, const OrbitSceneBuffers* scene, const void* record_masks, uint64_t capacity_records,
-                           const uint32_t* rank_record_counts, uint32_t world, uint64_t rank_capacity_records,
+int orbit_record_masks_put(orbit_ctx* ctx, const void* src_record_masks, const void* meshlet_dispatch_buffer, uint64_t capacity_records,
+                           void* dst_region, uint32_t* dst_count, void* stream);
+int orbit_draws_from_masks(orbit_ctx* ctx, const OrbitSceneBuffers* scene, const void* record_masks, uint64_t region_stride_records,
+                           const uint32_t* region_counts, uint32_t n_regions /* <= 16 */,
                            void* draw_command_buffer, uint64_t capacity_draws, void* stream);
 
 /* Peer-visible device memory for that assembly: one process per GPU, so a rank's output buffer is shared with the

@@ -41,9 +41,8 @@ PROTOTYPES = {
                                              C.c_void_p]),
     "orbit_meshlet_test": (C.c_int, [C.c_void_p, C.POINTER(L.CullInfo), C.POINTER(L.SceneBuffers), C.c_void_p, C.c_void_p, C.c_uint64,
                                      C.c_void_p, C.c_void_p]),
-    "orbit_record_masks_scatter_ranked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
-                                                    C.c_uint64, C.c_void_p]),
-    "orbit_draws_from_masks": (C.c_int, [C.c_void_p, C.POINTER(L.SceneBuffers), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64,
+    "orbit_record_masks_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "orbit_draws_from_masks": (C.c_int, [C.c_void_p, C.POINTER(L.SceneBuffers), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
                                          C.c_void_p, C.c_uint64, C.c_void_p]),
     "orbit_meshlet_bounds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "orbit_mesh_bounds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),

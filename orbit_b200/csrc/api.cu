@@ -504,24 +504,22 @@ int orbit_meshlet_test(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScene
     return meshlet_stage(c, cull, scene, hiz, meshlet_dispatch_buffer, capacity_records, nullptr, 0, nullptr, record_masks, stream);
 }
 
-int orbit_record_masks_scatter_ranked(orbit_ctx* c, const void* src_record_masks, uint64_t src_capacity_records, void* dst_record_masks,
-                                      const uint32_t* rank_record_counts, uint32_t rank, uint32_t world, uint64_t dst_capacity_records,
-                                      void* stream) {
-    if (!c || !src_record_masks || !dst_record_masks || !rank_record_counts || world == 0u || rank >= world) return ORBIT_ERR_INVALID_ARGUMENT;
-    if (((uintptr_t)src_record_masks | (uintptr_t)dst_record_masks) & 15u) return ORBIT_ERR_INVALID_ARGUMENT;
+int orbit_record_masks_put(orbit_ctx* c, const void* src_record_masks, const void* meshlet_dispatch_buffer, uint64_t capacity_records,
+                           void* dst_region, uint32_t* dst_count, void* stream) {
+    if (!c || !src_record_masks || !meshlet_dispatch_buffer || !dst_region || !dst_count) return ORBIT_ERR_INVALID_ARGUMENT;
+    if ((((uintptr_t)src_record_masks | (uintptr_t)dst_region) & 15u) || (((uintptr_t)meshlet_dispatch_buffer | (uintptr_t)dst_count) & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
     GUARD(c);
-    CK(launch_record_masks_scatter((const uint4*)src_record_masks, (uint4*)dst_record_masks, rank_record_counts, rank, world,
-                                   src_capacity_records, dst_capacity_records, c->sm_count * 8, (cudaStream_t)stream));
+    CK(launch_record_masks_put((const uint4*)src_record_masks, (const uint32_t*)meshlet_dispatch_buffer, (uint4*)dst_region, dst_count,
+                               capacity_records, c->sm_count * 8, (cudaStream_t)stream));
     c->launches += 1;
     return ORBIT_OK;
 }
 
-int orbit_draws_from_masks(orbit_ctx* c, const OrbitSceneBuffers* scene, const void* record_masks, uint64_t capacity_records,
-                           const uint32_t* rank_record_counts, uint32_t world, uint64_t rank_capacity_records,
-                           void* draw_command_buffer, uint64_t capacity_draws, void* stream) {
-    if (!c || !scene || !scene->meshlets || !record_masks || !rank_record_counts || world == 0u || !draw_command_buffer) return ORBIT_ERR_INVALID_ARGUMENT;
+int orbit_draws_from_masks(orbit_ctx* c, const OrbitSceneBuffers* scene, const void* record_masks, uint64_t region_stride_records,
+                           const uint32_t* region_counts, uint32_t n_regions, void* draw_command_buffer, uint64_t capacity_draws, void* stream) {
+    if (!c || !scene || !scene->meshlets || !record_masks || !region_counts || n_regions == 0u || n_regions > 16u || !draw_command_buffer) return ORBIT_ERR_INVALID_ARGUMENT;
     if (((uintptr_t)record_masks & 15u) || ((uintptr_t)draw_command_buffer & 3u) || ((uintptr_t)scene->meshlets & 15u)) return ORBIT_ERR_INVALID_ARGUMENT;
-    if (capacity_records > 0xFFFFFFFFull) capacity_records = 0xFFFFFFFFull;
+    if (region_stride_records > 0xFFFFFFFFull) return ORBIT_ERR_INVALID_ARGUMENT;
     GUARD(c);
     MeshletCullParams p{};
     p.meshlets = (const uint4*)scene->meshlets;
@@ -532,14 +530,14 @@ int orbit_draws_from_masks(orbit_ctx* c, const OrbitSceneBuffers* scene, const v
     p.draw_total = c->counters + 4;
     p.chunk_parity = c->counters + 6;
     p.chunk_counts = c->chunk_counts;
-    p.capacity_records = capacity_records;
+    p.capacity_records = 0xFFFFFFFFull;
     p.capacity_draws = capacity_draws;
     p.dispatch_words = c->counters + 16;      // a 3-word dispatch header written by the recount kernel
+    p.region_counts = region_counts; p.region_stride = region_stride_records; p.n_regions = n_regions;
     p.trace_emit = next_trace(c);
     if (c->emit_occupancy <= 0) c->emit_occupancy = meshlet_emit_max_ctas_per_sm();
     const int emit_per_sm = c->emit_occupancy < 2 ? (c->emit_occupancy > 0 ? c->emit_occupancy : 1) : 2;
-    CK(launch_draws_from_masks(p, rank_record_counts, world, rank_capacity_records, c->counters + 16, c->sm_count * 4,
-                               c->sm_count * emit_per_sm, (cudaStream_t)stream));
+    CK(launch_draws_from_masks(p, c->counters + 16, c->sm_count * 4, c->sm_count * emit_per_sm, (cudaStream_t)stream));
     c->launches += 2;
     return ORBIT_OK;
 }

@@ -35,9 +35,15 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
     pdl_wait();
     ORBIT_TRACE_STAMP(p.scan.trace, 0, 0);
     const unsigned int epoch = scan_epoch(p.scan);
+    // Tiles are handed out by an atomic ticket in BOTH variants, so the CTAs that own a tile's predecessors are always running
+    // or finished and the waits below (look-back, flat gather) cannot deadlock, whatever else shares the GPU and in whatever
+    // order CTAs are dispatched. The look-back variant waits for its ticket; the flat variant (small, latency-bound grids) does
+    // not: it requests the draw words of tile blockIdx.x while the ticket is in flight — CTAs are dispatched in index order in
+    // practice, so the guess is right and the atomic costs no dependent round trip — and re-requests them in the rare case
+    // that the ticket disagrees.
+    if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
     uint32_t tile = blockIdx.x;
     if (!kFlat) {
-        if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
         __syncthreads();
         tile = s_tile;
     }
@@ -45,12 +51,25 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
 
     // The draw words are requested before the device-side count is known (gid < draw_end <= the host's
     // entity_draw_count, which sized the buffer): one dependent round trip less on a latency-bound kernel.
-    const uint32_t gid = p.draw_begin + tile * kEcThreads + tid;
+    uint32_t gid = p.draw_begin + tile * kEcThreads + tid;
     uint32_t entity_index = 0u, mesh_index = 0u, vis_offset = 0u;
     if (gid < p.draw_end) {
         entity_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 0u);
         mesh_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 1u);
         vis_offset = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 2u);
+    }
+    if (kFlat) {
+        __syncthreads();
+        if (s_tile != tile) {                                    // out-of-order dispatch: take the ticket's tile instead
+            tile = s_tile;
+            gid = p.draw_begin + tile * kEcThreads + tid;
+            entity_index = mesh_index = vis_offset = 0u;
+            if (gid < p.draw_end) {
+                entity_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 0u);
+                mesh_index = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 1u);
+                vis_offset = __ldg(p.entity_draw_words + 1u + 3u * (size_t)gid + 2u);
+            }
+        }
     }
     const uint32_t count = min(__ldg(p.entity_draw_words), p.draw_end);
     ORBIT_TRACE_STAMP(p.scan.trace, 0, 1 + 0 * (count + epoch));

@@ -476,16 +476,9 @@ __global__ void __launch_bounds__(kLlWarps * 32) light_lists_kernel(const __grid
             // ---- 3. blocks in ascending order, 32 per step: rank of a block's first hit = hits of all earlier blocks
             const uint32_t* row = hits + (size_t)t * words_per_cluster;
             uint32_t running = 0u;
-#pragma unroll 1
-            for (uint32_t b0 = 0u; b0 < light_blocks && running < count; b0 += 32u) {
+            // one step = 32 blocks: n = this lane's block count; warp-uniform control flow (b0, running, count are uniform)
+            auto expand = [&](uint32_t b0, uint32_t n) {
                 const uint32_t b = b0 + lane;
-                uint32_t n = 0u;
-                if (b0 < (uint32_t)kKeep * 32u) {
-#pragma unroll
-                    for (int k = 0; k < kKeep; ++k) if (b0 == (uint32_t)k * 32u) n = kept[k];
-                } else if (b < light_blocks) {
-                    n = __ldcg(crow + b);
-                }
                 uint32_t inc = n;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -511,7 +504,16 @@ __global__ void __launch_bounds__(kLlWarps * 32) light_lists_kernel(const __grid
                     }
                 }
                 running += __shfl_sync(0xFFFFFFFFu, inc, 31);
-            }
+            };
+            // the kept counts are indexed by compile-time constants only: with a run-time select over kept[] inside a rolled
+            // loop the step at b0 = 32 received kept[0] on the device (C4: every hit in light blocks 32.. of some clusters was
+            // dropped; caught by the full-size C4 test, tools/debug/c4_lights.py shows the case)
+#pragma unroll
+            for (int k = 0; k < kKeep; ++k)
+                if ((uint32_t)k * 32u < light_blocks && running < count) expand((uint32_t)k * 32u, kept[k]);
+#pragma unroll 1
+            for (uint32_t b0 = (uint32_t)kKeep * 32u; b0 < light_blocks && running < count; b0 += 32u)
+                expand(b0, b0 + lane < light_blocks ? __ldcg(crow + b0 + lane) : 0u);
         }
     }
     if (tid == 0) scan_cta_exit(p.scan, epoch);

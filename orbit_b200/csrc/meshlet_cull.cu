@@ -912,14 +912,29 @@ __device__ __forceinline__ uint32_t select_set_bit(uint32_t m, uint32_t n) {
 //   3. the counts of the OTHER parity are zeroed for the next call and the parity word the next test kernel reads is
 //      flipped — no done-counter, fence or atomic on the way out (that exit chain was ~1/3 of this kernel's samples).
 constexpr int kEmitWarps = 8;
+constexpr uint32_t kMaxRegions = 16u;   // ranks of a sharded view (orbit_draws_from_masks)
 __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __grid_constant__ MeshletCullParams p) {
     __shared__ uint32_t s_prefix[kMaxChunks];            // inclusive survivor count up to chunk c
     __shared__ uint32_t s_warp_total[kEmitWarps];
     __shared__ uint32_t s_rec[kEmitWarps][4][32];
     __shared__ uint32_t s_payload[kEmitWarps][32 * 11];   // task-payload staging (only used when requested)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    __shared__ uint32_t s_region[kMaxRegions + 1];        // sharded view: first record of every rank's region of the entry array
     const bool want_payload = p.task_payloads != nullptr;
     pdl_wait();
+    if (p.n_regions != 0u && tid == 0) {
+        uint32_t acc = 0u;
+        for (uint32_t k = 0; k < p.n_regions; ++k) { s_region[k] = acc; acc += (uint32_t)min((uint64_t)__ldcg(p.region_counts + k), p.region_stride); }
+        s_region[p.n_regions] = acc;
+    }
+    if (p.n_regions != 0u) __syncthreads();
+    // record index -> entry index: identity, or (sharded view) rank k's records lie at k * region_stride
+    auto entry_of = [&](uint32_t rec) -> size_t {
+        if (p.n_regions == 0u) return rec;
+        uint32_t k = 0u;
+        while (k + 1u < p.n_regions && rec >= s_region[k + 1u]) ++k;
+        return (size_t)k * p.region_stride + (rec - s_region[k]);
+    };
     ORBIT_TRACE_STAMP(p.trace_emit, 3, 0);
     // both halves of the chunk counts are requested before the parity is known: one round trip instead of two
     uint32_t v0[8], v1[8];
@@ -974,6 +989,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
         const uint32_t o_begin = (uint32_t)(((uint64_t)total * gw) / GW);
         const uint32_t o_end = (uint32_t)(((uint64_t)total * (gw + 1u)) / GW);
         uint32_t* const sr = &s_rec[warp][0][0];
+        uint32_t* const stage = &s_payload[warp][0];          // command staging (the task-payload pass below runs after the emission)
         if (o_begin < o_end) {
             // chunk holding output o_begin: first c with P[c] > o_begin
             uint32_t lo = 0u, hi = nchunks - 1u;
@@ -1000,7 +1016,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
             };
             auto load_masks = [&](uint32_t r) -> uint4 {
                 const uint32_t my = r + lane;
-                return my < nrec ? __ldcg(p.draw_masks + my) : make_uint4(0u, 0u, 0u, 0u);
+                return my < nrec ? __ldcg(p.draw_masks + entry_of(my)) : make_uint4(0u, 0u, 0u, 0u);
             };
             // Four groups of 32 records in flight: a warp whose share of the outputs lies in a sparsely surviving stretch
             // walks many groups for its ~30 outputs, one dependent L2 round trip each (that tail was half of this kernel's
@@ -1041,25 +1057,38 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
                         __syncwarp();
                         const uint32_t l0 = o_begin > running ? o_begin - running : 0u;            // first local output of mine
                         const uint32_t l1 = min(step_total, o_end - running);                      // one past my last local output
-                        for (uint32_t ol = l0 + lane; ol < l1; ol += 32u) {
-                            uint32_t a = 0u, b = 31u;
+                        // 32 outputs per step: every lane builds its command (7 words) in shared memory, then the warp writes the
+                        // step's commands — contiguous in the output — as consecutive words (seven 128-byte stores instead of seven
+                        // 28-byte-strided ones that touch 28 sectors each; the emit kernel writes 28 B per survivor and was store-bound
+                        // at C5 scale)
+                        for (uint32_t ol0 = l0; ol0 < l1; ol0 += 32u) {
+                            const uint32_t ol = ol0 + lane;
+                            __syncwarp();
+                            if (ol < l1) {
+                                uint32_t a = 0u, b = 31u;
 #pragma unroll
-                            for (int it = 0; it < 5; ++it) {
-                                const uint32_t mid = (a + b) >> 1;
-                                if (sr[mid] > ol) b = mid; else a = mid + 1u;
+                                for (int it = 0; it < 5; ++it) {
+                                    const uint32_t mid = (a + b) >> 1;
+                                    if (sr[mid] > ol) b = mid; else a = mid + 1u;
+                                }
+                                const uint32_t r = a;
+                                const uint32_t excl = r ? sr[r - 1u] : 0u;
+                                const uint32_t j = select_set_bit(sr[32 + r], ol - excl);   // (ol-excl)-th survivor of the record
+                                const uint32_t mo = sr[96 + r];
+                                const uint32_t midx = (mo & 0x7FFFFFFFu) + j;
+                                // command words: from the side array the test kernel filled (x,y,z = vertex_offset, data_offset, packed
+                                // counts), or — pass 2, whose candidates do not carry them — from the meshlet itself
+                                uint4 cw;
+                                if (mo >> 31) { const uint4 mb = __ldg(p.meshlets + 2u * (size_t)midx + 1); cw = make_uint4(mb.y, mb.z, mb.w, 0u); }
+                                else cw = __ldcg(p.cmd_side + (size_t)(group_rec + r) * 32u + j);
+                                store_command(stage + lane * 7u, cw.x, cw.y, cw.z, sr[64 + r], midx);
                             }
-                            const uint32_t r = a;
-                            const uint32_t excl = r ? sr[r - 1u] : 0u;
-                            const uint32_t j = select_set_bit(sr[32 + r], ol - excl);   // (ol-excl)-th survivor of the record
-                            const uint32_t mo = sr[96 + r];
-                            const uint32_t midx = (mo & 0x7FFFFFFFu) + j;
-                            // command words: from the side array the test kernel filled (x,y,z = vertex_offset, data_offset, packed
-                            // counts), or — pass 2, whose candidates do not carry them — from the meshlet itself
-                            uint4 cw;
-                            if (mo >> 31) { const uint4 mb = __ldg(p.meshlets + 2u * (size_t)midx + 1); cw = make_uint4(mb.y, mb.z, mb.w, 0u); }
-                            else cw = __ldcg(p.cmd_side + (size_t)(group_rec + r) * 32u + j);
-                            const uint64_t idx = (uint64_t)running + ol;
-                            if (idx < p.capacity_draws) store_command(p.draw_words + 1u + idx * 7u, cw.x, cw.y, cw.z, sr[64 + r], midx);
+                            __syncwarp();
+                            const uint64_t first = (uint64_t)running + ol0;                 // index of this step's first command
+                            uint64_t n_out = min(32u, l1 - ol0);
+                            if (first >= p.capacity_draws) n_out = 0u; else if (first + n_out > p.capacity_draws) n_out = p.capacity_draws - first;
+                            uint32_t* const dst = p.draw_words + 1u + first * 7u;
+                            for (uint32_t w = lane; w < (uint32_t)n_out * 7u; w += 32u) dst[w] = stage[w];
                         }
                     }
                     running += step_total;
@@ -1085,7 +1114,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
         for (uint32_t base = gw * 32u; base < nrec; base += GW * 32u) {
             const uint32_t r = base + lane;
             uint4 e = make_uint4(0u, 0u, 0u, 0u);
-            if (r < nrec) e = __ldcg(p.draw_masks + r);
+            if (r < nrec) e = __ldcg(p.draw_masks + entry_of(r));
             uint32_t m = e.x;
             __syncwarp();
             st[lane * 11u] = __popc(m); st[lane * 11u + 1u] = e.y; st[lane * 11u + 2u] = e.z;
@@ -1111,17 +1140,16 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
 // ---------------------------------------------------------------------------------------------------------
 // Multi-GPU (meshlet ranges of one view): a rank that only TESTS its records ships the 16-byte
 // {draw mask, entity, meshlet offset, 1} entries instead of 28-byte draw commands (C3: 28 MB instead of 229 MB to the
-// rank that submits the draws); that rank lays the ranks' entries end to end — rank-major = canonical record order —
-// recounts the survivors per chunk and runs the ordinary emit kernel over the combined list.
+// rank that submits the draws) into its own region of that rank's entry array; the receiving rank reads the regions in rank
+// order — rank-major = canonical record order —, recounts the survivors per chunk and runs the ordinary emit kernel.
 //
-// Copies this rank's entries [0, own count) to dst[first ...), first = sum of the lower ranks' (clamped) record counts.
-__global__ void __launch_bounds__(256) record_masks_scatter_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
-                                                                   const uint32_t* __restrict__ rank_counts, uint32_t rank, uint32_t world,
-                                                                   uint64_t src_capacity, uint64_t dst_capacity) {
-    uint64_t first = 0u;
-    for (uint32_t r = 0; r < rank; ++r) first += min((uint64_t)__ldcg(rank_counts + r), src_capacity);
-    uint64_t n = min((uint64_t)__ldcg(rank_counts + rank), src_capacity);
-    if (first >= dst_capacity) n = 0u; else if (first + n > dst_capacity) n = dst_capacity - first;
+// Stores this rank's entries [0, own count) into its region of the receiving rank's entry array (dst_region: usually
+// peer-mapped, so these are NVLink stores) and its record count into dst_count — no rank needs another rank's count, so the
+// exchange has no collective besides the closing fence. The count comes from the dispatch buffer's header on the device.
+__global__ void __launch_bounds__(256) record_masks_put_kernel(const uint4* __restrict__ src, const uint32_t* __restrict__ dispatch_words,
+                                                               uint4* __restrict__ dst_region, uint32_t* __restrict__ dst_count, uint64_t capacity) {
+    const uint64_t n = min((uint64_t)__ldcg(dispatch_words), capacity);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *dst_count = (uint32_t)n;
     const uint64_t gsize = (uint64_t)gridDim.x * blockDim.x;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3u * gsize < n; i += 4u * gsize) {                          // four independent 16-byte stores in flight (NVLink)
@@ -1129,18 +1157,22 @@ __global__ void __launch_bounds__(256) record_masks_scatter_kernel(const uint4* 
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = __ldcg(src + i + (uint64_t)k * gsize);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) __stcg(dst + first + i + (uint64_t)k * gsize, v[k]);
+        for (int k = 0; k < 4; ++k) __stcg(dst_region + i + (uint64_t)k * gsize, v[k]);
     }
-    for (; i < n; i += gsize) __stcg(dst + first + i, __ldcg(src + i));
+    for (; i < n; i += gsize) __stcg(dst_region + i, __ldcg(src + i));
 }
 
 // Survivors per chunk of the combined list (same double-buffered scratch protocol as the test kernels, so the emit kernel
 // that follows cannot tell the difference) and the combined record count as a dispatch-buffer header for it.
-__global__ void __launch_bounds__(256) record_masks_recount_kernel(const __grid_constant__ MeshletCullParams p, const uint32_t* __restrict__ rank_counts,
-                                                                   uint32_t world, uint64_t rank_capacity, uint32_t* __restrict__ header_out) {
-    uint64_t total = 0u;
-    for (uint32_t r = 0; r < world; ++r) total += min((uint64_t)__ldcg(rank_counts + r), rank_capacity);
-    const uint32_t nrec = (uint32_t)min(total, p.capacity_records);
+__global__ void __launch_bounds__(256) record_masks_recount_kernel(const __grid_constant__ MeshletCullParams p, uint32_t* __restrict__ header_out) {
+    __shared__ uint32_t s_region[kMaxRegions + 1];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0u;
+        for (uint32_t k = 0; k < p.n_regions; ++k) { s_region[k] = acc; acc += (uint32_t)min((uint64_t)__ldcg(p.region_counts + k), p.region_stride); }
+        s_region[p.n_regions] = acc;
+    }
+    __syncthreads();
+    const uint32_t nrec = (uint32_t)min((uint64_t)s_region[p.n_regions], p.capacity_records);
     const uint32_t chunk_shift = chunk_shift_of(nrec);
     const uint32_t half = __ldcg(p.chunk_parity) & 1u;
     if (blockIdx.x == 0 && threadIdx.x == 0) { p.chunk_parity[1] = half; header_out[0] = nrec; header_out[1] = 1u; header_out[2] = 1u; }
@@ -1149,23 +1181,27 @@ __global__ void __launch_bounds__(256) record_masks_recount_kernel(const __grid_
     uint32_t mine = 0u;
     // a warp covers 32 consecutive records = at most one chunk (chunks are >= 32 records and 32-aligned)
     for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < nrec; base += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t r = base + lane;
-        const uint32_t pc = r < nrec ? (uint32_t)__popc(__ldcg(reinterpret_cast<const uint32_t*>(p.draw_masks + r))) : 0u;
+        const uint32_t r = (uint32_t)base + lane;
+        uint32_t pc = 0u;
+        if (r < nrec) {
+            uint32_t k = 0u;
+            while (k + 1u < p.n_regions && r >= s_region[k + 1u]) ++k;
+            pc = (uint32_t)__popc(__ldcg(reinterpret_cast<const uint32_t*>(p.draw_masks + (size_t)k * p.region_stride + (r - s_region[k]))));
+        }
         const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, pc);
         if (lane == 0u && s != 0u) { atomicAdd(chunk_counts + (uint32_t)(base >> chunk_shift), s); mine += s; }
     }
     if (mine != 0u) atomicAdd(p.draw_total + half, mine);
 }
 
-cudaError_t launch_record_masks_scatter(const uint4* src, uint4* dst, const uint32_t* rank_counts, uint32_t rank, uint32_t world,
-                                        uint64_t src_capacity, uint64_t dst_capacity, int grid, cudaStream_t s) {
-    record_masks_scatter_kernel<<<grid, 256, 0, s>>>(src, dst, rank_counts, rank, world, src_capacity, dst_capacity);
+cudaError_t launch_record_masks_put(const uint4* src, const uint32_t* dispatch_words, uint4* dst_region, uint32_t* dst_count, uint64_t capacity,
+                                    int grid, cudaStream_t s) {
+    record_masks_put_kernel<<<grid, 256, 0, s>>>(src, dispatch_words, dst_region, dst_count, capacity);
     return cudaGetLastError();
 }
 
-cudaError_t launch_draws_from_masks(const MeshletCullParams& p, const uint32_t* rank_counts, uint32_t world, uint64_t rank_capacity,
-                                    uint32_t* header, int grid, int emit_grid, cudaStream_t s) {
-    record_masks_recount_kernel<<<grid, 256, 0, s>>>(p, rank_counts, world, rank_capacity, header);
+cudaError_t launch_draws_from_masks(const MeshletCullParams& p, uint32_t* header, int grid, int emit_grid, cudaStream_t s) {
+    record_masks_recount_kernel<<<grid, 256, 0, s>>>(p, header);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return launch_kernel(meshlet_emit_kernel, dim3(emit_grid), dim3(kEmitWarps * 32), 0, s, p);

@@ -42,6 +42,11 @@ struct MeshletCullParams {
     float2 planes_t[6][4];            // cull planes paired for the packed test: [j][c] = (planes[2j][c], planes[2j+1][c]); an odd last plane is repeated
     ScanState scan;                   // only .trace is used (development timeline of the test kernel)
     unsigned long long* trace_emit;   // development timeline of the emit kernel
+    // sharded view on the receiving rank (orbit_draws_from_masks), else n_regions == 0: draw_masks holds one region of
+    // region_stride entries per rank, rank k's first region_counts[k] entries are its records
+    const uint32_t* region_counts;
+    uint64_t region_stride;
+    uint32_t n_regions;
 };
 
 struct EntityCullParams {
@@ -122,10 +127,9 @@ int meshlet_cull_max_ctas_per_sm(const MeshletCullParams&);
 int meshlet_cull_variant_index(const OrbitCullInfo&);
 cudaError_t meshlet_cull_configure_device();
 cudaError_t light_cluster_configure_device();
-cudaError_t launch_record_masks_scatter(const uint4* src, uint4* dst, const uint32_t* rank_counts, uint32_t rank, uint32_t world,
-                                        uint64_t src_capacity, uint64_t dst_capacity, int grid, cudaStream_t s);
-cudaError_t launch_draws_from_masks(const MeshletCullParams& p, const uint32_t* rank_counts, uint32_t world, uint64_t rank_capacity,
-                                    uint32_t* header, int grid, int emit_grid, cudaStream_t s);
+cudaError_t launch_record_masks_put(const uint4* src, const uint32_t* dispatch_words, uint4* dst_region, uint32_t* dst_count, uint64_t capacity,
+                                    int grid, cudaStream_t s);
+cudaError_t launch_draws_from_masks(const MeshletCullParams& p, uint32_t* header, int grid, int emit_grid, cudaStream_t s);
 cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t);
 int entity_cull_max_ctas_per_sm();
 cudaError_t launch_hiz_build(const HizBuildParams&, cudaStream_t);

@@ -182,22 +182,25 @@ class PeerExchange:
 class MaskExchange:
     """Survivor exchange of a sharded view in its compact form: every rank ships one 16-byte entry per dispatch record
     ({draw mask, entity, meshlet offset, 1}, written by orbit_meshlet_test) to the ROOT rank — the GPU that submits the draws —
-    by NVLink peer stores at the record offset of its range (rank-major = canonical record order); the root recounts and
-    emits the 28-byte commands itself (orbit_draws_from_masks). C3: 28 MB cross the switch instead of 229 MB, and the
-    emission (a local HBM-bound kernel) no longer waits for a single GPU's NVLink ingress. Device-side counts throughout:
-    the all-gathered dispatch headers are the only collective besides the closing 4-byte fence."""
+    by NVLink peer stores into ITS OWN region of the root's entry array, plus its record count into its slot of the root's
+    count words (orbit_record_masks_put): no rank needs another rank's count, so the only collective is the closing 4-byte
+    fence. The root reads the regions in rank order (rank-major = canonical record order), recounts and emits the 28-byte
+    commands itself (orbit_draws_from_masks). C3: 28 MB cross the switch instead of 229 MB, and the emission (a local
+    HBM-bound kernel) no longer waits for a single GPU's NVLink ingress."""
 
-    def __init__(self, context, capacity_records_rank, capacity_records_total, root=0, group=None):
+    HEADER_BYTES = 256      # the root's count words live in front of the regions
+
+    def __init__(self, context, capacity_records_rank, root=0, group=None):
         import ctypes as C
         from . import _lib
         self.C, self.lib, self.context, self.group, self.root = C, _lib.lib(), context, group, root
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        assert self.world <= 16
         cap = torch.tensor([int(capacity_records_rank)], dtype=torch.int64, device=context.device)
-        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)          # one capacity for every rank: counts are clamped to it
-        self.rank_capacity = int(cap.item())
-        self.total_capacity = int(capacity_records_total)
-        self.local_masks = torch.zeros(16 * max(self.rank_capacity, 1), dtype=torch.uint8, device=context.device)
-        nbytes = 16 * max(self.total_capacity, 1) if self.rank == root else 256
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)          # one region size for every rank
+        self.rank_capacity = max(int(cap.item()), 1)
+        self.local_masks = torch.zeros(16 * self.rank_capacity, dtype=torch.uint8, device=context.device)
+        nbytes = self.HEADER_BYTES + 16 * self.rank_capacity * self.world if self.rank == root else 256
         ptr, handle = C.c_void_p(), C.create_string_buffer(64)
         _lib.check(self.lib.orbit_peer_alloc(context._h, nbytes, C.byref(ptr), handle), "orbit_peer_alloc")
         self.local_ptr = ptr.value
@@ -209,27 +212,25 @@ class MaskExchange:
             q = C.c_void_p()
             _lib.check(self.lib.orbit_peer_open(context._h, handles[root], C.byref(q)), "orbit_peer_open")
             self.root_ptr = q.value
-        self.counts = torch.zeros(self.world, dtype=torch.int32, device=context.device)
         self._fence = torch.zeros(1, dtype=torch.int32, device=context.device)
         dist.barrier(group=group)
 
     def exchange(self, dispatch_buffer):
-        """Enqueued on the current stream: all-gather of the record counts, this rank's entries -> root, closing fence."""
+        """Enqueued on the current stream: this rank's entries + count -> its region on the root, then the closing fence."""
         C = self.C
-        dist.all_gather_into_tensor(self.counts, dispatch_buffer[:4].view(torch.int32), group=self.group)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        rc = self.lib.orbit_record_masks_scatter_ranked(self.context._h, C.c_void_p(self.local_masks.data_ptr()), self.rank_capacity,
-                                                        C.c_void_p(self.root_ptr), C.c_void_p(self.counts.data_ptr()), self.rank, self.world,
-                                                        self.total_capacity, stream)
+        region = self.root_ptr + self.HEADER_BYTES + 16 * self.rank_capacity * self.rank
+        rc = self.lib.orbit_record_masks_put(self.context._h, C.c_void_p(self.local_masks.data_ptr()), C.c_void_p(dispatch_buffer.data_ptr()),
+                                             self.rank_capacity, C.c_void_p(region), C.c_void_p(self.root_ptr + 4 * self.rank), stream)
         if rc:
-            raise RuntimeError("orbit_record_masks_scatter_ranked: %d" % rc)
+            raise RuntimeError("orbit_record_masks_put: %d" % rc)
         dist.all_reduce(self._fence, group=self.group)     # completes on the root only after every rank's stores were issued and flushed
 
     def expand(self, scene_buffers, draw_buffer, capacity_draws):
-        """Root only, after exchange(): the combined entries -> MeshletDrawCommandBuffer."""
+        """Root only, after exchange(): the ranks' regions -> MeshletDrawCommandBuffer."""
         C = self.C
-        rc = self.lib.orbit_draws_from_masks(self.context._h, C.byref(scene_buffers), C.c_void_p(self.local_ptr), self.total_capacity,
-                                             C.c_void_p(self.counts.data_ptr()), self.world, self.rank_capacity,
+        rc = self.lib.orbit_draws_from_masks(self.context._h, C.byref(scene_buffers), C.c_void_p(self.local_ptr + self.HEADER_BYTES),
+                                             self.rank_capacity, C.c_void_p(self.local_ptr), self.world,
                                              C.c_void_p(draw_buffer.data_ptr()), int(capacity_draws),
                                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc:
@@ -250,6 +251,7 @@ class ShardedView:
         self.frame = frame
         self.context, self.view, self.rank, self.world = context, view, rank, world
         lod0 = scene.mesh_infos["mesh_lods"][:, 0, 1][scene.draws["mesh_index"]]
+        self._lod0_records = (lod0.astype(np.int64) + 31) // 32
         self.ranges = partition_draws(lod0, world)
         b, e = self.ranges[rank]
         if b == e:            # empty range: keep the launch legal
@@ -326,46 +328,72 @@ class ShardedView:
     # ---- the sharded frame with the compact exchange (what bench.py times as "including the exchange") --------------------
     def enable_mask_exchange(self, capacity_records_total, capacity_draws_total):
         """Record-entry exchange (MaskExchange) for both lists; the early list's exchange gets its own process group (its own
-        NCCL stream), so it overlaps the pyramid broadcast and the late pass instead of queueing behind them."""
+        NCCL stream), so it overlaps the pyramid broadcast and the late pass instead of queueing behind them, and runs — with
+        rank 0's emission of the early list — on a low-priority stream, so that it fills the gaps of the critical path (Hi-Z,
+        broadcast, late pass on a high-priority stream) instead of delaying it."""
         self.side_group = dist.new_group()
-        rcap = self.prepared.rcap
-        self.mx_early = MaskExchange(self.context, rcap, capacity_records_total, root=0, group=self.side_group)
-        self.mx_late = MaskExchange(self.context, rcap, capacity_records_total, root=0)
+        lod0 = self._lod0_records
+        b, e = self.ranges[self.rank]
+        rcap_rank = int(lod0[b:e].sum())                          # records this rank can produce (every entity at LOD 0)
+        self.mx_early = MaskExchange(self.context, rcap_rank, root=0, group=self.side_group)
+        self.mx_late = MaskExchange(self.context, rcap_rank, root=0)
         self.total_dcap = int(capacity_draws_total)
         if self.rank == 0:
             self.gathered_early = torch.zeros(4 + DRAW_BYTES * self.total_dcap, dtype=torch.uint8, device=self.context.device)
             self.gathered_late = torch.zeros(4 + DRAW_BYTES * self.total_dcap, dtype=torch.uint8, device=self.context.device)
-        self._side = torch.cuda.Stream()
+        self._side = torch.cuda.Stream()                          # default = lowest priority
+        self._crit = torch.cuda.Stream(priority=-1)
 
     def best_exchange_name(self):
         return ("16-byte record entries {draw mask, entity, meshlet offset} to rank 0 by NVLink peer stores (device-side counts), "
                 "rank 0 emits the commands of the combined list; the early list's exchange + emission overlap Hi-Z, its broadcast and the late pass")
 
-    def step_best(self):
+    def step_best(self, marks=None):
         """early cull (test only) -> [side stream: entries -> rank 0, rank 0 emits the early list] || Hi-Z on rank 0 + broadcast ->
-        late cull (test only) -> entries -> rank 0, rank 0 emits the late list."""
+        late cull (test only) -> entries -> rank 0, rank 0 emits the late list. `marks`: a dict that receives CUDA events recorded
+        at the stage boundaries (development timeline: tools/bench_configs.py c3 --timeline)."""
         pf = self.prepared
-        main = torch.cuda.current_stream()
-        if not self.empty:
-            pf.entity(False); pf.meshlet_test(False, self.mx_early.local_masks)
-        else:
-            pf.early_dispatch[:4].zero_()
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
-            self.mx_early.exchange(pf.early_dispatch)
+        caller = torch.cuda.current_stream()
+        main = self._crit
+        main.wait_stream(caller)
+
+        def mark(name, stream=None):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream or main)
+                marks[name] = ev
+        with torch.cuda.stream(main):
+            mark("start")
+            if not self.empty:
+                pf.entity(False); pf.meshlet_test(False, self.mx_early.local_masks)
+            else:
+                pf.early_dispatch[:4].zero_()
+            mark("early tested")
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.mx_early.exchange(pf.early_dispatch)
+                mark("early entries on rank 0", self._side)
+                if self.rank == 0:
+                    self.mx_early.expand(pf.sb_early, self.gathered_early, self.total_dcap)
+                mark("early list emitted", self._side)
             if self.rank == 0:
-                self.mx_early.expand(pf.sb_early, self.gathered_early, self.total_dcap)
-        if self.rank == 0:
-            pf.hiz()
-        broadcast_pyramid(self.vstate.depth_pyramid.texels, src=0)
-        if not self.empty:
-            pf.entity(True); pf.meshlet_test(True, self.mx_late.local_masks)
-        else:
-            pf.late_dispatch[:4].zero_()
-        self.mx_late.exchange(pf.late_dispatch)
-        if self.rank == 0:
-            self.mx_late.expand(pf.sb_late, self.gathered_late, self.total_dcap)
-        main.wait_stream(self._side)
+                pf.hiz()
+            mark("hiz built")
+            broadcast_pyramid(self.vstate.depth_pyramid.texels, src=0)
+            mark("pyramid broadcast")
+            if not self.empty:
+                pf.entity(True); pf.meshlet_test(True, self.mx_late.local_masks)
+            else:
+                pf.late_dispatch[:4].zero_()
+            mark("late tested")
+            self.mx_late.exchange(pf.late_dispatch)
+            mark("late entries on rank 0")
+            if self.rank == 0:
+                self.mx_late.expand(pf.sb_late, self.gathered_late, self.total_dcap)
+            mark("late list emitted")
+            main.wait_stream(self._side)
+            mark("end")
+        caller.wait_stream(main)
 
     def clear_gathered(self):
         if self.rank == 0:

@@ -135,12 +135,11 @@ extern "C" {
                                       rank_counts: *const u32, rank: u32, world: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
     pub fn orbit_meshlet_test(ctx: *mut orbit_ctx, cull: *const OrbitCullInfo, scene: *const OrbitSceneBuffers, hiz: *const orbit_hiz,
                               meshlet_dispatch_buffer: *const c_void, capacity_records: u64, record_masks: *mut c_void, stream: *mut c_void) -> i32;
-    pub fn orbit_record_masks_scatter_ranked(ctx: *mut orbit_ctx, src_record_masks: *const c_void, src_capacity_records: u64,
-                                             dst_record_masks: *mut c_void, rank_record_counts: *const u32, rank: u32, world: u32,
-                                             dst_capacity_records: u64, stream: *mut c_void) -> i32;
-    pub fn orbit_draws_from_masks(ctx: *mut orbit_ctx, scene: *const OrbitSceneBuffers, record_masks: *const c_void, capacity_records: u64,
-                                  rank_record_counts: *const u32, world: u32, rank_capacity_records: u64,
-                                  draw_command_buffer: *mut c_void, capacity_draws: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_record_masks_put(ctx: *mut orbit_ctx, src_record_masks: *const c_void, meshlet_dispatch_buffer: *const c_void, capacity_records: u64,
+                                  dst_region: *mut c_void, dst_count: *mut u32, stream: *mut c_void) -> i32;
+    pub fn orbit_draws_from_masks(ctx: *mut orbit_ctx, scene: *const OrbitSceneBuffers, record_masks: *const c_void, region_stride_records: u64,
+                                  region_counts: *const u32, n_regions: u32, draw_command_buffer: *mut c_void, capacity_draws: u64,
+                                  stream: *mut c_void) -> i32;
     pub fn orbit_scene_update(ctx: *mut orbit_ctx, update: *const OrbitSceneUpdate, stream: *mut c_void) -> i32;
     pub fn orbit_meshlet_bounds(ctx: *mut orbit_ctx, vertices: *const c_void, vertex_stride: u32, meshlet_data: *const u32, meshlets: *mut c_void,
                                 n_meshlets: u32, stream: *mut c_void) -> i32;

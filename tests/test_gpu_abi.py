@@ -201,9 +201,10 @@ def test_draw_ranges_on_one_gpu_concatenate_to_the_unsharded_result(gpu_context,
 
 
 def test_record_mask_exchange_on_one_gpu(gpu_context, oracle):
-    """The compact survivor exchange of the sharded view (orbit_meshlet_test -> orbit_record_masks_scatter_ranked ->
-    orbit_draws_from_masks) with three 'ranks' played by one GPU: each range is tested into its own entry buffer, the buffers
-    are laid end to end by the scatter call, and the emitted list must be the unsharded oracle list (two frames, both lists)."""
+    """The compact survivor exchange of the sharded view (orbit_meshlet_test -> orbit_record_masks_put ->
+    orbit_draws_from_masks) with three 'ranks' played by one GPU: each range is tested into its own entry buffer, every buffer
+    is put into its own region (with its count word) of the receiving array, and the list emitted from the regions must be the
+    unsharded oracle list (two frames, both lists)."""
     from orbit_b200 import _lib, frame
     from orbit_b200.multi_gpu import partition_draws
     ctx, lib = gpu_context, _lib.lib()
@@ -219,7 +220,7 @@ def test_record_mask_exchange_on_one_gpu(gpu_context, oracle):
              for i, (b, e) in enumerate(ranges)]
     rcap, dcap = parts[0].rcap, parts[0].dcap
     masks = [torch.zeros(16 * rcap, dtype=torch.uint8, device=ctx.device) for _ in parts]
-    combined = torch.zeros(16 * rcap, dtype=torch.uint8, device=ctx.device)
+    combined = torch.zeros(16 * rcap * world, dtype=torch.uint8, device=ctx.device)   # one region of rcap entries per rank
     counts = torch.zeros(world, dtype=torch.int32, device=ctx.device)
     out = torch.zeros(4 + 28 * dcap, dtype=torch.uint8, device=ctx.device)
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -227,13 +228,13 @@ def test_record_mask_exchange_on_one_gpu(gpu_context, oracle):
     hs = oracle.HostScene(sc)
 
     def gather(late):
+        combined.fill_(0xAB); counts.fill_(-1)
         for i, pf in enumerate(parts):
-            counts[i:i + 1] = (pf.late_dispatch if late else pf.early_dispatch)[:4].view(torch.int32)
-        combined.zero_()
-        for i in range(world):
-            assert lib.orbit_record_masks_scatter_ranked(ctx._h, p(masks[i]), rcap, p(combined), p(counts), i, world, rcap, stream) == 0
+            disp = pf.late_dispatch if late else pf.early_dispatch
+            assert lib.orbit_record_masks_put(ctx._h, p(masks[i]), p(disp), rcap, C.c_void_p(combined.data_ptr() + 16 * rcap * i),
+                                              C.c_void_p(counts.data_ptr() + 4 * i), stream) == 0
         sb = parts[0].sb_late if late else parts[0].sb_early
-        assert lib.orbit_draws_from_masks(ctx._h, C.byref(sb), p(combined), rcap, p(counts), world, rcap, p(out), dcap, stream) == 0
+        assert lib.orbit_draws_from_masks(ctx._h, C.byref(sb), p(combined), rcap, p(counts), world, p(out), dcap, stream) == 0
         torch.cuda.synchronize()
         return frame.read_draws(out)
     for f in range(2):

@@ -85,7 +85,36 @@ def check_against_oracle(name, O, hs, view, kind, gpu_pair, results):
     return ok
 
 
+def run_c3_timeline(args, rank, world, ctx):
+    """Where the sharded frame's time goes: CUDA events at the stage boundaries of ShardedView.step_best, every rank."""
+    scene, view = scenes.config_c3(args.scale)
+    depth = scenes.make_depth(scene, view) if rank == 0 else np.zeros((view.height, view.width), np.float32)
+    sv = multi_gpu.ShardedView(ctx, scene, view, depth, rank, world)
+    sv.enable_mask_exchange(scene.n_records_lod0, scene.n_meshlet_instances)
+    for _ in range(3):
+        sv.step_best()
+    torch.cuda.synchronize(); dist.barrier()
+    rows = []
+    for _ in range(5):
+        marks = {}
+        dist.barrier(); torch.cuda.synchronize()
+        sv.step_best(marks)
+        torch.cuda.synchronize()
+        rows.append({k: marks["start"].elapsed_time(v) * 1e3 for k, v in marks.items()})
+    med = {k: float(np.median([r[k] for r in rows])) for k in rows[0]}
+    allm = [None] * world
+    dist.all_gather_object(allm, med)
+    if rank == 0:
+        keys = list(med)
+        print("C3 sharded frame, %d GPUs: us from the frame's start (median of 5), per rank" % world)
+        for k in keys:
+            print("  %-26s %s" % (k, "  ".join("%7.1f" % m[k] for m in allm)))
+    sv.close()
+
+
 def run_c3(args, rank, world, ctx):
+    if args.timeline:
+        return run_c3_timeline(args, rank, world, ctx)
     import oracle_ref as O
     scene, view = scenes.config_c3(args.scale)
     depth = scenes.make_depth(scene, view)
@@ -268,6 +297,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--views", type=int, default=32)
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="c3: stage-boundary timeline of the sharded frame")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
