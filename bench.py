@@ -6,8 +6,10 @@
 Workload (N=1): BASELINE config C2 — procedural 10k-entity / 2M-meshlet city, one 1920x1080 view, two-pass
 occlusion. One *step* = the reference's culling of one steady-state frame (BASELINE.md protocol):
 EARLY entity+meshlet cull (pass 1) -> Hi-Z build -> LATE entity+meshlet cull (pass 2) (forward.rs:266-403), then the
-MAIN pass (pass 1 again with the bits the late pass wrote, forward.rs:518-548): 10 kernel launches (the meshlet stage is a
-test kernel + an emit kernel). `value` = scene meshlet instances x views / step time with every input resident in HBM;
+MAIN pass (pass 1 again with the bits the late pass wrote, forward.rs:518-548). LATE and MAIN run in their fused form
+(orbit_entity_cull_late_main / orbit_meshlet_cull_late_main: the MAIN pass's tests repeat the LATE pass's, so one entity
+kernel and one test kernel produce both passes' buffers, byte for byte): 7 kernel launches per step (entity_cull, meshlet
+test + emit, hiz_build, entity_cull, meshlet test + one emit launch for the LATE and the MAIN list). `value` = scene meshlet instances x views / step time with every input resident in HBM;
 the step rotates over 4 independent copies of the scene + view state (> L2) so inputs come from HBM.
 Besides the contract's K timed steps the line carries `repeats` (5 x >= 50 steps: median and min), `moving_camera`
 (a frame whose late pass finds survivors), and — nested, not separate lines — `c3_sharded` and `c5_many_view`:
@@ -42,7 +44,7 @@ METRIC = "Gmeshlets culled/s (C2: 10k entities / 2M meshlets, 1920x1080, two-pas
 UNIT = "Gmeshlets/s"
 WORKLOAD = "C2 city 10k entities / 2M meshlets, one 1920x1080 view per GPU, steady-state frame: early cull + Hi-Z + late cull + main cull"
 N_COPIES = 4
-KERNELS_PER_STEP = 10   # 3 x entity_cull, 3 x (meshlet test + meshlet_emit), 1 x hiz_build
+KERNELS_PER_STEP = 7    # early: entity_cull, meshlet test, meshlet_emit; hiz_build; late + main fused: entity_cull, meshlet test, one meshlet_emit launch for both lists
 
 
 def c2_view(scenes, scene, index):
@@ -446,10 +448,13 @@ def run_ours(args, rank, world, local_rank):
             ts.append(a.elapsed_time(b) * 1e3 / per_graph)
         return float(np.median(ts[1:])), float(np.min(ts[1:]))
 
+    assert all(pf.fused for pf in copies), "the C2 LATE / MAIN pair must be a compatible pair"
     stages = {"entity_early": lambda pf, s: pf.entity(False, s), "meshlet_early": lambda pf, s: pf.meshlet(False, s),
-              "hiz": lambda pf, s: pf.hiz(s), "entity_late": lambda pf, s: pf.entity(True, s),
-              "meshlet_late": lambda pf, s: pf.meshlet(True, s), "entity_main": lambda pf, s: pf.entity("main", s),
-              "meshlet_main": lambda pf, s: pf.meshlet("main", s)}
+              "hiz": lambda pf, s: pf.hiz(s), "entity_late_main": lambda pf, s: pf.entity_late_main(s),
+              "meshlet_late_main": lambda pf, s: pf.meshlet_late_main(s),
+              # the unfused stages, for comparison (not part of the timed step)
+              "unfused_entity_late": lambda pf, s: pf.entity(True, s), "unfused_meshlet_late": lambda pf, s: pf.meshlet(True, s),
+              "unfused_entity_main": lambda pf, s: pf.entity("main", s), "unfused_meshlet_main": lambda pf, s: pf.meshlet("main", s)}
     k_times = {k: time_stage(fn) for k, fn in stages.items()}
     # the late-pass TEST kernel alone (the dominant kernel the roofline object is quoted on): a second context whose
     # meshlet stage skips the emit launch (ORBIT_DEBUG_SKIP=1, read at context creation; timing only — in the steady
@@ -458,9 +463,12 @@ def run_ours(args, rank, world, local_rank):
     ctx_test_only = Context(local_rank)
     del os.environ["ORBIT_DEBUG_SKIP"]
     for pf in copies:
-        pf.meshlet(True, context=ctx_test_only)     # grow that context's scratch outside the capture
+        pf.meshlet_late_main(context=ctx_test_only)     # grow that context's scratch outside the capture
     torch.cuda.synchronize()
-    k_times["meshlet_late_test_kernel"] = time_stage(lambda pf, s: pf.meshlet(True, s, context=ctx_test_only))
+    k_times["meshlet_late_test_kernel"] = time_stage(lambda pf, s: pf.meshlet_late_main(s, context=ctx_test_only))
+    for pf in copies:
+        pf.launch()                                     # leave every copy in its steady state again
+    torch.cuda.synchronize()
     # pass 0 (frustum + cone only, no Hi-Z math) over every meshlet the frustum keeps: the HBM-heaviest use of the stage
     # (extra information; the roofline object below stays on the dominant kernel of the timed step)
     from orbit_b200.passes import OcclusionCullInfo, create_meshlet_dispatch_command, create_meshlet_draw_commands
@@ -598,7 +606,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         late_us = k_times["meshlet_late_test_kernel"][0]   # the dominant kernel alone, as ncu's traffic figure is
-        stage_us = k_times["meshlet_late"][0]              # test + (empty) emit kernel
+        stage_us = k_times["meshlet_late_main"][0]         # test + emit (LATE list: empty in the steady state) + emit (MAIN list)
         achieved = late_bytes / (late_us * 1e-6) / 1e9
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
@@ -610,16 +618,16 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD,
                        "l2": "rotating %d independent copies of scene + view state (~%d MB each) so inputs come from HBM" % (
                            N_COPIES, sum(scene.bytes_summary().values()) // 2 ** 20),
-                       "launch": "one CUDA graph replay per step (%d kernels: 3x entity_cull, 3x meshlet test + meshlet_emit, hiz_build)" % KERNELS_PER_STEP,
+                       "launch": "one CUDA graph replay per step (%d kernels: early = entity_cull + meshlet test + meshlet_emit; hiz_build; late + main fused = entity_cull + meshlet test + one meshlet_emit launch for both lists)" % KERNELS_PER_STEP,
                        "views": "every rank culls its own instance of the C2 view on a replicated scene; no data-path collective"},
             "repeats": {"what": "the timed step again, 5 repeats of %d steps each (BASELINE.md protocol)" % rep_steps,
                         "ms_per_step_median": float(np.median(rep_ms)), "ms_per_step_min": float(np.min(rep_ms)), "ms_per_step_all": rep_ms},
-            "roofline": {"bound": "hbm", "kernel": "meshlet_test_direct_kernel<4,pass2,persp> (late pass, occlusion_pass=2)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "meshlet_test_direct_kernel<4,pass2,persp> (late pass, occlusion_pass=2, also filling the MAIN pass's record entries)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                          "traffic_source": "profiles/r2_meshlet_test_ncu.json (ncu --set full, per launch, bytes)",
                          "algorithmic_bytes_per_launch": late_bytes, "launch_us_median": late_us, "launch_us_min": k_times["meshlet_late_test_kernel"][1],
                          "stage_us_median": stage_us, "frac_stage": late_bytes / (stage_us * 1e-6) / 1e9 / peak,
-                         "stage": "test kernel + meshlet_emit_kernel (nothing to emit in the steady-state late pass)",
+                         "stage": "test kernel + meshlet_emit_kernel (LATE list: nothing to emit in the steady state) + meshlet_emit_kernel (MAIN list)",
                          "lanes": late_lanes, "records": late_R, "entities": late_E, "survivors": n_late_draws,
                          "stage_gmeshlets_per_s": late_lanes / (stage_us * 1e-6) / 1e9,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
@@ -639,7 +647,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes_box[0]),
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "what": "per step: pinned host entity Transforms (48 B each) + depth -> device, orbit_scene_update + 7 stage calls (C ABI: early, Hi-Z, late, main), three draw lists + counts -> host; issued by the compiled host driver (orbit_b200/host/frame_driver.cpp), software-pipelined over 3 streams (copy-in / compute / copy-out), two steps enqueued ahead of the one being read back",
+                    "what": "per step: pinned host entity Transforms (48 B each) + depth -> device, orbit_scene_update + 5 stage calls (C ABI: early entity + meshlet, Hi-Z, fused late + main entity / meshlet), three draw lists + counts -> host; issued by the compiled host driver (orbit_b200/host/frame_driver.cpp), software-pipelined over 3 streams (copy-in / compute / copy-out), two steps enqueued ahead of the one being read back",
                     "depth_resident": {"what": "same loop with the depth buffer already on the device (Vulkan interop imports the depth attachment instead of copying it)",
                                        "value": units / (e2e_res_ms * 1e-3) / 1e9, "ms_per_step": e2e_res_ms,
                                        "h2d_bytes_per_step": int(rep_res["h2d_bytes_per_step"]), "d2h_bytes_per_step": int(rep_res["d2h_bytes_per_step"])}},

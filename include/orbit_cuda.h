@@ -162,6 +162,26 @@ int orbit_meshlet_cull(orbit_ctx* ctx, const OrbitCullInfo* cull, const OrbitSce
                        void* draw_command_buffer, uint64_t capacity_draws,
                        void* task_payloads, void* stream);
 
+/* ---- fused LATE + MAIN passes (forward.rs:266-403 followed by forward.rs:518-548) --------------------------------
+ * The MAIN pass is pass 1 over the visibility bits the LATE pass (pass 2) has just written. When both passes use the same
+ * camera, planes, LOD parameters and visibility buffers and meshlet occlusion culling is on (orbit_cull_pair_compatible
+ * returns 1: view matrix, planes, projection type, LOD parameters and visibility buffers are equal; alpha_mode_flags and the
+ * fields only pass 2 reads may differ), the
+ * MAIN pass's tests repeat the LATE pass's: its dispatch list is the LATE list, and its draw list holds the meshlets the
+ * LATE pass finds visible, filtered by the MAIN pass's alpha_mode_flags. The two calls below produce, in one entity
+ * kernel and one test kernel (+ one emit kernel per list), byte for byte what
+ *   orbit_entity_cull(late) ; orbit_meshlet_cull(late) ; orbit_entity_cull(main) ; orbit_meshlet_cull(main)
+ * produce. They return ORBIT_ERR_INVALID_ARGUMENT for an incompatible pair (call the four stages separately then). */
+int orbit_cull_pair_compatible(const OrbitCullInfo* late, const OrbitCullInfo* main_pass);
+int orbit_entity_cull_late_main(orbit_ctx* ctx, const OrbitCullInfo* late, const OrbitCullInfo* main_pass,
+                                const OrbitSceneBuffers* scene, const orbit_hiz* hiz, void* late_dispatch_buffer,
+                                void* main_dispatch_buffer, uint64_t capacity_records, void* stream);
+int orbit_meshlet_cull_late_main(orbit_ctx* ctx, const OrbitCullInfo* late, const OrbitCullInfo* main_pass,
+                                 const OrbitSceneBuffers* scene, const orbit_hiz* hiz, const void* late_dispatch_buffer,
+                                 uint64_t capacity_records, void* late_draw_command_buffer, void* main_draw_command_buffer,
+                                 uint64_t capacity_draws, void* late_task_payloads /* nullable */,
+                                 void* main_task_payloads /* nullable */, void* stream);
+
 /* ---- compute_clusters (cluster.rs:368-591) + light_cluster/{mark_active,active_cluster_compaction,
  *      light_culling}.comp --------------------------------------------------------------------------------- */
 /* tile_masks: u32[cx*cy]; depth_bounds: OrbitClusterDepthBounds[cx*cy*cz]; unique_clusters:

@@ -39,6 +39,11 @@ PROTOTYPES = {
                                       C.c_void_p]),
     "orbit_draws_scatter_ranked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
                                              C.c_void_p]),
+    "orbit_cull_pair_compatible": (C.c_int, [C.POINTER(L.CullInfo), C.POINTER(L.CullInfo)]),
+    "orbit_entity_cull_late_main": (C.c_int, [C.c_void_p, C.POINTER(L.CullInfo), C.POINTER(L.CullInfo), C.POINTER(L.SceneBuffers), C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "orbit_meshlet_cull_late_main": (C.c_int, [C.c_void_p, C.POINTER(L.CullInfo), C.POINTER(L.CullInfo), C.POINTER(L.SceneBuffers), C.c_void_p,
+                                               C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "orbit_meshlet_test": (C.c_int, [C.c_void_p, C.POINTER(L.CullInfo), C.POINTER(L.SceneBuffers), C.c_void_p, C.c_void_p, C.c_uint64,
                                      C.c_void_p, C.c_void_p]),
     "orbit_record_masks_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),

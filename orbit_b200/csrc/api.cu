@@ -48,6 +48,8 @@ struct orbit_ctx {
     // scan scratch
     unsigned long long* status = nullptr;
     size_t status_capacity = 0;       // descriptors
+    uint4* main_masks = nullptr;      // record entries of the fused MAIN pass
+    size_t main_mask_capacity = 0;
     unsigned int* counters = nullptr; // 32 words: [0] ticket, [1] done, [2] hiz ticket, [3] scan epoch (device-advanced), [4,5] meshlet survivor
                                       // totals per parity, [6,7] parity words A/B of the meshlet stage, [8] scene-update cursor snapshot,
                                       // [10..13] the same four words for test-only calls, [16..18] dispatch header of orbit_draws_from_masks
@@ -127,6 +129,18 @@ static int ensure_tile_sums(orbit_ctx* c, size_t tiles) {
     c->tile_sums = nullptr; c->tile_sums_capacity = 0;
     CK(cudaMalloc(&c->tile_sums, cap * sizeof(unsigned long long)));
     c->tile_sums_capacity = cap;
+    return ORBIT_OK;
+}
+
+// record entries of the fused MAIN pass (orbit_meshlet_cull_late_main)
+static int ensure_main_masks(orbit_ctx* c, uint64_t max_records) {
+    if (max_records <= c->main_mask_capacity) return ORBIT_OK;
+    int rc = retire(c, c->main_masks);
+    if (rc != ORBIT_OK) return rc;
+    c->main_masks = nullptr; c->main_mask_capacity = 0;
+    size_t cap = 65536; while (cap < max_records) cap *= 2;
+    CK(cudaMalloc(&c->main_masks, cap * sizeof(uint4)));
+    c->main_mask_capacity = cap;
     return ORBIT_OK;
 }
 
@@ -229,8 +243,8 @@ int orbit_ctx_create(int device, orbit_ctx** out) {
     CK(cudaMalloc(&c->counters, 32 * sizeof(unsigned int)));
     CK(cudaMemset(c->counters, 0, 32 * sizeof(unsigned int)));
     { const unsigned int one = 1u; CK(cudaMemcpy(c->counters + 3, &one, sizeof(one), cudaMemcpyHostToDevice)); }
-    CK(cudaMalloc(&c->chunk_counts, 4 * 2048 * sizeof(uint32_t)));   // two parities for orbit_meshlet_cull + two (never read) for orbit_meshlet_test
-    CK(cudaMemset(c->chunk_counts, 0, 4 * 2048 * sizeof(uint32_t)));
+    CK(cudaMalloc(&c->chunk_counts, 6 * 2048 * sizeof(uint32_t)));   // two parities for orbit_meshlet_cull + two (never read) for orbit_meshlet_test + two for the fused MAIN pass
+    CK(cudaMemset(c->chunk_counts, 0, 6 * 2048 * sizeof(uint32_t)));
     CK(cudaHostAlloc(&c->status_host, sizeof(OrbitStatus), cudaHostAllocMapped));
     std::memset(c->status_host, 0, sizeof(OrbitStatus));
     CK(cudaHostGetDevicePointer(&c->status_dev, c->status_host, 0));
@@ -257,7 +271,7 @@ void orbit_ctx_destroy(orbit_ctx* c) {
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < c->n_retired; ++i) cudaFree(c->retired[i]);
-    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->light_hits); cudaFree(c->draw_masks); cudaFree(c->cmd_side); cudaFree(c->chunk_counts); cudaFree(c->tile_sums);
+    cudaFree(c->status); cudaFree(c->counters); cudaFree(c->light_view); cudaFree(c->light_hits); cudaFree(c->draw_masks); cudaFree(c->cmd_side); cudaFree(c->main_masks); cudaFree(c->chunk_counts); cudaFree(c->tile_sums);
     cudaFree(c->trace);
     cudaFreeHost(c->status_host);
     delete c;
@@ -388,8 +402,8 @@ static int check_cull(const OrbitCullInfo* cull, const OrbitSceneBuffers* scene,
     return ORBIT_OK;
 }
 
-int orbit_entity_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
-                      void* meshlet_dispatch_buffer, uint64_t capacity_records, void* stream) {
+static int entity_stage(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
+                        void* meshlet_dispatch_buffer, void* mirror_dispatch_buffer, uint64_t capacity_records, void* stream) {
     if (!c || !meshlet_dispatch_buffer || ((uintptr_t)meshlet_dispatch_buffer & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
     int rc = check_cull(cull, scene, hiz, false);
     if (rc != ORBIT_OK) return rc;
@@ -408,6 +422,7 @@ int orbit_entity_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneB
     p.entities = (const float4*)scene->entities;
     p.entity_visibility = scene->entity_visibility;
     p.dispatch_words = (uint32_t*)meshlet_dispatch_buffer;
+    p.dispatch_mirror = (uint32_t*)mirror_dispatch_buffer;
     p.overflow_flag = &c->status_dev->dispatch_overflow;
     p.capacity_records = capacity_records;
     p.draw_begin = begin; p.draw_end = end;
@@ -418,11 +433,51 @@ int orbit_entity_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneB
     return ORBIT_OK;
 }
 
+int orbit_entity_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
+                      void* meshlet_dispatch_buffer, uint64_t capacity_records, void* stream) {
+    return entity_stage(c, cull, scene, hiz, meshlet_dispatch_buffer, nullptr, capacity_records, stream);
+}
+
+// ---- fused LATE + MAIN -----------------------------------------------------------------------------------
+// The MAIN pass (forward.rs:518-548) is pass 1 over the visibility bits the LATE pass (pass 2, forward.rs:266-403) has just
+// written. With the same camera, planes, LOD parameters and buffers, and meshlet occlusion culling on:
+//   entity level   MAIN: visible = bit_new && frustum = LATE's `visible` (the bit IS that value and already includes the same
+//                  frustum test), should_draw = visible; LATE: should_draw = visible && (!bit_old || mocc) = visible
+//                  (entity_cull.comp:137-189) -> the two dispatch lists are the same list.
+//   meshlet level  MAIN: visible = bit_new && frustum && cone = LATE's `visible`; should_draw = visible && alpha filter
+//                  (meshlet_cull.comp:137,207), LATE: visible && !bit_old (or the alpha filter for noskip modes).
+// So one entity kernel writes both dispatch buffers and the LATE test kernel fills both record-entry arrays; each list is
+// then emitted by its own emit kernel. Everything else falls back to separate calls: orbit_cull_pair_compatible says which.
+int orbit_cull_pair_compatible(const OrbitCullInfo* late, const OrbitCullInfo* main_pass) {
+    if (!late || !main_pass) return 0;
+    if (late->occlusion_pass != 2u || main_pass->occlusion_pass != 1u) return 0;
+    if (late->meshlet_visibility_buffer == ORBIT_NO_BUFFER || main_pass->meshlet_visibility_buffer == ORBIT_NO_BUFFER) return 0;
+    if (late->visibility_buffer != main_pass->visibility_buffer || late->meshlet_visibility_buffer != main_pass->meshlet_visibility_buffer) return 0;
+    // view matrix, reprojection matrix, planes, plane count: bytes [0, 324)
+    if (std::memcmp(late, main_pass, offsetof(OrbitCullInfo, alpha_mode_flags)) != 0) return 0;
+    // projection type (cone test) and LOD parameters, bytes [372, 400); p00 / p11 / z_near / z_far are only read by the
+    // occlusion test and are left zero for pass 1 by CullInfo::to_gpu (draw_gen.rs:150-198)
+    if (late->projection_type != main_pass->projection_type) return 0;
+    if (std::memcmp(&late->lod_base, &main_pass->lod_base, sizeof(OrbitCullInfo) - offsetof(OrbitCullInfo, lod_base)) != 0) return 0;
+    return 1;
+}
+
+int orbit_entity_cull_late_main(orbit_ctx* c, const OrbitCullInfo* late, const OrbitCullInfo* main_pass, const OrbitSceneBuffers* scene,
+                                const orbit_hiz* hiz, void* late_dispatch_buffer, void* main_dispatch_buffer, uint64_t capacity_records,
+                                void* stream) {
+    if (!main_dispatch_buffer || ((uintptr_t)main_dispatch_buffer & 3u) || main_dispatch_buffer == late_dispatch_buffer) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (!orbit_cull_pair_compatible(late, main_pass)) return ORBIT_ERR_INVALID_ARGUMENT;
+    return entity_stage(c, late, scene, hiz, late_dispatch_buffer, main_dispatch_buffer, capacity_records, stream);
+}
+
 // ---- meshlet stage ---------------------------------------------------------------------------------------
 // mode 0: test + emit (orbit_meshlet_cull); mode 1: test only, record entries into `record_masks` (orbit_meshlet_test)
+struct MainPassOutputs { const OrbitCullInfo* cull; void* draw_command_buffer; void* task_payloads; };   // fused LATE + MAIN
+
 static int meshlet_stage(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,
                          const void* meshlet_dispatch_buffer, uint64_t capacity_records, void* draw_command_buffer,
-                         uint64_t capacity_draws, void* task_payloads, void* record_masks, void* stream) {
+                         uint64_t capacity_draws, void* task_payloads, void* record_masks, void* stream,
+                         const MainPassOutputs* fused_main = nullptr) {
     const bool test_only = record_masks != nullptr;
     if (!c || !meshlet_dispatch_buffer || (!test_only && !draw_command_buffer)) return ORBIT_ERR_INVALID_ARGUMENT;
     if (((uintptr_t)meshlet_dispatch_buffer & 3u) || ((uintptr_t)draw_command_buffer & 3u) || ((uintptr_t)task_payloads & 3u) ||
@@ -436,6 +491,10 @@ static int meshlet_stage(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSce
     GUARD(c);
     if (!test_only) {
         rc = ensure_record_scratch(c, max_records);
+        if (rc != ORBIT_OK) return rc;
+    }
+    if (fused_main) {
+        rc = ensure_main_masks(c, max_records);
         if (rc != ORBIT_OK) return rc;
     }
     MeshletCullParams p{};
@@ -463,6 +522,13 @@ static int meshlet_stage(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSce
         p.chunk_parity = c->counters + 12;  // [12],[13]
         p.chunk_counts = c->chunk_counts + 2 * 2048;
     }
+    if (fused_main) {
+        p.main_masks = c->main_masks;
+        p.main_chunk_counts = c->chunk_counts + 4 * 2048;
+        p.main_chunk_parity = c->counters + 22;   // [22] word A, [23] word B
+        p.main_draw_total = c->counters + 20;     // [20],[21]
+        p.main_alpha_mode_flags = fused_main->cull->alpha_mode_flags;
+    }
     p.capacity_records = max_records;
     p.capacity_draws = capacity_draws;
     p.scan.trace = next_trace(c);
@@ -486,9 +552,35 @@ static int meshlet_stage(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSce
     if (c->emit_ctas_per_sm >= 1 && c->emit_ctas_per_sm <= c->emit_occupancy) emit_per_sm = c->emit_ctas_per_sm;   // tuning knob
     const uint64_t emit_grid = (uint64_t)c->sm_count * (uint64_t)emit_per_sm;
     const bool skip_emit = test_only || c->debug_skip == 1;
-    CK(launch_meshlet_cull(p, c->debug_skip == 2 ? 0 : (int)grid, skip_emit ? 0 : (int)emit_grid, (cudaStream_t)stream));
+    const bool pair = fused_main && !skip_emit;      // both lists leave in one emit launch
+    CK(launch_meshlet_cull(p, c->debug_skip == 2 ? 0 : (int)grid, (skip_emit || pair) ? 0 : (int)emit_grid, (cudaStream_t)stream));
     c->launches += test_only ? 1 : 2;   // test kernel (+ emit kernel)
+    if (pair) {
+        // the MAIN list: the ordinary emit code over the second set of record entries / chunk counts; its entries carry
+        // flag 1, so the command words are read from the meshlets (the survivors of a steady frame: a few MB)
+        MeshletCullParams m = p;
+        m.cull = *fused_main->cull;
+        m.draw_masks = c->main_masks; m.cmd_side = nullptr;
+        m.chunk_counts = p.main_chunk_counts; m.chunk_parity = p.main_chunk_parity; m.draw_total = p.main_draw_total;
+        m.draw_words = (uint32_t*)fused_main->draw_command_buffer;
+        m.task_payloads = (uint32_t*)fused_main->task_payloads;
+        m.main_masks = nullptr;
+        m.trace_emit = next_trace(c);
+        CK(launch_meshlet_emit_pair(p, m, (int)emit_grid, (cudaStream_t)stream));
+    }
     return ORBIT_OK;
+}
+
+int orbit_meshlet_cull_late_main(orbit_ctx* c, const OrbitCullInfo* late, const OrbitCullInfo* main_pass, const OrbitSceneBuffers* scene,
+                                 const orbit_hiz* hiz, const void* late_dispatch_buffer, uint64_t capacity_records,
+                                 void* late_draw_command_buffer, void* main_draw_command_buffer, uint64_t capacity_draws,
+                                 void* late_task_payloads, void* main_task_payloads, void* stream) {
+    if (!main_draw_command_buffer || ((uintptr_t)main_draw_command_buffer & 3u) || ((uintptr_t)main_task_payloads & 3u) ||
+        main_draw_command_buffer == late_draw_command_buffer) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (!orbit_cull_pair_compatible(late, main_pass)) return ORBIT_ERR_INVALID_ARGUMENT;
+    const MainPassOutputs mo{main_pass, main_draw_command_buffer, main_task_payloads};
+    return meshlet_stage(c, late, scene, hiz, late_dispatch_buffer, capacity_records, late_draw_command_buffer, capacity_draws,
+                         late_task_payloads, nullptr, stream, &mo);
 }
 
 int orbit_meshlet_cull(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSceneBuffers* scene, const orbit_hiz* hiz,

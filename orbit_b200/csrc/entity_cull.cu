@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
                 p.dispatch_words[0] = base + tile_total;   // workgroup_count_x
                 p.dispatch_words[1] = 1u;                  // fill_buffer {.,1,1}: draw_gen.rs:356-363
                 p.dispatch_words[2] = 1u;
+                if (p.dispatch_mirror != nullptr) { p.dispatch_mirror[0] = base + tile_total; p.dispatch_mirror[1] = 1u; p.dispatch_mirror[2] = 1u; }
                 if ((uint64_t)base + tile_total > p.capacity_records) *p.overflow_flag = 1u;
             }
         }
@@ -193,12 +194,15 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
         const uint32_t k = j - s_excl[lo];
         const uint64_t out = base + j;
         if (out < p.capacity_records) {
-            uint32_t* rec = p.dispatch_words + 3u + out * 4u;
             const uint32_t cnt = s_cnt[lo];
-            rec[0] = s_entity[lo];
-            rec[1] = s_off[lo] + 32u * k;
-            rec[2] = min(cnt - 32u * k, 32u);
-            rec[3] = s_vo[lo] + k;   // every earlier chunk of this draw is full, so += count/32 adds exactly 1 each
+            // every earlier chunk of this draw is full, so visibility_offset += count/32 adds exactly 1 each
+            const uint4 rec = make_uint4(s_entity[lo], s_off[lo] + 32u * k, min(cnt - 32u * k, 32u), s_vo[lo] + k);
+            uint32_t* dst = p.dispatch_words + 3u + out * 4u;                    // records start 12 bytes into the buffer: word stores
+            dst[0] = rec.x; dst[1] = rec.y; dst[2] = rec.z; dst[3] = rec.w;
+            if (p.dispatch_mirror != nullptr) {
+                dst = p.dispatch_mirror + 3u + out * 4u;
+                dst[0] = rec.x; dst[1] = rec.y; dst[2] = rec.z; dst[3] = rec.w;
+            }
         }
     }
     ORBIT_TRACE_STAMP(p.scan.trace, 0, 6);

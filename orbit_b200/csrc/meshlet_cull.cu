@@ -333,10 +333,12 @@ struct RecordWords { uint32_t ent, moff, cnt, vo; };
 template <int kProj>
 __device__ __forceinline__ uint32_t drain_candidates(const MeshletCullParams& p, const PkConsts& k, const uint32_t qbase, const uint32_t ring_mask, const uint32_t qhead,
                                                   const uint32_t n, uint32_t* const chunk_counts, const uint32_t chunk_shift,
-                                                  const uint32_t hiz_lw, const uint32_t hiz_lh, const uint32_t lane) {
+                                                  const uint32_t hiz_lw, const uint32_t hiz_lh, const uint32_t lane,
+                                                  uint32_t* const main_chunk_counts, uint32_t& main_drawn_out) {
     const OrbitCullInfo& ci = p.cull;
     const uint32_t cs4 = (ring_mask + 1u) * 4u;      // bytes between the component arrays of the ring
-    uint32_t drawn = 0u;
+    // per slot c: record, and the lane's bit where the candidate goes into the LATE / the MAIN list
+    uint32_t rec_c[2] = {0u, 0u}, late_bit[2] = {0u, 0u}, main_bit[2] = {0u, 0u};
     if (2u * lane < n) {
         // candidates 2*lane and 2*lane+1 sit in adjacent slots (qhead is even: the ring advances by 64 or empties)
         const uint32_t qa = qbase + ((qhead + 2u * lane) & ring_mask) * 4u;
@@ -358,16 +360,37 @@ __device__ __forceinline__ uint32_t drain_candidates(const MeshletCullParams& p,
                 // should_draw = visible && !visible_last_frame (this overrides the alpha filter, meshlet_cull.comp:207-213)
                 const uint32_t abit = shl1(id >> 6);
                 const bool draw = (abit & ci.noskip_alpha_mode) ? (abit & ci.alpha_mode_flags) != 0u : (id & 32u) == 0u;
-                if (draw) {
-                    atomicOr(reinterpret_cast<uint32_t*>(p.draw_masks + rec), bit);
-                    atomicAdd(chunk_counts + (rec >> chunk_shift), 1u);
-                    ++drawn;
-                }
+                rec_c[c] = rec;
+                if (draw) late_bit[c] = bit;
+                // fused MAIN pass: pass 1 over the bit just written, same camera — visible there is this `visible`, and
+                // should_draw = visible && alpha passes the MAIN pass's filter (meshlet_cull.comp:137,207)
+                if (main_chunk_counts != nullptr && (abit & p.main_alpha_mode_flags) != 0u) main_bit[c] = bit;
             }
         }
     }
     __syncwarp();
-    return __reduce_add_sync(0xFFFFFFFFu, drawn);
+    // The candidates of a drain are in record order, so the lanes of a slot that go into a list mostly share a few records and
+    // chunks: one RED.OR per record and one RED.ADD per chunk from the warp instead of one each per candidate (the chunk
+    // counters of the visible part of the scene are a few dozen addresses; per-candidate atomics on them cost the fused late
+    // pass of C2 10 us). Skipped with one ballot when the slot has nothing for the list (the late list of a steady frame).
+    const uint32_t lt = (1u << lane) - 1u;
+    auto publish = [&](uint4* const masks, uint32_t* const counts, const uint32_t rec, const uint32_t bit) -> uint32_t {
+        const uint32_t any = __ballot_sync(0xFFFFFFFFu, bit != 0u);
+        if (any == 0u) return 0u;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bit != 0u ? rec : 0xFFFFFFFFu);
+        const uint32_t ored = __reduce_or_sync(peers, bit);
+        if (bit != 0u && (peers & lt) == 0u) atomicOr(reinterpret_cast<uint32_t*>(masks + rec), ored);
+        const uint32_t chunk = bit != 0u ? (rec >> chunk_shift) : 0xFFFFFFFFu;
+        const uint32_t cpeers = __match_any_sync(0xFFFFFFFFu, chunk);
+        if (bit != 0u && (cpeers & lt) == 0u) atomicAdd(counts + chunk, (uint32_t)__popc(cpeers));
+        return (uint32_t)__popc(any);
+    };
+    uint32_t drawn = 0u;
+    if (__any_sync(0xFFFFFFFFu, (late_bit[0] | late_bit[1]) != 0u))
+        drawn = publish(p.draw_masks, chunk_counts, rec_c[0], late_bit[0]) + publish(p.draw_masks, chunk_counts, rec_c[1], late_bit[1]);
+    if (main_chunk_counts != nullptr && __any_sync(0xFFFFFFFFu, (main_bit[0] | main_bit[1]) != 0u))
+        main_drawn_out += publish(p.main_masks, main_chunk_counts, rec_c[0], main_bit[0]) + publish(p.main_masks, main_chunk_counts, rec_c[1], main_bit[1]);
+    return drawn;
 }
 
 // ---- TMA bulk copy + mbarrier plumbing (PTX; SASS: UBLKCP / SYNCS) --------------------------------------------
@@ -505,6 +528,13 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
     if (blockIdx.x == 0 && threadIdx.x == 0) p.chunk_parity[1] = half;
     uint32_t* const chunk_counts = p.chunk_counts + half * kMaxChunks;
     uint32_t* const draw_total = p.draw_total + half;
+    uint32_t* main_chunk_counts = nullptr;            // fused MAIN pass (pass 2 only): its own double-buffered scratch
+    uint32_t main_total = 0u, mhalf = 0u;
+    if (kPass2 && p.main_masks != nullptr) {
+        mhalf = __ldcg(p.main_chunk_parity) & 1u;
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.main_chunk_parity[1] = mhalf;
+        main_chunk_counts = p.main_chunk_counts + mhalf * kMaxChunks;
+    }
     const uint32_t tiles_total = (nrec + R - 1) / R;
     // row `lane&3` of the view matrix, for the 16-lane view*model product
     const uint32_t vrow_i = lane & 3u;
@@ -580,7 +610,10 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
                     vw = ws.vis[lane];
                     p.meshlet_visibility[my_vo] = 0u;
                 }
-                if (lane < (uint32_t)R && rec0 + lane < nrec) p.draw_masks[rec0 + lane] = make_uint4(0u, ent, mof, 1u);   // .w = 1: no side-array entries, the emit kernel reads the meshlet
+                if (lane < (uint32_t)R && rec0 + lane < nrec) {
+                    p.draw_masks[rec0 + lane] = make_uint4(0u, ent, mof, 1u);   // .w = 1: no side-array entries, the emit kernel reads the meshlet
+                    if (main_chunk_counts != nullptr) p.main_masks[rec0 + lane] = make_uint4(0u, ent, mof, 1u);
+                }
             } else {
                 cp_async_wait_all();
                 __syncwarp();
@@ -642,7 +675,8 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
             if (kPass2 && (qn >= 64u || (final_pass && qn != 0u))) {
                 const uint32_t n = min(qn, 64u);
                 __syncwarp();
-                warp_total += drain_candidates<kProj>(p, k, qbase, kRing - 1u, qhead, n, chunk_counts, chunk_shift, hiz_lw, hiz_lh, lane);
+                warp_total += drain_candidates<kProj>(p, k, qbase, kRing - 1u, qhead, n, chunk_counts, chunk_shift, hiz_lw, hiz_lh, lane,
+                                                      main_chunk_counts, main_total);
                 qhead = (qhead + n) & (kRing - 1u);
                 qn -= n;
             }
@@ -668,6 +702,7 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
     ORBIT_TRACE_STAMP(p.scan.trace, 1, 3);
     pdl_launch_dependents();
     if (lane == 0u && warp_total != 0u) atomicAdd(draw_total, warp_total);
+    if (kPass2 && lane == 0u && main_total != 0u) atomicAdd(p.main_draw_total + mhalf, main_total);
 #ifdef ORBIT_TRACE
     __syncthreads();
     ORBIT_TRACE_STAMP(p.scan.trace, 1, 4);
@@ -913,7 +948,7 @@ __device__ __forceinline__ uint32_t select_set_bit(uint32_t m, uint32_t n) {
 //      flipped — no done-counter, fence or atomic on the way out (that exit chain was ~1/3 of this kernel's samples).
 constexpr int kEmitWarps = 8;
 constexpr uint32_t kMaxRegions = 16u;   // ranks of a sharded view (orbit_draws_from_masks)
-__global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __grid_constant__ MeshletCullParams p) {
+__device__ __forceinline__ void meshlet_emit_body(const MeshletCullParams& p) {
     __shared__ uint32_t s_prefix[kMaxChunks];            // inclusive survivor count up to chunk c
     __shared__ uint32_t s_warp_total[kEmitWarps];
     __shared__ uint32_t s_rec[kEmitWarps][4][32];
@@ -1137,6 +1172,13 @@ __global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __g
     }
 }
 
+__global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_kernel(const __grid_constant__ MeshletCullParams p) { meshlet_emit_body(p); }
+
+// Two lists in one launch (fused LATE + MAIN: blockIdx.y = 0 emits the LATE list, 1 the MAIN list; each list's CTAs only ever
+// look at blockIdx.x / gridDim.x): the LATE list of a steady frame is empty, and its emit kernel was 3 us of launch + look.
+struct EmitPair { MeshletCullParams list[2]; };
+__global__ void __launch_bounds__(kEmitWarps * 32) meshlet_emit_pair_kernel(const __grid_constant__ EmitPair pp) { meshlet_emit_body(pp.list[blockIdx.y]); }
+
 // ---------------------------------------------------------------------------------------------------------
 // Multi-GPU (meshlet ranges of one view): a rank that only TESTS its records ships the 16-byte
 // {draw mask, entity, meshlet offset, 1} entries instead of 28-byte draw commands (C3: 28 MB instead of 229 MB to the
@@ -1276,6 +1318,15 @@ int meshlet_cull_max_ctas_per_sm(const MeshletCullParams& p) {
     int n = 0;
     launch_test(p, 0, nullptr, &n);
     return n;
+}
+
+cudaError_t launch_meshlet_emit(const MeshletCullParams& p, int emit_grid, cudaStream_t stream) {
+    return launch_kernel(meshlet_emit_kernel, dim3(emit_grid), dim3(kEmitWarps * 32), 0, stream, p);
+}
+cudaError_t launch_meshlet_emit_pair(const MeshletCullParams& a, const MeshletCullParams& b, int emit_grid, cudaStream_t stream) {
+    EmitPair pp;
+    pp.list[0] = a; pp.list[1] = b;
+    return launch_kernel(meshlet_emit_pair_kernel, dim3(emit_grid, 2), dim3(kEmitWarps * 32), 0, stream, pp);
 }
 
 cudaError_t launch_meshlet_cull(const MeshletCullParams& p, int grid, int emit_grid, cudaStream_t stream) {

@@ -47,6 +47,13 @@ struct MeshletCullParams {
     const uint32_t* region_counts;
     uint64_t region_stride;
     uint32_t n_regions;
+    // fused LATE + MAIN (orbit_meshlet_cull_late_main), else main_masks == nullptr: the pass-2 test kernel also fills the MAIN
+    // pass's record entries (pass 1 over the bits it is writing: should_draw = visible && alpha filter) and survivor counts
+    uint4* main_masks;
+    uint32_t* main_chunk_counts;      // 2 x 2048, double-buffered like chunk_counts
+    uint32_t* main_chunk_parity;      // [2], like chunk_parity
+    uint32_t* main_draw_total;        // [2], like draw_total
+    uint32_t main_alpha_mode_flags;
 };
 
 struct EntityCullParams {
@@ -57,6 +64,7 @@ struct EntityCullParams {
     const float4* entities;              // 8 x float4 each
     uint32_t* entity_visibility;
     uint32_t* dispatch_words;            // MeshletDispatchBuffer as u32[]: x,y,z then 4 words per record
+    uint32_t* dispatch_mirror;           // nullable: a second buffer that receives the same header and records (fused LATE + MAIN)
     uint32_t* overflow_flag;
     uint64_t capacity_records;
     uint32_t draw_begin, draw_end;       // sub-range of draws covered by this launch (begin % 32 == 0)
@@ -129,6 +137,8 @@ cudaError_t meshlet_cull_configure_device();
 cudaError_t light_cluster_configure_device();
 cudaError_t launch_record_masks_put(const uint4* src, const uint32_t* dispatch_words, uint4* dst_region, uint32_t* dst_count, uint64_t capacity,
                                     int grid, cudaStream_t s);
+cudaError_t launch_meshlet_emit(const MeshletCullParams& p, int emit_grid, cudaStream_t s);
+cudaError_t launch_meshlet_emit_pair(const MeshletCullParams& a, const MeshletCullParams& b, int emit_grid, cudaStream_t s);
 cudaError_t launch_draws_from_masks(const MeshletCullParams& p, uint32_t* header, int grid, int emit_grid, cudaStream_t s);
 cudaError_t launch_entity_cull(const EntityCullParams&, uint32_t n_draws, uint32_t coresident_ctas, cudaStream_t);
 int entity_cull_max_ctas_per_sm();

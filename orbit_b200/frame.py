@@ -88,6 +88,36 @@ def main_pass_culling(context, dscene, vstate, view, meshlet_occlusion=True, nam
     return cull_pass(context, name, dscene, info)
 
 
+def late_and_main_culling(context, dscene, vstate, view, meshlet_occlusion=True, name="forward_depth_prepass", main_name="forward"):
+    """LATE + MAIN in their fused form (orbit_entity_cull_late_main / orbit_meshlet_cull_late_main): byte for byte the buffers of
+    the LATE half of depth_prepass_culling followed by main_pass_culling, from one entity kernel and one test kernel. Expects the
+    pyramid to be up to date. Raises if the two CullInfos are not a compatible pair (see orbit_cuda.h)."""
+    import ctypes as C
+    from . import _lib
+    from .passes import _ptr, _scene_buffers, _stream
+    mvis = vstate.meshlet_visibility if meshlet_occlusion else None
+    late = cull_info_for(view, OcclusionCullInfo("write", vstate.entity_visibility, mvis, vstate.depth_pyramid,
+                                                 noskip_alphamode=0, aspect_ratio=view.aspect))
+    main = cull_info_for(view, OcclusionCullInfo("read", vstate.entity_visibility, mvis))
+    gl, gm = late.to_gpu(), main.to_gpu()
+    lib = _lib.lib()
+    if not lib.orbit_cull_pair_compatible(C.byref(gl), C.byref(gm)):
+        raise ValueError("LATE and MAIN CullInfos are not a compatible pair: call the passes separately")
+    sc = dscene.scene
+    rcap, dcap = int(sc.record_capacity) or 1_000_000, int(sc.draw_capacity) or 1_000_000
+    mk = context.create_transient
+    out = {}
+    for k, n in (("late", "late_" + name), ("main", main_name)):
+        out[k] = (mk(n + "_meshlet_dispatch_buffer", L.DISPATCH_HEADER + 16 * rcap), mk(n + "_meshlet_draw_command_buffer", L.DRAW_HEADER + 28 * dcap))
+    sb = _scene_buffers(dscene.assets, sc, late)
+    _lib.check(lib.orbit_entity_cull_late_main(context._h, C.byref(gl), C.byref(gm), C.byref(sb), vstate.depth_pyramid._h,
+                                               _ptr(out["late"][0]), _ptr(out["main"][0]), rcap, _stream(context)), "orbit_entity_cull_late_main")
+    _lib.check(lib.orbit_meshlet_cull_late_main(context._h, C.byref(gl), C.byref(gm), C.byref(sb), vstate.depth_pyramid._h,
+                                                _ptr(out["late"][0]), rcap, _ptr(out["late"][1]), _ptr(out["main"][1]), dcap, None, None,
+                                                _stream(context)), "orbit_meshlet_cull_late_main")
+    return out
+
+
 def shadow_pass_culling(context, dscene, view, name="shadow"):
     """One cascade (shadow_renderer.rs:693-707): pass 0, no occlusion."""
     return cull_pass(context, name, dscene, cull_info_for(view, OcclusionCullInfo("none")))
@@ -116,7 +146,8 @@ class PreparedFrame:
     asynchronous stage calls on one stream, optionally captured into a CUDA graph (`capture()` / `replay()`) so
     a frame costs one graph launch. Safe to replay: the scan epoch and tickets live in device memory."""
 
-    def __init__(self, context, dscene, vstate, view, depth_buffer, meshlet_occlusion=True, name="forward_depth_prepass", main_pass=False):
+    def __init__(self, context, dscene, vstate, view, depth_buffer, meshlet_occlusion=True, name="forward_depth_prepass", main_pass=False,
+                 fuse_late_main=True):
         import ctypes as C
         from . import _lib
         from .passes import _ptr, _scene_buffers
@@ -142,6 +173,8 @@ class PreparedFrame:
         if main_pass:
             self.main_dispatch = mk("main_" + name + "_meshlet_dispatch_buffer", L.DISPATCH_HEADER + 16 * self.rcap)
             self.main_draws = mk("main_" + name + "_meshlet_draw_command_buffer", L.DRAW_HEADER + 28 * self.dcap)
+        # LATE + MAIN fused (one entity kernel, one test kernel, an emit kernel per list) whenever the pair allows it
+        self.fused = bool(main_pass and fuse_late_main and self._lib.orbit_cull_pair_compatible(C.byref(self.g_late), C.byref(self.g_early)))
         self.graph = None
         h, w = depth_buffer.shape
         self._hw = (w, h)
@@ -175,6 +208,21 @@ class PreparedFrame:
         if rc:
             raise RuntimeError("orbit_meshlet_cull: %d" % rc)
 
+    def entity_late_main(self, s=None):
+        C, lib, p = self._C, self._lib, self._ptr
+        rc = lib.orbit_entity_cull_late_main(self.context._h, C.byref(self.g_late), C.byref(self.g_early), C.byref(self.sb_late),
+                                             self.vstate.depth_pyramid._h, p(self.late_dispatch), p(self.main_dispatch), self.rcap, s or self._stream())
+        if rc:
+            raise RuntimeError("orbit_entity_cull_late_main: %d" % rc)
+
+    def meshlet_late_main(self, s=None, context=None):
+        C, lib, p = self._C, self._lib, self._ptr
+        rc = lib.orbit_meshlet_cull_late_main((context or self.context)._h, C.byref(self.g_late), C.byref(self.g_early), C.byref(self.sb_late),
+                                              self.vstate.depth_pyramid._h, p(self.late_dispatch), self.rcap, p(self.late_draws), p(self.main_draws),
+                                              self.dcap, None, None, s or self._stream())
+        if rc:
+            raise RuntimeError("orbit_meshlet_cull_late_main: %d" % rc)
+
     def meshlet_test(self, late, record_masks, s=None):
         """The test half of the meshlet stage (orbit_meshlet_test): visibility words + one 16-byte entry per dispatch record into
         `record_masks`; used by the sharded view, whose draw commands are emitted on the rank that submits them."""
@@ -200,7 +248,11 @@ class PreparedFrame:
         with a static tile split — ends 7 us later when 40 SMs start a third of their CTAs late, so the frame gains nothing
         (104.5 vs 104.2 us); off by default, kept because it is bit-identical and pays off when the late pass is small."""
         s = self._stream()
-        self.entity(False, s); self.meshlet(False, s); self.hiz(s); self.entity(True, s)
+        self.entity(False, s); self.meshlet(False, s); self.hiz(s)
+        if self.fused:
+            self.entity_late_main(s); self.meshlet_late_main(s)
+            return
+        self.entity(True, s)
         if not self.main_pass:
             self.meshlet(True, s)
             return

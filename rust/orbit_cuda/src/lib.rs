@@ -131,6 +131,14 @@ extern "C" {
     pub fn orbit_light_cluster(ctx: *mut orbit_ctx, params: *const OrbitClusterParams, depth: *const f32, lights: *const c_void,
                                tile_masks: *mut c_void, depth_bounds: *mut c_void, unique_clusters: *mut c_void,
                                offset_count_image: *mut c_void, light_index_list: *mut c_void, capacity_indices: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_cull_pair_compatible(late: *const OrbitCullInfo, main_pass: *const OrbitCullInfo) -> c_int;
+    pub fn orbit_entity_cull_late_main(ctx: *mut orbit_ctx, late: *const OrbitCullInfo, main_pass: *const OrbitCullInfo, scene: *const OrbitSceneBuffers,
+                                       hiz: *const orbit_hiz, late_dispatch_buffer: *mut c_void, main_dispatch_buffer: *mut c_void,
+                                       capacity_records: u64, stream: *mut c_void) -> c_int;
+    pub fn orbit_meshlet_cull_late_main(ctx: *mut orbit_ctx, late: *const OrbitCullInfo, main_pass: *const OrbitCullInfo, scene: *const OrbitSceneBuffers,
+                                        hiz: *const orbit_hiz, late_dispatch_buffer: *const c_void, capacity_records: u64,
+                                        late_draw_command_buffer: *mut c_void, main_draw_command_buffer: *mut c_void, capacity_draws: u64,
+                                        late_task_payloads: *mut c_void, main_task_payloads: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn orbit_draws_scatter_ranked(ctx: *mut orbit_ctx, src_draw_buffer: *const c_void, src_capacity_draws: u64, dst_draw_buffer: *mut c_void,
                                       rank_counts: *const u32, rank: u32, world: u32, dst_capacity_draws: u64, stream: *mut c_void) -> i32;
     pub fn orbit_meshlet_test(ctx: *mut orbit_ctx, cull: *const OrbitCullInfo, scene: *const OrbitSceneBuffers, hiz: *const orbit_hiz,
