@@ -1025,7 +1025,67 @@ __device__ __forceinline__ void meshlet_emit_body(const MeshletCullParams& p) {
         const uint32_t o_end = (uint32_t)(((uint64_t)total * (gw + 1u)) / GW);
         uint32_t* const sr = &s_rec[warp][0][0];
         uint32_t* const stage = &s_payload[warp][0];          // command staging (the task-payload pass below runs after the emission)
-        if (o_begin < o_end) {
+        if (o_begin < o_end && chunk_rec == 32u) {
+            // ---- 2a. lists of at most 65 536 records (a chunk IS one 32-record group): every LANE locates its own output.
+            // The prefix gives the group of output o and its rank k inside it; the lane reads the group's 32 mask words (32
+            // independent 4-byte loads: lanes of the same group hit the same sectors), finds the record holding the k-th survivor,
+            // then fetches the record's entry and the command words together. Two dependent round trips however sparse the
+            // survivors are — the group walk below pays one per 4 groups, and a share of ~30 outputs in a sparse stretch of the
+            // C2 lists took up to seven (profiles/r2_frame_timeline_before.txt: emitted after 3.3 .. 7.9 us).
+            const bool side_possible = p.cmd_side != nullptr && p.cull.occlusion_pass != 2u;   // pass-2 entries never have side words
+            for (uint32_t ob = o_begin; ob < o_end; ob += 32u) {
+                const bool act = ob + lane < o_end;
+                const uint32_t o = act ? ob + lane : o_end - 1u;                // idle lanes shadow the share's last output
+                uint32_t lo = 0u, hi = nchunks - 1u;
+#pragma unroll 1
+                while (__any_sync(0xFFFFFFFFu, lo < hi)) {
+                    if (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (s_prefix[mid] > o) hi = mid; else lo = mid + 1u;
+                    }
+                }
+                const uint32_t k = o - (lo ? s_prefix[lo - 1u] : 0u);
+                const uint32_t rec0 = lo * 32u;
+                uint32_t m[32];
+                if (p.n_regions == 0u) {            // entries in record order: 32 plain loads, nothing between them
+                    const uint32_t* const mw = reinterpret_cast<const uint32_t*>(p.draw_masks + rec0);
+#pragma unroll
+                    for (uint32_t r = 0; r < 32u; ++r) m[r] = rec0 + r < nrec ? __ldcg(mw + 4u * r) : 0u;
+                } else {                            // sharded view: a group may straddle two ranks' regions
+#pragma unroll 1
+                    for (uint32_t r = 0; r < 32u; ++r) {
+                        const uint32_t v = rec0 + r < nrec ? __ldcg(reinterpret_cast<const uint32_t*>(p.draw_masks + entry_of(rec0 + r))) : 0u;
+#pragma unroll
+                        for (uint32_t q = 0; q < 32u; ++q) if (q == r) m[q] = v;
+                    }
+                }
+                uint32_t acc = 0u, rsel = 0u, ksel = 0u, msel = 1u;
+#pragma unroll
+                for (uint32_t r = 0; r < 32u; ++r) {
+                    const uint32_t pc = (uint32_t)__popc(m[r]);
+                    if (k >= acc && k < acc + pc) { rsel = r; ksel = k - acc; msel = m[r]; }
+                    acc += pc;
+                }
+                const uint32_t j = select_set_bit(msel, ksel);
+                const uint32_t rec = rec0 + rsel;
+                const uint4 e = __ldcg(p.draw_masks + entry_of(rec));
+                uint4 cw = make_uint4(0u, 0u, 0u, 0u);
+                if (side_possible) cw = __ldcg(p.cmd_side + (size_t)rec * 32u + j);
+                const uint32_t midx = e.z + j;
+                if (e.w & 1u) { const uint4 mb = __ldg(p.meshlets + 2u * (size_t)midx + 1); cw = make_uint4(mb.y, mb.z, mb.w, 0u); }
+                else if (!side_possible) cw = __ldcg(p.cmd_side + (size_t)rec * 32u + j);
+                __syncwarp();
+                if (act) store_command(stage + lane * 7u, cw.x, cw.y, cw.z, e.y, midx);
+                __syncwarp();
+                const uint64_t first = ob;
+                uint64_t n_out = min(32u, o_end - ob);
+                if (first >= p.capacity_draws) n_out = 0u; else if (first + n_out > p.capacity_draws) n_out = p.capacity_draws - first;
+                uint32_t* const dst = p.draw_words + 1u + first * 7u;
+                for (uint32_t w = lane; w < (uint32_t)n_out * 7u; w += 32u) dst[w] = stage[w];
+            }
+            ORBIT_TRACE_STAMP(p.trace_emit, 3, 6);
+        } else if (o_begin < o_end) {
+            // ---- 2b. longer lists: walk the groups of the share
             // chunk holding output o_begin: first c with P[c] > o_begin
             uint32_t lo = 0u, hi = nchunks - 1u;
             while (lo < hi) {
