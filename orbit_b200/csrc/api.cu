@@ -295,7 +295,12 @@ int orbit_ctx_reserve(orbit_ctx* c, uint64_t entity_draws, uint64_t capacity_rec
     if ((size_t)n_clusters + 1u > tiles) tiles = (size_t)n_clusters + 1u;
     int rc = ensure_status(c, tiles, nullptr);
     if (rc == ORBIT_OK && capacity_records) rc = ensure_record_scratch(c, capacity_records);
+    if (rc == ORBIT_OK && capacity_records) rc = ensure_main_masks(c, capacity_records);        // fused LATE + MAIN
     if (rc == ORBIT_OK && n_lights) rc = ensure_lights(c, n_lights);
+    if (rc == ORBIT_OK && n_lights && n_clusters) {                                             // light-parallel culling path
+        const uint64_t words = light_hits_words_needed(n_clusters, n_lights);
+        if (words * 4u <= c->light_hits_budget) rc = ensure_light_hits(c, words);
+    }
     if (rc == ORBIT_OK && n_entities) rc = ensure_tile_sums(c, ((size_t)n_entities + 255u) / 256u);
     if (rc != ORBIT_OK) return rc;
     CK(cudaDeviceSynchronize());   // the one place that may synchronise: after this, stage calls within these sizes never allocate

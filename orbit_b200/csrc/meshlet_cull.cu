@@ -337,8 +337,10 @@ __device__ __forceinline__ uint32_t drain_candidates(const MeshletCullParams& p,
                                                   uint32_t* const main_chunk_counts, uint32_t& main_drawn_out) {
     const OrbitCullInfo& ci = p.cull;
     const uint32_t cs4 = (ring_mask + 1u) * 4u;      // bytes between the component arrays of the ring
-    // per slot c: record, and the lane's bit where the candidate goes into the LATE / the MAIN list
-    uint32_t rec_c[2] = {0u, 0u}, late_bit[2] = {0u, 0u}, main_bit[2] = {0u, 0u};
+    // per lane: the record of its first visible candidate with the bits the lane contributes to that record's visibility word
+    // / LATE entry / MAIN entry, and — when the lane's two candidates belong to different records — the second one apart
+    uint32_t rec0 = 0xFFFFFFFFu, vo0 = 0u, vbits = 0u, lbits = 0u, mbits = 0u;
+    uint32_t rec1 = 0xFFFFFFFFu, vo1 = 0u, vbit1 = 0u, lbit1 = 0u, mbit1 = 0u;
     if (2u * lane < n) {
         // candidates 2*lane and 2*lane+1 sit in adjacent slots (qhead is even: the ring advances by 64 or empties)
         const uint32_t qa = qbase + ((qhead + 2u * lane) & ring_mask) * 4u;
@@ -355,41 +357,50 @@ __device__ __forceinline__ uint32_t drain_candidates(const MeshletCullParams& p,
             if ((vis >> c) & 1u) {
                 const uint32_t rec = lds32(qa + 5u * cs4 + c * 4u), vo = lds32(qa + 6u * cs4 + c * 4u), id = lds32(qa + 7u * cs4 + c * 4u);
                 const uint32_t bit = 1u << (id & 31u);
-                atomicOr(p.meshlet_visibility + vo, bit);
                 // should_draw = visible && alpha passes the filter; in pass 2, unless the alpha mode is "noskip",
                 // should_draw = visible && !visible_last_frame (this overrides the alpha filter, meshlet_cull.comp:207-213)
                 const uint32_t abit = shl1(id >> 6);
                 const bool draw = (abit & ci.noskip_alpha_mode) ? (abit & ci.alpha_mode_flags) != 0u : (id & 32u) == 0u;
-                rec_c[c] = rec;
-                if (draw) late_bit[c] = bit;
-                // fused MAIN pass: pass 1 over the bit just written, same camera — visible there is this `visible`, and
+                // fused MAIN pass: pass 1 over the bit being written, same camera — visible there is this `visible`, and
                 // should_draw = visible && alpha passes the MAIN pass's filter (meshlet_cull.comp:137,207)
-                if (main_chunk_counts != nullptr && (abit & p.main_alpha_mode_flags) != 0u) main_bit[c] = bit;
+                const bool mdraw = main_chunk_counts != nullptr && (abit & p.main_alpha_mode_flags) != 0u;
+                if (rec0 == 0xFFFFFFFFu || rec == rec0) {
+                    rec0 = rec; vo0 = vo; vbits |= bit; if (draw) lbits |= bit; if (mdraw) mbits |= bit;
+                } else {
+                    rec1 = rec; vo1 = vo; vbit1 = bit; if (draw) lbit1 = bit; if (mdraw) mbit1 = bit;
+                }
             }
         }
     }
     __syncwarp();
-    // The candidates of a drain are in record order, so the lanes of a slot that go into a list mostly share a few records and
-    // chunks: one RED.OR per record and one RED.ADD per chunk from the warp instead of one each per candidate (the chunk
-    // counters of the visible part of the scene are a few dozen addresses; per-candidate atomics on them cost the fused late
-    // pass of C2 10 us). Skipped with one ballot when the slot has nothing for the list (the late list of a steady frame).
-    const uint32_t lt = (1u << lane) - 1u;
-    auto publish = [&](uint4* const masks, uint32_t* const counts, const uint32_t rec, const uint32_t bit) -> uint32_t {
-        const uint32_t any = __ballot_sync(0xFFFFFFFFu, bit != 0u);
-        if (any == 0u) return 0u;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bit != 0u ? rec : 0xFFFFFFFFu);
-        const uint32_t ored = __reduce_or_sync(peers, bit);
-        if (bit != 0u && (peers & lt) == 0u) atomicOr(reinterpret_cast<uint32_t*>(masks + rec), ored);
-        const uint32_t chunk = bit != 0u ? (rec >> chunk_shift) : 0xFFFFFFFFu;
-        const uint32_t cpeers = __match_any_sync(0xFFFFFFFFu, chunk);
-        if (bit != 0u && (cpeers & lt) == 0u) atomicAdd(counts + chunk, (uint32_t)__popc(cpeers));
-        return (uint32_t)__popc(any);
-    };
+    // Publication, once per RECORD instead of once per candidate: the candidates of a drain are in record order, so the lanes
+    // that found something mostly share two or three records. The lanes of a record (match.any) OR their bits together and
+    // the lowest of them issues one RED.OR per word — visibility word, LATE entry, MAIN entry — and one RED.ADD of the
+    // popcount per list to the record's chunk counter (the bits of a record are distinct, so the popcount of the OR is the
+    // number of survivors). Per-candidate atomics on the few dozen chunk counters of the visible part of the scene cost the
+    // fused late pass of C2 10 us. A lane whose two candidates straddle a record boundary publishes the second one itself.
     uint32_t drawn = 0u;
-    if (__any_sync(0xFFFFFFFFu, (late_bit[0] | late_bit[1]) != 0u))
-        drawn = publish(p.draw_masks, chunk_counts, rec_c[0], late_bit[0]) + publish(p.draw_masks, chunk_counts, rec_c[1], late_bit[1]);
-    if (main_chunk_counts != nullptr && __any_sync(0xFFFFFFFFu, (main_bit[0] | main_bit[1]) != 0u))
-        main_drawn_out += publish(p.main_masks, main_chunk_counts, rec_c[0], main_bit[0]) + publish(p.main_masks, main_chunk_counts, rec_c[1], main_bit[1]);
+    if (__any_sync(0xFFFFFFFFu, vbits != 0u)) {
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, rec0);
+        const uint32_t v = __reduce_or_sync(peers, vbits);
+        const bool any_late = __any_sync(0xFFFFFFFFu, (lbits | lbit1) != 0u);
+        const uint32_t l = any_late ? __reduce_or_sync(peers, lbits) : 0u;
+        const uint32_t m = main_chunk_counts != nullptr ? __reduce_or_sync(peers, mbits) : 0u;
+        if (vbits != 0u && (peers & lt) == 0u) {
+            atomicOr(p.meshlet_visibility + vo0, v);
+            if (l != 0u) { atomicOr(reinterpret_cast<uint32_t*>(p.draw_masks + rec0), l); atomicAdd(chunk_counts + (rec0 >> chunk_shift), (uint32_t)__popc(l)); }
+            if (m != 0u) { atomicOr(reinterpret_cast<uint32_t*>(p.main_masks + rec0), m); atomicAdd(main_chunk_counts + (rec0 >> chunk_shift), (uint32_t)__popc(m)); }
+        }
+        if (vbit1 != 0u) {
+            atomicOr(p.meshlet_visibility + vo1, vbit1);
+            if (lbit1 != 0u) { atomicOr(reinterpret_cast<uint32_t*>(p.draw_masks + rec1), lbit1); atomicAdd(chunk_counts + (rec1 >> chunk_shift), 1u); }
+            if (mbit1 != 0u) { atomicOr(reinterpret_cast<uint32_t*>(p.main_masks + rec1), mbit1); atomicAdd(main_chunk_counts + (rec1 >> chunk_shift), 1u); }
+        }
+        __syncwarp();
+        if (any_late) drawn = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(lbits) + (lbit1 != 0u ? 1u : 0u));
+        if (main_chunk_counts != nullptr) main_drawn_out += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(mbits) + (mbit1 != 0u ? 1u : 0u));
+    }
     return drawn;
 }
 
@@ -433,6 +444,11 @@ constexpr uint32_t kRing = 128u;
 #ifndef ORBIT_DIRECT_MIN_CTAS
 #define ORBIT_DIRECT_MIN_CTAS 3
 #endif
+#ifndef ORBIT_DIRECT_WARPS
+#define ORBIT_DIRECT_WARPS 8
+#endif
+constexpr int kDwWarps = ORBIT_DIRECT_WARPS;     // warps per CTA of the direct test kernel (they share the CTA's tile counter)
+constexpr int kDwThreads = kDwWarps * 32;
 
 // view * model (+ largest column scale) for every record of a tile: 16 lanes per record, two records per step
 template <int R>
@@ -481,7 +497,7 @@ __device__ __forceinline__ void tile_model_view(const float4* rows, float* mv_ba
 // between the stores and the first drain orders the two), likewise the draw masks and the chunks' survivor counts — so
 // a record never waits for its candidates and there are no per-record result masks to carry.
 template <int R, bool kPass2, int kProj>
-__global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_test_direct_kernel(const __grid_constant__ MeshletCullParams p) {
+__global__ void __launch_bounds__(kDwThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_test_direct_kernel(const __grid_constant__ MeshletCullParams p) {
     static_assert(R == 2 || R == 4 || R == 8, "records per warp tile");
     extern __shared__ __align__(128) unsigned char s_raw[];
     WarpSmem<R>* const all = reinterpret_cast<WarpSmem<R>*>(s_raw + 128);
@@ -494,7 +510,7 @@ __global__ void __launch_bounds__(kMcThreads, ORBIT_DIRECT_MIN_CTAS) meshlet_tes
     const PkConsts k = {p.pk_one, p.pk_mone};
     pdl_wait();
     ORBIT_TRACE_STAMP(p.scan.trace, 1, 0);
-    if (threadIdx.x == 0) *s_next_tile = kMcWarps;
+    if (threadIdx.x == 0) *s_next_tile = kDwWarps;
     __syncthreads();
     // ---- this CTA's tiles: local index j -> tile blockIdx.x + j * gridDim.x; j = warp first, then from the counter.
     // (Device-wide dynamic hand-out was measured twice and lost twice: a ticket per tile serialises ~13 k same-address atomics
@@ -1328,15 +1344,15 @@ constexpr int kTileR = ORBIT_TILE_RECORDS;   // records per warp tile of the dir
 #define ORBIT_PACKED_RECORDS 8
 #endif
 constexpr int kPackedR = ORBIT_PACKED_RECORDS;   // records per warp tile of the packed (pass 1) test kernel
-static constexpr size_t direct_smem_bytes() { return 128u + sizeof(WarpSmem<kTileR>) * kMcWarps; }
+static constexpr size_t direct_smem_bytes() { return 128u + sizeof(WarpSmem<kTileR>) * kDwWarps; }
 
 template <bool kPass2, int kProj>
 static cudaError_t launch_stream(const MeshletCullParams& p, int grid, cudaStream_t stream, int* occupancy) {
     if (occupancy) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_direct_kernel<kTileR, kPass2, kProj>, kMcThreads, direct_smem_bytes());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, meshlet_test_direct_kernel<kTileR, kPass2, kProj>, kDwThreads, direct_smem_bytes());
         return cudaSuccess;
     }
-    return launch_kernel(meshlet_test_direct_kernel<kTileR, kPass2, kProj>, dim3(grid), dim3(kMcThreads), direct_smem_bytes(), stream, p);
+    return launch_kernel(meshlet_test_direct_kernel<kTileR, kPass2, kProj>, dim3(grid), dim3(kDwThreads), direct_smem_bytes(), stream, p);
 }
 
 // The direct test kernels use more than 48 KB of dynamic shared memory: opt in once per DEVICE (the attribute is per device,
