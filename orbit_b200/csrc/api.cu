@@ -13,10 +13,12 @@ using namespace orbit;
 
 namespace orbit {
 bool pdl_enabled() {
-    // measured on B200 (profiles/r1_pdl.txt): trigger at kernel ENTRY: frame ~10% slower; trigger at the END of each
-    // kernel's main work: steady-state C2 frame 1.3% faster, but a pass-0 sweep with 1.2M survivors 15% slower.
-    // Not a clear win -> opt-in: ORBIT_PDL=1.
-    static const bool on = std::getenv("ORBIT_PDL") != nullptr;
+    // Programmatic dependent launch between the stage kernels (every kernel waits — griddepcontrol.wait — before its first
+    // global access, and triggers at the end of its main work). Round 1 (profiles/r1_pdl.txt): C2 frame 1.3% faster but a
+    // pass-0 sweep with 1.2M survivors 15% slower -> opt-in. Round 2, with the emit kernel's trigger after its emission and
+    // the per-lane emission path (profiles/r2_pdl.txt): C2 frame 84.5 -> 83.4 us, pass-0 sweep 52.4 -> 52.2 us, C3 1220 ->
+    // 1213 us, C5 185.7 -> 188.7 us per view -> on by default; ORBIT_NO_PDL=1 turns it off.
+    static const bool on = std::getenv("ORBIT_NO_PDL") == nullptr;
     return on;
 }
 }  // namespace orbit
@@ -71,6 +73,7 @@ struct orbit_ctx {
     uint32_t* light_hits = nullptr;   // bit matrix [active cluster][light / 32] of the light-parallel culling path
     size_t light_hits_words = 0;
     // tuning (ORBIT_MC_CTAS_PER_SM environment override, read once)
+    bool prefetch_meshlets = true;    // ORBIT_NO_PREFETCH=1 turns the entity stage's L2 prefetch of meshlets off (experiments)
     int mc_ctas_per_sm = 0;
     int emit_occupancy = 0;
     int debug_skip = 0;               // ORBIT_DEBUG_SKIP: 1 = skip emit kernel, 2 = skip test kernel (timing experiments only)
@@ -258,6 +261,7 @@ int orbit_ctx_create(int device, orbit_ctx** out) {
     CK(cudaMemset(c->trace, 0, 16u * 1024u * 16u * sizeof(unsigned long long)));
 #endif
     if (const char* s = std::getenv("ORBIT_DEBUG_SKIP")) c->debug_skip = std::atoi(s);
+    if (std::getenv("ORBIT_NO_PREFETCH")) c->prefetch_meshlets = false;
     if (const char* s = std::getenv("ORBIT_MC_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->mc_ctas_per_sm = v; }
     c->light_hits_budget = kLightHitsBudgetBytes;
     if (const char* s = std::getenv("ORBIT_LIGHT_HITS_BUDGET_MB")) { const long v = std::atol(s); if (v >= 0) c->light_hits_budget = (uint64_t)v << 20; }
@@ -428,6 +432,9 @@ static int entity_stage(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScen
     p.entity_visibility = scene->entity_visibility;
     p.dispatch_words = (uint32_t*)meshlet_dispatch_buffer;
     p.dispatch_mirror = (uint32_t*)mirror_dispatch_buffer;
+    // passes 0 / 2 test every meshlet of every record: prefetch them into L2 while this kernel drains (pass 1 loads only the
+    // meshlets whose visibility bit is set — a prefetch of whole records would read 15x what it uses on C2)
+    p.prefetch_meshlets = (c->prefetch_meshlets && cull->occlusion_pass != 1u) ? (const uint8_t*)scene->meshlets : nullptr;
     p.overflow_flag = &c->status_dev->dispatch_overflow;
     p.capacity_records = capacity_records;
     p.draw_begin = begin; p.draw_end = end;
