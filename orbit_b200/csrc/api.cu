@@ -73,7 +73,6 @@ struct orbit_ctx {
     uint32_t* light_hits = nullptr;   // bit matrix [active cluster][light / 32] of the light-parallel culling path
     size_t light_hits_words = 0;
     // tuning (ORBIT_MC_CTAS_PER_SM environment override, read once)
-    bool prefetch_meshlets = true;    // ORBIT_NO_PREFETCH=1 turns the entity stage's L2 prefetch of meshlets off (experiments)
     int mc_ctas_per_sm = 0;
     int emit_occupancy = 0;
     int debug_skip = 0;               // ORBIT_DEBUG_SKIP: 1 = skip emit kernel, 2 = skip test kernel (timing experiments only)
@@ -261,7 +260,6 @@ int orbit_ctx_create(int device, orbit_ctx** out) {
     CK(cudaMemset(c->trace, 0, 16u * 1024u * 16u * sizeof(unsigned long long)));
 #endif
     if (const char* s = std::getenv("ORBIT_DEBUG_SKIP")) c->debug_skip = std::atoi(s);
-    if (std::getenv("ORBIT_NO_PREFETCH")) c->prefetch_meshlets = false;
     if (const char* s = std::getenv("ORBIT_MC_CTAS_PER_SM")) { int v = std::atoi(s); if (v > 0 && v <= 32) c->mc_ctas_per_sm = v; }
     c->light_hits_budget = kLightHitsBudgetBytes;
     if (const char* s = std::getenv("ORBIT_LIGHT_HITS_BUDGET_MB")) { const long v = std::atol(s); if (v >= 0) c->light_hits_budget = (uint64_t)v << 20; }
@@ -432,9 +430,6 @@ static int entity_stage(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitScen
     p.entity_visibility = scene->entity_visibility;
     p.dispatch_words = (uint32_t*)meshlet_dispatch_buffer;
     p.dispatch_mirror = (uint32_t*)mirror_dispatch_buffer;
-    // passes 0 / 2 test every meshlet of every record: prefetch them into L2 while this kernel drains (pass 1 loads only the
-    // meshlets whose visibility bit is set — a prefetch of whole records would read 15x what it uses on C2)
-    p.prefetch_meshlets = (c->prefetch_meshlets && cull->occlusion_pass != 1u) ? (const uint8_t*)scene->meshlets : nullptr;
     p.overflow_flag = &c->status_dev->dispatch_overflow;
     p.capacity_records = capacity_records;
     p.draw_begin = begin; p.draw_end = end;

@@ -22,7 +22,6 @@ namespace orbit {
 #endif
 constexpr int kEcThreads = ORBIT_EC_THREADS;   // entity draws per CTA (tuning experiments: -DORBIT_EC_THREADS=128)
 constexpr uint32_t kEcBatch = 2048u;           // records staged in shared memory per round of the emission (32 KB)
-constexpr uint64_t kPrefetchRecords = 65536u;  // records whose meshlets are prefetched into L2 for the test kernel (64 MB of the 126 MB L2)
 
 
 template <bool kFlat>
@@ -189,12 +188,9 @@ __global__ void __launch_bounds__(kEcThreads) entity_cull_kernel(const __grid_co
         for (uint32_t k = my_excl < batch0 ? batch0 - my_excl : 0u; k < chunks && my_excl + k < batch0 + kEcBatch; ++k) {
             const uint32_t n = min(lod_cnt - 32u * k, 32u);
             s_recs[my_excl + k - batch0] = make_uint4(entity_index, lod_off + 32u * k, n, vis_offset + k);
-            // The meshlet test kernel that follows reads every meshlet of every record (passes 0 and 2): ask for them now,
-            // one bulk L2 prefetch per record (<= 1 KB), while HBM is idle (this kernel's tail, the next kernel's ramp and
-            // its three dependent round trips before the first test). Only the first kPrefetchRecords records of the list:
-            // a list that does not fit L2 gains nothing. C2 late pass: 27.8 -> 26.3 us with its 33 MB L2-resident.
-            if (p.prefetch_meshlets != nullptr && base + my_excl + k < kPrefetchRecords)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.prefetch_meshlets + (size_t)(lod_off + 32u * k) * 32u), "r"(n * 32u) : "memory");
+            // (An L2 prefetch of the records' meshlets from here — one cp.async.bulk.prefetch per record, for the test kernel
+            // that follows — was measured: 880 bulk prefetches per CTA queue up in the SM's copy unit and the C2 frame got
+            // 11 us SLOWER.)
         }
         __syncthreads();
         const uint64_t first = base + batch0;                                     // record index of the image's first record

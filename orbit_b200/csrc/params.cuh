@@ -65,7 +65,6 @@ struct EntityCullParams {
     uint32_t* entity_visibility;
     uint32_t* dispatch_words;            // MeshletDispatchBuffer as u32[]: x,y,z then 4 words per record
     uint32_t* dispatch_mirror;           // nullable: a second buffer that receives the same header and records (fused LATE + MAIN)
-    const uint8_t* prefetch_meshlets;    // nullable: meshlet array (32 B each) whose records' meshlets are prefetched into L2 (passes 0 / 2)
     uint32_t* overflow_flag;
     uint64_t capacity_records;
     uint32_t draw_begin, draw_end;       // sub-range of draws covered by this launch (begin % 32 == 0)
