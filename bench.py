@@ -466,6 +466,8 @@ def run_ours(args, rank, world, local_rank):
         pf.meshlet_late_main(context=ctx_test_only)     # grow that context's scratch outside the capture
     torch.cuda.synchronize()
     k_times["meshlet_late_test_kernel"] = time_stage(lambda pf, s: pf.meshlet_late_main(s, context=ctx_test_only))
+    # the same kernel without the MAIN pass's bookkeeping (the LATE pass alone: what round 1's roofline was quoted on)
+    k_times["meshlet_late_only_test_kernel"] = time_stage(lambda pf, s: pf.meshlet(True, s, context=ctx_test_only))
     for pf in copies:
         pf.launch()                                     # leave every copy in its steady state again
     torch.cuda.synchronize()
@@ -627,6 +629,9 @@ def run_ours(args, rank, world, local_rank):
                          "traffic_source": "profiles/r2_meshlet_test_ncu.json (ncu --set full, per launch, bytes)",
                          "algorithmic_bytes_per_launch": late_bytes, "launch_us_median": late_us, "launch_us_min": k_times["meshlet_late_test_kernel"][1],
                          "stage_us_median": stage_us, "frac_stage": late_bytes / (stage_us * 1e-6) / 1e9 / peak,
+                         "late_pass_alone": {"what": "the same test kernel launched for the LATE pass only (no MAIN entries / counters): the form round 1 quoted",
+                                             "launch_us_median": k_times["meshlet_late_only_test_kernel"][0],
+                                             "frac": late_bytes / (k_times["meshlet_late_only_test_kernel"][0] * 1e-6) / 1e9 / peak},
                          "stage": "test kernel + meshlet_emit_kernel (LATE list: nothing to emit in the steady state) + meshlet_emit_kernel (MAIN list)",
                          "lanes": late_lanes, "records": late_R, "entities": late_E, "survivors": n_late_draws,
                          "stage_gmeshlets_per_s": late_lanes / (stage_us * 1e-6) / 1e9,

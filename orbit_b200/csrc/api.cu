@@ -163,7 +163,7 @@ static int ensure_record_scratch(orbit_ctx* c, uint64_t max_records) {
 // reference's default 8-pixel tiles: ~10^6 clusters) take the CTA-per-cluster kernel instead.
 static constexpr uint64_t kLightHitsBudgetBytes = 256ull << 20;
 static uint64_t light_hits_words_needed(uint64_t clusters, uint64_t n_lights) {   // bit matrix + per-(cluster, light block) counts
-    return clusters * ((uint64_t)light_hits_blocks((uint32_t)n_lights) * 17u + 8u);   // 16 words of bits + 1 count per (cluster, light block), 8 words of box per cluster
+    return clusters * ((uint64_t)light_hits_blocks((uint32_t)n_lights) * 17u + 9u);   // 16 words of bits + 1 count per (cluster, light block), 8 words of box + 1 hit total per cluster
 }
 
 static int ensure_light_hits(orbit_ctx* c, uint64_t words) {
@@ -672,8 +672,9 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
     p.unique_clusters = (uint32_t*)unique_clusters; p.offset_count_image = (uint32_t*)offset_count_image;
     p.light_index_words = (uint32_t*)light_index_list; p.overflow_flag = &c->status_dev->light_index_overflow;
     p.capacity_indices = capacity_indices;
-    // scratch of the light-parallel path: [boxes: 8 words per cluster][bit matrix][block counts]
+    // scratch of the light-parallel path: [boxes: 8 words per cluster][bit matrix][block counts][hit totals: 1 word per cluster]
     p.cluster_boxes = light_parallel ? reinterpret_cast<float4*>(c->light_hits) : nullptr;
+    p.cluster_totals = light_parallel ? c->light_hits + clusters * (8u + (uint64_t)light_hits_blocks(L) * 17u) : nullptr;
     // fill_buffer(.., 0) of masks and bounds: cluster.rs:447-450; inactive image texels are zeroed (unspecified in the reference)
     CK(cudaMemsetAsync(tile_masks, 0, cx * cy * 4u, s));
     CK(cudaMemsetAsync(depth_bounds, 0, clusters * 8u, s));
@@ -690,7 +691,6 @@ int orbit_light_cluster(orbit_ctx* c, const OrbitClusterParams* params, const fl
         uint32_t* const hit_rows = c->light_hits + clusters * 8u;
         uint32_t* const block_counts = hit_rows + clusters * wpc;
         CK(launch_light_hits(p, hit_rows, block_counts, wpc, (uint32_t)clusters, s));
-        p.scan = next_scan(c);
         uint64_t lgrid = (clusters + 31u) / 32u;     // a warp per active cluster, 32 per CTA, persistent over tiles
         const uint64_t lcap = (uint64_t)c->sm_count * 2u;
         if (lgrid > lcap) lgrid = lcap;

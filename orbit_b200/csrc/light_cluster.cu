@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256) compact_clusters_kernel(const __grid_cons
     const uint32_t tile = s_tile;
     const uint32_t idx = tile * 256u + tid;
     bool active = false;
+    if (idx < total && p.cluster_totals != nullptr) p.cluster_totals[idx] = 0u;   // hit totals of the light-parallel path (one per possible slot)
     if (idx < total) {
         const uint32_t z = idx / (cx * cy);
         const uint32_t t = idx - z * cx * cy;   // tile index = x + y*cx
@@ -350,55 +351,110 @@ constexpr uint32_t kLhLightsPerCta = 512u, kLhClusterChunk = 32u, kLhWordsPerCta
 
 // hits:   [active cluster][words_per_cluster]   one bit per light; words_per_cluster = 16 x light blocks (rows are 64-byte aligned)
 // counts: [active cluster][light_blocks]        hits of the cluster among the 512 lights of one light block
+// totals: [active cluster]                      hits of the cluster among all lights (atomic sums; zeroed by the compaction kernel)
+//
+// Most lights touch no active cluster at all (C4: 743 hits in 6.5 M tests), so the CTA first tests its 512 lights against the
+// UNION of the chunk's 32 boxes — exact as a filter: per axis the distance to the union is <= the distance to a member, and
+// rounding (subtract, max, fma accumulate in the same order) is monotonic, so acc(union) > r^2 implies acc(member) > r^2 —
+// and only the lights that pass (compacted in ascending order) meet the 32 boxes: a warp takes one light, lane = cluster, the
+// ballot is the light's hit mask over the chunk. Same arithmetic per test as the CTA-per-cluster kernel: identical lists.
 __global__ void __launch_bounds__(256) light_hits_kernel(const __grid_constant__ ClusterParams p, uint32_t* __restrict__ hits,
                                                          uint32_t* __restrict__ counts, uint32_t words_per_cluster) {
-    __shared__ float s_box[kLhClusterChunk][8];                  // lo xyz, hi xyz (padded to 32 bytes: two 16-byte broadcast reads)
+    __shared__ float s_box[kLhClusterChunk][8];                  // lo xyz, hi xyz (padded to 32 bytes)
+    __shared__ float s_union[8];
     __shared__ uint32_t s_out[kLhClusterChunk][kLhWordsPerCta];
+    __shared__ float4 s_sphere[kLhLightsPerCta];                 // view-space centre, squared radius (-1: no such light)
+    __shared__ uint32_t s_list[kLhLightsPerCta];                 // lights that pass the union test, ascending
+    __shared__ uint32_t s_wcount[16], s_nlist;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t nactive = __ldcg(p.unique_clusters + 3);
     if (blockIdx.y * kLhClusterChunk >= nactive) return;        // chunk rows beyond the active clusters: nothing to do, before any load
     const uint32_t L = p.info.global_light_count;
     const uint32_t light0 = blockIdx.x * kLhLightsPerCta;
-    // this thread's two lights: light0 + tid and light0 + 256 + tid (word = block * 16 + k * 8 + warp, bit = lane)
-    float lx[2], ly[2], lz[2], lr2[2];
-    bool live[2];
+    // this thread's two lights: light0 + tid and light0 + 256 + tid (bit matrix word = block * 16 + k * 8 + warp, bit = lane)
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const uint32_t j = light0 + (uint32_t)k * 256u + tid;
-        live[k] = j < L;
-        lx[k] = ly[k] = lz[k] = 0.0f; lr2[k] = -1.0f;
-        if (live[k]) {
+        float4 sp = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+        if (j < L) {
             const uint8_t* l = p.lights + (size_t)j * 64u;
             const uint32_t type = __ldg(reinterpret_cast<const uint32_t*>(l));
             const float4 pos = __ldg(reinterpret_cast<const float4*>(l + 32));      // position xyz, inner_radius
             const float radius = __ldg(reinterpret_cast<const float*>(l + 60));
             const float* m = &p.info.world_to_view_matrix.m[0][0];
-            lx[k] = add(add(add(mul(m[0], pos.x), mul(m[4], pos.y)), mul(m[8], pos.z)), mul(m[12], 1.0f));
-            ly[k] = add(add(add(mul(m[1], pos.x), mul(m[5], pos.y)), mul(m[9], pos.z)), mul(m[13], 1.0f));
-            lz[k] = add(add(add(mul(m[2], pos.x), mul(m[6], pos.y)), mul(m[10], pos.z)), mul(m[14], 1.0f));
+            sp.x = add(add(add(mul(m[0], pos.x), mul(m[4], pos.y)), mul(m[8], pos.z)), mul(m[12], 1.0f));
+            sp.y = add(add(add(mul(m[1], pos.x), mul(m[5], pos.y)), mul(m[9], pos.z)), mul(m[13], 1.0f));
+            sp.z = add(add(add(mul(m[2], pos.x), mul(m[6], pos.y)), mul(m[10], pos.z)), mul(m[14], 1.0f));
             const float w = (type == ORBIT_LIGHT_POINT) ? radius : __uint_as_float(0x7F800000u);   // non-point lights always hit
-            lr2[k] = mul(w, w);
+            sp.w = mul(w, w);
         }
+        s_sphere[(uint32_t)k * 256u + tid] = sp;
     }
+    // squared distance from a sphere centre to a box, per axis: v < lo adds (lo-v)^2, v > hi adds (v-hi)^2
+    // (light_culling.comp:52-66); lo <= hi, so at most one applies and d is that term's base (or 0, and fma(0,0,acc) == acc)
+    auto dist2 = [](const float4 sp, const float4 lo, const float4 hi) -> float {
+        float acc = 0.0f;
+        float d = fmaxf(fmaxf(sub(lo.x, sp.x), sub(sp.x, hi.x)), 0.0f); acc = fma_(d, d, acc);
+        d = fmaxf(fmaxf(sub(lo.y, sp.y), sub(sp.y, hi.y)), 0.0f); acc = fma_(d, d, acc);
+        d = fmaxf(fmaxf(sub(lo.z, sp.z), sub(sp.z, hi.z)), 0.0f); acc = fma_(d, d, acc);
+        return acc;
+    };
     for (uint32_t chunk0 = blockIdx.y * kLhClusterChunk; chunk0 < nactive; chunk0 += gridDim.y * kLhClusterChunk) {
         const uint32_t nc = min(kLhClusterChunk, nactive - chunk0);
-        __syncthreads();                                         // previous chunk's boxes and rows are no longer read
+        __syncthreads();                                         // previous chunk's boxes, rows and list are no longer read
         if (tid < 2u * nc) *reinterpret_cast<float4*>(&s_box[tid >> 1][(tid & 1u) * 4u]) = __ldcg(p.cluster_boxes + 2u * (size_t)chunk0 + tid);
+        s_out[tid >> 4][tid & 15u] = 0u; s_out[16u + (tid >> 4)][tid & 15u] = 0u;
         __syncthreads();
-        for (uint32_t c = 0; c < nc; ++c) {
-            const float4 lo = *reinterpret_cast<const float4*>(&s_box[c][0]);
-            const float4 hi = *reinterpret_cast<const float4*>(&s_box[c][4]);
+        if (warp == 0u) {                                        // union of the chunk's boxes (lanes beyond nc: neutral)
+            float lo[3], hi[3];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                // per axis: v < lo adds (lo-v)^2, v > hi adds (v-hi)^2 (light_culling.comp:52-66); lo <= hi, so at most one
-                // applies and d is that term's base (or 0, and fma(0,0,acc) == acc): same value, no divergence
-                float acc = 0.0f;
-                float d = fmaxf(fmaxf(sub(lo.x, lx[k]), sub(lx[k], hi.x)), 0.0f); acc = fma_(d, d, acc);
-                d = fmaxf(fmaxf(sub(lo.y, ly[k]), sub(ly[k], hi.y)), 0.0f); acc = fma_(d, d, acc);
-                d = fmaxf(fmaxf(sub(lo.z, lz[k]), sub(lz[k], hi.z)), 0.0f); acc = fma_(d, d, acc);
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, live[k] && acc <= lr2[k]);
-                if (lane == 0u) s_out[c][(uint32_t)k * 8u + warp] = bal;
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = lane < nc ? s_box[lane][a] : __uint_as_float(0x7F800000u);
+                hi[a] = lane < nc ? s_box[lane][4 + a] : __uint_as_float(0xFF800000u);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
+                    hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
+                }
             }
+            if (lane == 0u) { s_union[0] = lo[0]; s_union[1] = lo[1]; s_union[2] = lo[2]; s_union[3] = 0.0f;
+                              s_union[4] = hi[0]; s_union[5] = hi[1]; s_union[6] = hi[2]; s_union[7] = 0.0f; }
+        }
+        __syncthreads();
+        // ---- lights that reach the union, in ascending order (thread's light k has local index k * 256 + tid)
+        const float4 ulo = *reinterpret_cast<const float4*>(&s_union[0]), uhi = *reinterpret_cast<const float4*>(&s_union[4]);
+        uint32_t bal[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float4 sp = s_sphere[(uint32_t)k * 256u + tid];
+            bal[k] = __ballot_sync(0xFFFFFFFFu, sp.w >= 0.0f && dist2(sp, ulo, uhi) <= sp.w);
+            if (lane == 0u) s_wcount[(uint32_t)k * 8u + warp] = (uint32_t)__popc(bal[k]);
+        }
+        __syncthreads();
+        {
+            uint32_t before[2] = {0u, 0u}, total = 0u;
+#pragma unroll
+            for (uint32_t w = 0; w < 16u; ++w) {
+                const uint32_t v = s_wcount[w];
+                if (w < warp) before[0] += v;
+                if (w < 8u + warp) before[1] += v;
+                total += v;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if ((bal[k] >> lane) & 1u) s_list[before[k] + (uint32_t)__popc(bal[k] & ((1u << lane) - 1u))] = (uint32_t)k * 256u + tid;
+            if (tid == 0) s_nlist = total;
+        }
+        __syncthreads();
+        // ---- a warp per listed light, lane = cluster of the chunk: the ballot is the light's hit mask over the chunk
+        const uint32_t nlist = s_nlist;
+        const float4 lo = lane < nc ? *reinterpret_cast<const float4*>(&s_box[lane][0]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 hi = lane < nc ? *reinterpret_cast<const float4*>(&s_box[lane][4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t i = warp; i < nlist; i += 8u) {
+            const uint32_t li = s_list[i];
+            const float4 sp = s_sphere[li];
+            const bool hit = lane < nc && dist2(sp, lo, hi) <= sp.w;
+            if (hit) atomicOr(&s_out[lane][li >> 5], 1u << (li & 31u));
         }
         __syncthreads();
         // rows out: 16 consecutive words per cluster + their popcount (16 lanes per cluster: half-warp reduction)
@@ -410,113 +466,107 @@ __global__ void __launch_bounds__(256) light_hits_kernel(const __grid_constant__
             uint32_t n = (uint32_t)__popc(v);
             n += __shfl_xor_sync(0xFFFFFFFFu, n, 1); n += __shfl_xor_sync(0xFFFFFFFFu, n, 2);
             n += __shfl_xor_sync(0xFFFFFFFFu, n, 4); n += __shfl_xor_sync(0xFFFFFFFFu, n, 8);
-            if (c < nc && w == 0u) counts[(size_t)(chunk0 + c) * gridDim.x + blockIdx.x] = n;
+            if (c < nc && w == 0u) {
+                counts[(size_t)(chunk0 + c) * gridDim.x + blockIdx.x] = n;
+                if (n != 0u) atomicAdd(p.cluster_totals + chunk0 + c, n);
+            }
         }
     }
 }
 
-// One warp per active cluster, 32 clusters per CTA (a tile of the look-back scan: with ~100 active clusters the chain is four
-// tiles long). The cluster's hits per light block are scanned (ascending light order = ascending block order), the total is
-// capped at the reference's 256, the tile's range comes from the look-back over tiles in compacted-list order, and every lane
-// expands the blocks it owns at their ranks — only blocks that hold a hit are ever read from the bit matrix.
+// One warp per active cluster, 32 clusters per CTA, no dependency between CTAs: a tile's first index in the global list is
+// the sum of the capped totals of all clusters before it (the totals are a few hundred words: every CTA adds them up itself,
+// one round of loads, instead of a look-back chain over tiles). The cluster's hit BLOCKS (light blocks with a hit: at most
+// 256) are compacted into shared memory in ascending order with their ranks, and lanes expand them in parallel — one
+// round of 64-byte row reads for up to 32 hit blocks, wherever in the light range they lie (block by block in 32-block steps
+// took one dependent round trip per step).
 constexpr int kLlWarps = 32;
 __global__ void __launch_bounds__(kLlWarps * 32) light_lists_kernel(const __grid_constant__ ClusterParams p, const uint32_t* __restrict__ hits,
                                                                     const uint32_t* __restrict__ counts, uint32_t words_per_cluster, uint32_t light_blocks) {
-    __shared__ uint32_t s_cnt[kLlWarps];
-    __shared__ uint32_t s_tile, s_base;
+    __shared__ uint32_t s_cnt[kLlWarps], s_part[kLlWarps];
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_blocks[kLlWarps][ORBIT_MAX_LIGHTS_PER_CLUSTER];   // block << 9 | rank of its first hit (< 256), per hit block of the warp's cluster
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const unsigned int epoch = scan_epoch(p.scan);
     const uint32_t nactive = __ldcg(p.unique_clusters + 3);
+    if (nactive == 0u) {
+        if (blockIdx.x == 0 && tid == 0) p.light_index_words[0] = 0u;
+        return;
+    }
     const uint32_t ntiles = (nactive + kLlWarps - 1u) / kLlWarps;
-    while (true) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(p.scan.ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= ntiles) {
-            if (tile == 0u && tid == 0) p.light_index_words[0] = 0u;      // no active cluster at all
-            break;
-        }
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t t = tile * kLlWarps + warp;                         // this warp's active cluster (compacted-list position)
         const bool have = t < nactive;
         const uint32_t* crow = counts + (size_t)t * light_blocks;
-        // ---- 1. hits of the cluster, capped at the reference's 256
-        uint32_t count = 0u;
-        constexpr int kKeep = 8;                                          // block counts kept in registers: 8 x 32 blocks = 131 072 lights
+        // ---- loads of this round, all independent: the totals below the tile, the cluster's total, index and block counts
+        uint32_t below = 0u;
+        for (uint32_t c = tid; c < tile * kLlWarps; c += kLlWarps * 32u) below += min(__ldcg(p.cluster_totals + c), (uint32_t)ORBIT_MAX_LIGHTS_PER_CLUSTER);
+        const uint32_t count = have ? min(__ldcg(p.cluster_totals + t), (uint32_t)ORBIT_MAX_LIGHTS_PER_CLUSTER) : 0u;
+        const uint32_t idx = have ? __ldcg(p.unique_clusters + 4u + t) : 0u;
+        constexpr int kKeep = 8;
         uint32_t kept[kKeep];
 #pragma unroll
-        for (int k = 0; k < kKeep; ++k) {
-            const uint32_t b = (uint32_t)k * 32u + lane;
-            kept[k] = (have && b < light_blocks) ? __ldcg(crow + b) : 0u;
-            count += kept[k];
-        }
-        if (have) for (uint32_t b = (uint32_t)kKeep * 32u + lane; b < light_blocks; b += 32u) count += __ldcg(crow + b);
-        count = min(__reduce_add_sync(0xFFFFFFFFu, count), (uint32_t)ORBIT_MAX_LIGHTS_PER_CLUSTER);
-        if (lane == 0u) s_cnt[warp] = count;
+        for (int k = 0; k < kKeep; ++k) kept[k] = (have && (uint32_t)k * 32u + lane < light_blocks) ? __ldcg(crow + (uint32_t)k * 32u + lane) : 0u;
+        below = __reduce_add_sync(0xFFFFFFFFu, below);
+        __syncthreads();                                                   // previous round's s_cnt / s_part / s_base are no longer read
+        if (lane == 0u) { s_cnt[warp] = count; s_part[warp] = below; }
         __syncthreads();
-        uint32_t before = 0u, total = 0u;
+        uint32_t before = 0u, total = 0u, base = 0u;
 #pragma unroll
-        for (int w = 0; w < kLlWarps; ++w) { const uint32_t v = s_cnt[w]; if ((uint32_t)w < warp) before += v; total += v; }
-        // ---- 2. the tile's range in the global list: look-back over tiles in compacted-list order
-        if (warp == 0u) {
-            const uint32_t off = lookback_exclusive(p.scan, epoch, tile, total);
-            if (lane == 0u) {
-                s_base = off;
-                if (tile == ntiles - 1u) {
-                    p.light_index_words[0] = off + total;
-                    if ((uint64_t)off + total > p.capacity_indices) *p.overflow_flag = 1u;
+        for (int w = 0; w < kLlWarps; ++w) { const uint32_t v = s_cnt[w]; if ((uint32_t)w < warp) before += v; total += v; base += s_part[w]; }
+        if (tile == ntiles - 1u && tid == 0) {
+            p.light_index_words[0] = base + total;
+            if ((uint64_t)base + total > p.capacity_indices) *p.overflow_flag = 1u;
+        }
+        if (!have) continue;
+        const uint32_t off = base + before;
+        if (lane == 0u) { p.offset_count_image[2u * (size_t)idx] = off; p.offset_count_image[2u * (size_t)idx + 1u] = count; }
+        if (count == 0u) continue;
+        // ---- hit blocks of the cluster in ascending order, with the rank of their first hit. The block counts were requested
+        // with the round's other loads (kept[]: 8 x 32 blocks = 131 072 lights in registers, indexed by compile-time constants
+        // only); lights beyond that are walked 32 blocks per dependent load.
+        uint32_t* const blk = &s_blocks[warp][0];
+        uint32_t nblk = 0u, running = 0u;
+        auto step = [&](const uint32_t b0, const uint32_t n) {
+            uint32_t inc = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= (uint32_t)d) inc += v;
+            }
+            const uint32_t pos = running + inc - n;
+            const bool keep = n != 0u && pos < count;
+            const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+            if (keep) blk[nblk + (uint32_t)__popc(km & ((1u << lane) - 1u))] = ((b0 + lane) << 9) | pos;
+            nblk += (uint32_t)__popc(km);
+            running += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        };
+#pragma unroll
+        for (int k = 0; k < kKeep; ++k)
+            if ((uint32_t)k * 32u < light_blocks && running < count) step((uint32_t)k * 32u, kept[k]);
+#pragma unroll 1
+        for (uint32_t b0 = (uint32_t)kKeep * 32u; b0 < light_blocks && running < count; b0 += 32u)
+            step(b0, b0 + lane < light_blocks ? __ldcg(crow + b0 + lane) : 0u);
+        __syncwarp();
+        // ---- expansion: a lane per hit block, the block's 16 words in four 16-byte loads
+        const uint32_t* row = hits + (size_t)t * words_per_cluster;
+        for (uint32_t i = lane; i < nblk; i += 32u) {
+            const uint32_t e = blk[i], eb = e >> 9;
+            uint32_t pos = e & 511u;
+            const uint4* r4 = reinterpret_cast<const uint4*>(row + (size_t)eb * kLhWordsPerCta);
+            const uint4 v0 = __ldcg(r4), v1 = __ldcg(r4 + 1), v2 = __ldcg(r4 + 2), v3 = __ldcg(r4 + 3);
+            const uint32_t words[kLhWordsPerCta] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+            for (uint32_t w = 0; w < kLhWordsPerCta; ++w) {
+                uint32_t word = words[w];
+                while (word != 0u && pos < count) {
+                    const uint32_t bit = (uint32_t)__ffs((int)word) - 1u;
+                    if ((uint64_t)off + pos < p.capacity_indices) p.light_index_words[1u + off + pos] = (eb * kLhWordsPerCta + w) * 32u + bit;
+                    word &= word - 1u;
+                    ++pos;
                 }
             }
         }
-        __syncthreads();
-        if (have) {
-            const uint32_t off = s_base + before;
-            const uint32_t idx = __ldcg(p.unique_clusters + 4u + t);
-            if (lane == 0u) { p.offset_count_image[2u * (size_t)idx] = off; p.offset_count_image[2u * (size_t)idx + 1u] = count; }
-            // ---- 3. blocks in ascending order, 32 per step: rank of a block's first hit = hits of all earlier blocks
-            const uint32_t* row = hits + (size_t)t * words_per_cluster;
-            uint32_t running = 0u;
-            // one step = 32 blocks: n = this lane's block count; warp-uniform control flow (b0, running, count are uniform)
-            auto expand = [&](uint32_t b0, uint32_t n) {
-                const uint32_t b = b0 + lane;
-                uint32_t inc = n;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                    if (lane >= (uint32_t)d) inc += v;
-                }
-                uint32_t pos = running + inc - n;
-                if (n != 0u && pos < count) {
-                    // the block's 16 words in four 16-byte loads, all in flight at once (one word at a time made every hit block
-                    // a chain of 16 dependent L2 round trips: 32 us for the 99 clusters of C4)
-                    const uint4* r4 = reinterpret_cast<const uint4*>(row + (size_t)b * kLhWordsPerCta);
-                    const uint4 v0 = __ldcg(r4), v1 = __ldcg(r4 + 1), v2 = __ldcg(r4 + 2), v3 = __ldcg(r4 + 3);
-                    const uint32_t words[kLhWordsPerCta] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-#pragma unroll
-                    for (uint32_t w = 0; w < kLhWordsPerCta; ++w) {
-                        uint32_t word = words[w];
-                        while (word != 0u && pos < count) {
-                            const uint32_t bit = (uint32_t)__ffs((int)word) - 1u;
-                            if ((uint64_t)off + pos < p.capacity_indices) p.light_index_words[1u + off + pos] = (b * kLhWordsPerCta + w) * 32u + bit;
-                            word &= word - 1u;
-                            ++pos;
-                        }
-                    }
-                }
-                running += __shfl_sync(0xFFFFFFFFu, inc, 31);
-            };
-            // the kept counts are indexed by compile-time constants only: with a run-time select over kept[] inside a rolled
-            // loop the step at b0 = 32 received kept[0] on the device (C4: every hit in light blocks 32.. of some clusters was
-            // dropped; caught by the full-size C4 test, tools/debug/c4_lights.py shows the case)
-#pragma unroll
-            for (int k = 0; k < kKeep; ++k)
-                if ((uint32_t)k * 32u < light_blocks && running < count) expand((uint32_t)k * 32u, kept[k]);
-#pragma unroll 1
-            for (uint32_t b0 = (uint32_t)kKeep * 32u; b0 < light_blocks && running < count; b0 += 32u)
-                expand(b0, b0 + lane < light_blocks ? __ldcg(crow + b0 + lane) : 0u);
-        }
     }
-    if (tid == 0) scan_cta_exit(p.scan, epoch);
 }
 
 uint32_t light_hits_blocks(uint32_t n_lights) { return (n_lights + kLhLightsPerCta - 1u) / kLhLightsPerCta; }

@@ -374,23 +374,30 @@ __device__ __forceinline__ uint32_t drain_candidates(const MeshletCullParams& p,
     }
     __syncwarp();
     // Publication, once per RECORD instead of once per candidate: the candidates of a drain are in record order, so the lanes
-    // that found something mostly share two or three records. The lanes of a record (match.any) OR their bits together and
+    // that found something mostly share two or three records. The lanes of a record OR their bits together (redux.or) and
     // the lowest of them issues one RED.OR per word — visibility word, LATE entry, MAIN entry — and one RED.ADD of the
     // popcount per list to the record's chunk counter (the bits of a record are distinct, so the popcount of the OR is the
     // number of survivors). Per-candidate atomics on the few dozen chunk counters of the visible part of the scene cost the
     // fused late pass of C2 10 us. A lane whose two candidates straddle a record boundary publishes the second one itself.
     uint32_t drawn = 0u;
-    if (__any_sync(0xFFFFFFFFu, vbits != 0u)) {
-        const uint32_t lt = (1u << lane) - 1u;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, rec0);
-        const uint32_t v = __reduce_or_sync(peers, vbits);
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, vbits != 0u);
+    if (todo != 0u) {
         const bool any_late = __any_sync(0xFFFFFFFFu, (lbits | lbit1) != 0u);
-        const uint32_t l = any_late ? __reduce_or_sync(peers, lbits) : 0u;
-        const uint32_t m = main_chunk_counts != nullptr ? __reduce_or_sync(peers, mbits) : 0u;
-        if (vbits != 0u && (peers & lt) == 0u) {
-            atomicOr(p.meshlet_visibility + vo0, v);
-            if (l != 0u) { atomicOr(reinterpret_cast<uint32_t*>(p.draw_masks + rec0), l); atomicAdd(chunk_counts + (rec0 >> chunk_shift), (uint32_t)__popc(l)); }
-            if (m != 0u) { atomicOr(reinterpret_cast<uint32_t*>(p.main_masks + rec0), m); atomicAdd(main_chunk_counts + (rec0 >> chunk_shift), (uint32_t)__popc(m)); }
+        // one record at a time with FULL-mask reductions (a partial-mask redux is a ~32-instruction software loop, and so is
+        // match.any; a drain's visible candidates belong to two or three records)
+        while (todo != 0u) {
+            const uint32_t key = __shfl_sync(0xFFFFFFFFu, rec0, __ffs((int)todo) - 1);
+            const bool mine = vbits != 0u && rec0 == key;
+            const uint32_t same = __ballot_sync(0xFFFFFFFFu, mine);
+            const uint32_t v = __reduce_or_sync(0xFFFFFFFFu, mine ? vbits : 0u);
+            const uint32_t l = any_late ? __reduce_or_sync(0xFFFFFFFFu, mine ? lbits : 0u) : 0u;
+            const uint32_t m = main_chunk_counts != nullptr ? __reduce_or_sync(0xFFFFFFFFu, mine ? mbits : 0u) : 0u;
+            if (lane == (uint32_t)(__ffs((int)same) - 1)) {
+                atomicOr(p.meshlet_visibility + vo0, v);
+                if (l != 0u) { atomicOr(reinterpret_cast<uint32_t*>(p.draw_masks + rec0), l); atomicAdd(chunk_counts + (rec0 >> chunk_shift), (uint32_t)__popc(l)); }
+                if (m != 0u) { atomicOr(reinterpret_cast<uint32_t*>(p.main_masks + rec0), m); atomicAdd(main_chunk_counts + (rec0 >> chunk_shift), (uint32_t)__popc(m)); }
+            }
+            todo &= ~same;
         }
         if (vbit1 != 0u) {
             atomicOr(p.meshlet_visibility + vo1, vbit1);

@@ -119,6 +119,7 @@ struct ClusterParams {
     const uint8_t* lights;            // OrbitLightData[]
     float4* light_view;               // scratch: (view xyz, outer_radius or +inf for non-point lights)
     float4* cluster_boxes;            // scratch (light-parallel path, else nullptr): view-space box lo / hi per compacted-list slot
+    uint32_t* cluster_totals;         // scratch (light-parallel path): hits per compacted-list slot, zeroed by the compaction kernel
     uint32_t* tile_masks;
     uint32_t* depth_bounds;           // 2 words per cluster
     uint32_t* unique_clusters;        // 4-word header + indices
