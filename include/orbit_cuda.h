@@ -72,7 +72,9 @@ typedef struct OrbitStatus {
                                      panics here: scene.rs:427 `.unwrap()`)                                   */
     uint32_t asset_error;         /* orbit_meshlet_bounds met a meshlet with more than 128 triangles (left untouched);
                                      orbit_ctx_poll_status then returns ORBIT_ERR_INVALID_ARGUMENT              */
-    uint32_t reserved[3];
+    uint32_t peer_timeout;        /* orbit_peer_wait gave up (~2 s) waiting for a flag: a peer never delivered;
+                                     orbit_ctx_poll_status then returns ORBIT_ERR_CUDA                           */
+    uint32_t reserved[2];
 } OrbitStatus;
 
 /* Device pointers to the long-lived scene / asset arrays the culling path reads.
@@ -274,6 +276,20 @@ int  orbit_peer_open(orbit_ctx* ctx, const void* handle /* 64 bytes */, void** o
 int  orbit_peer_close(orbit_ctx* ctx, void* mapped_ptr);
 void orbit_peer_free(orbit_ctx* ctx, void* ptr);
 int  orbit_device_copy(void* dst, const void* src, uint64_t bytes, void* stream);
+
+/* One-sided transfers with completion flags — what the sharded view uses instead of a collective to get the depth pyramid
+ * from the GPU that built it to the others (scatter its chunks, then every GPU forwards its chunk: orbit_b200/multi_gpu.py
+ * PyramidBroadcast). orbit_peer_put: up to 16 transfers in ONE launch; a transfer copies `bytes` (a multiple of 16; src and
+ * dst 16-byte aligned) from local memory to `dst` (usually peer-mapped: NVLink stores) and then — after all of its stores
+ * have been issued and fenced at system scope — writes `flag_value` to `dst_flag` (nullable; usually a word on the receiving
+ * GPU). orbit_peer_wait: the stream waits until `n_flags` (<= 32) LOCAL words, `stride_words` apart, all hold `flag_value`
+ * (device-side polling, bounded at ~2 s: a flag that never arrives sets OrbitStatus::peer_timeout instead of hanging the
+ * GPU). Use a value that increases with every use (a frame counter): no flag is ever reset. Put calls of one context
+ * must not overlap each other (they share 16 completion counters). */
+typedef struct OrbitPeerPut { const void* src; void* dst; uint64_t bytes; uint32_t* dst_flag; } OrbitPeerPut;
+int  orbit_peer_put(orbit_ctx* ctx, const OrbitPeerPut* puts, uint32_t n_puts /* <= 16 */, uint32_t flag_value, void* stream);
+int  orbit_peer_wait(orbit_ctx* ctx, const uint32_t* flags, uint32_t n_flags /* <= 32 */, uint32_t stride_words, uint32_t flag_value,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -128,6 +128,26 @@ inline void create_meshlet_draw_commands(orbit_ctx* ctx, const AssetGraphData& a
           "create_meshlet_draw_commands");
 }
 
+// The LATE cull of the depth prepass (forward.rs:266-403) and the MAIN pass's cull (forward.rs:518-548) in their fused form
+// (orbit_cuda.h): both passes' dispatch buffers and draw lists from one entity kernel and one test kernel, byte for byte what the
+// four separate create_* calls write. Returns false — nothing launched — when the two CullInfos are not a compatible pair
+// (another camera, planes or LOD parameters, or no meshlet visibility buffer): the caller then issues the separate calls.
+inline bool create_late_and_main_commands(orbit_ctx* ctx, const AssetGraphData& assets, const SceneGraphData& scene, const CullInfo& late,
+                                          const CullInfo& main_pass, void* late_dispatch_buffer, void* main_dispatch_buffer,
+                                          uint64_t capacity_records, void* late_draw_command_buffer, void* main_draw_command_buffer,
+                                          uint64_t capacity_draws, void* stream, void* late_task_payloads = nullptr,
+                                          void* main_task_payloads = nullptr) {
+    const OrbitCullInfo gl = late.to_gpu(), gm = main_pass.to_gpu();
+    if (!orbit_cull_pair_compatible(&gl, &gm)) return false;
+    const OrbitSceneBuffers sb = scene_buffers(assets, scene, late);
+    check(orbit_entity_cull_late_main(ctx, &gl, &gm, &sb, late.occlusion_culling.depth_pyramid, late_dispatch_buffer, main_dispatch_buffer,
+                                      capacity_records, stream), "create_late_and_main_commands (entity stage)");
+    check(orbit_meshlet_cull_late_main(ctx, &gl, &gm, &sb, late.occlusion_culling.depth_pyramid, late_dispatch_buffer, capacity_records,
+                                       late_draw_command_buffer, main_draw_command_buffer, capacity_draws, late_task_payloads,
+                                       main_task_payloads, stream), "create_late_and_main_commands (meshlet stage)");
+    return true;
+}
+
 // draw_gen.rs:451-567
 class DepthPyramid {
 public:

@@ -49,6 +49,8 @@ PROTOTYPES = {
     "orbit_record_masks_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "orbit_draws_from_masks": (C.c_int, [C.c_void_p, C.POINTER(L.SceneBuffers), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
                                          C.c_void_p, C.c_uint64, C.c_void_p]),
+    "orbit_peer_put": (C.c_int, [C.c_void_p, C.POINTER(L.PeerPut), C.c_uint32, C.c_uint32, C.c_void_p]),
+    "orbit_peer_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "orbit_meshlet_bounds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "orbit_mesh_bounds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "orbit_peer_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]),

@@ -242,8 +242,8 @@ int orbit_ctx_create(int device, orbit_ctx** out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    CK(cudaMalloc(&c->counters, 32 * sizeof(unsigned int)));
-    CK(cudaMemset(c->counters, 0, 32 * sizeof(unsigned int)));
+    CK(cudaMalloc(&c->counters, 64 * sizeof(unsigned int)));
+    CK(cudaMemset(c->counters, 0, 64 * sizeof(unsigned int)));
     { const unsigned int one = 1u; CK(cudaMemcpy(c->counters + 3, &one, sizeof(one), cudaMemcpyHostToDevice)); }
     CK(cudaMalloc(&c->chunk_counts, 6 * 2048 * sizeof(uint32_t)));   // two parities for orbit_meshlet_cull + two (never read) for orbit_meshlet_test + two for the fused MAIN pass
     CK(cudaMemset(c->chunk_counts, 0, 6 * 2048 * sizeof(uint32_t)));
@@ -284,6 +284,7 @@ int orbit_ctx_poll_status(orbit_ctx* c, OrbitStatus* out) {
     *out = *c->status_host;
     std::memset(c->status_host, 0, sizeof(OrbitStatus));
     if (out->asset_error) return ORBIT_ERR_INVALID_ARGUMENT;
+    if (out->peer_timeout) return ORBIT_ERR_CUDA;
     return (out->dispatch_overflow || out->draw_overflow || out->light_index_overflow || out->visibility_overflow) ? ORBIT_ERR_CAPACITY : ORBIT_OK;
 }
 
@@ -892,3 +893,90 @@ cudaError_t launch_draws_scatter(const uint32_t* src, uint64_t src_capacity, uin
     return cudaGetLastError();
 }
 }  // namespace orbit
+
+// ---- peer put / wait: one-sided transfers with a completion flag (no collective) ---------------------------------------
+// orbit_peer_put: up to 16 transfers in one launch (blockIdx.y = transfer). A transfer copies `bytes` (multiple of 16, both
+// ends 16-byte aligned) from local memory to `dst` — usually another GPU's memory mapped with orbit_peer_open, so the stores
+// travel over NVLink — and, once every CTA of the transfer has issued and fenced its stores (the last one to count itself
+// out knows), writes `flag_value` to `dst_flag` on the receiving GPU. orbit_peer_wait makes the stream wait until n local
+// flag words all hold `flag_value` (a one-warp kernel polling with ld.acquire.sys). Flags only ever take the values the
+// callers pass, so a monotonically increasing value per use needs no reset. The wait is bounded (~2 s): a peer that never
+// arrives sets OrbitStatus::peer_timeout instead of hanging the GPU.
+namespace orbit {
+struct PeerPutParams { const uint4* src[16]; uint4* dst[16]; uint64_t n16[16]; uint32_t* flag[16]; uint32_t flag_value; uint32_t* done; };
+
+__global__ void __launch_bounds__(256) peer_put_kernel(const __grid_constant__ PeerPutParams p) {
+    const uint32_t t = blockIdx.y;
+    const uint4* __restrict__ src = p.src[t];
+    uint4* __restrict__ dst = p.dst[t];
+    const uint64_t n = p.n16[t], gsize = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3u * gsize < n; i += 4u * gsize) {                       // four independent 16-byte stores in flight
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldcg(src + i + (uint64_t)k * gsize);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) __stcg(dst + i + (uint64_t)k * gsize, v[k]);
+    }
+    for (; i < n; i += gsize) __stcg(dst + i, __ldcg(src + i));
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(p.done + t, 1u);
+        if (prev + 1u == gridDim.x) {
+            p.done[t] = 0u;
+            __threadfence_system();
+            if (p.flag[t] != nullptr) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag[t]), "r"(p.flag_value) : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) peer_wait_kernel(const uint32_t* flags, uint32_t n, uint32_t stride, uint32_t value, uint32_t* timeout_flag) {
+    const uint32_t lane = threadIdx.x;
+    bool ok = lane >= n;
+    for (uint32_t spin = 0; spin < (1u << 22) && !__all_sync(0xFFFFFFFFu, ok); ++spin) {
+        if (!ok) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + (size_t)lane * stride) : "memory");
+            ok = v == value;
+            if (!ok) __nanosleep(200);
+        }
+    }
+    if (!__all_sync(0xFFFFFFFFu, ok) && lane == 0) *timeout_flag = 1u;
+    __threadfence_system();
+}
+}  // namespace orbit
+
+extern "C" {
+int orbit_peer_put(orbit_ctx* c, const OrbitPeerPut* puts, uint32_t n_puts, uint32_t flag_value, void* stream) {
+    if (!c || !puts || n_puts == 0u || n_puts > 16u) return ORBIT_ERR_INVALID_ARGUMENT;
+    orbit::PeerPutParams p{};
+    uint64_t largest = 0u;
+    for (uint32_t i = 0; i < n_puts; ++i) {
+        if ((!puts[i].src || !puts[i].dst) && puts[i].bytes) return ORBIT_ERR_INVALID_ARGUMENT;
+        if ((((uintptr_t)puts[i].src | (uintptr_t)puts[i].dst | puts[i].bytes) & 15u) || ((uintptr_t)puts[i].dst_flag & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
+        p.src[i] = (const uint4*)puts[i].src; p.dst[i] = (uint4*)puts[i].dst; p.n16[i] = puts[i].bytes / 16u; p.flag[i] = puts[i].dst_flag;
+        if (p.n16[i] > largest) largest = p.n16[i];
+    }
+    p.flag_value = flag_value;
+    p.done = c->counters + 24;                 // [24..39]: CTAs that have finished, per transfer (self-resetting)
+    GUARD(c);
+    uint64_t gx = (largest + 1023u) / 1024u;   // four 16-byte stores per thread
+    const uint64_t cap = (uint64_t)c->sm_count * 8u / n_puts;
+    if (gx > cap) gx = cap;
+    if (gx == 0u) gx = 1u;
+    orbit::peer_put_kernel<<<dim3((unsigned)gx, n_puts), 256, 0, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    return ORBIT_OK;
+}
+
+int orbit_peer_wait(orbit_ctx* c, const uint32_t* flags, uint32_t n_flags, uint32_t stride_words, uint32_t flag_value, void* stream) {
+    if (!c || !flags || n_flags == 0u || n_flags > 32u || stride_words == 0u || ((uintptr_t)flags & 3u)) return ORBIT_ERR_INVALID_ARGUMENT;
+    GUARD(c);
+    orbit::peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n_flags, stride_words, flag_value, &c->status_dev->peer_timeout);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    return ORBIT_OK;
+}
+}  // extern "C"

@@ -122,7 +122,12 @@ class ClusterParams(C.Structure):
 
 class Status(C.Structure):
     _fields_ = [("dispatch_overflow", C.c_uint32), ("draw_overflow", C.c_uint32), ("light_index_overflow", C.c_uint32),
-                ("visibility_overflow", C.c_uint32), ("asset_error", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("visibility_overflow", C.c_uint32), ("asset_error", C.c_uint32), ("peer_timeout", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+
+
+class PeerPut(C.Structure):
+    """OrbitPeerPut (include/orbit_cuda.h): one transfer of orbit_peer_put."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes", C.c_uint64), ("dst_flag", C.c_void_p)]
 
 
 class SceneUpdate(C.Structure):

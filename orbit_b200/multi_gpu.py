@@ -24,16 +24,19 @@ def views_for_rank(n_views: int, rank: int, world: int) -> List[int]:
     return [v for v in range(n_views) if v % world == rank]
 
 
-def partition_draws(meshlet_counts: Sequence[int], world: int) -> List[Tuple[int, int]]:
-    """Cuts draws [0, N) into `world` contiguous ranges of (nearly) equal meshlet sums whose interior boundaries
-    are multiples of 32 draws (entity visibility words are indexed by draw/32). Ranges may be empty."""
+def partition_draws(meshlet_counts: Sequence[int], world: int, weights: Sequence[float] = None) -> List[Tuple[int, int]]:
+    """Cuts draws [0, N) into `world` contiguous ranges of (nearly) equal meshlet sums — or sums proportional to `weights` —
+    whose interior boundaries are multiples of 32 draws (entity visibility words are indexed by draw/32). Ranges may be empty."""
     c = np.asarray(meshlet_counts, dtype=np.int64)
     n = len(c)
     prefix = np.concatenate([[0], np.cumsum(c)])
     total = int(prefix[-1])
+    w = np.ones(world) if weights is None else np.asarray(weights, dtype=np.float64)
+    assert len(w) == world and (w >= 0).all() and w.sum() > 0
+    share = np.concatenate([[0.0], np.cumsum(w) / w.sum()])
     cuts = [0]
     for k in range(1, world):
-        target = total * k / world
+        target = total * share[k]
         i = int(np.searchsorted(prefix, target, side="left"))
         i = int(round(i / 32.0)) * 32
         i = min(max(i, cuts[-1]), n)
@@ -242,17 +245,115 @@ class MaskExchange:
         self.lib.orbit_peer_free(self.context._h, self.C.c_void_p(self.local_ptr))
 
 
+class PyramidBroadcast:
+    """The depth pyramid from the rank that built it to every other rank WITHOUT a collective: the pyramids live in
+    peer-mapped memory, the source rank scatters one chunk to each other rank (orbit_peer_put: NVLink stores + a completion
+    flag on the receiver), every rank forwards the chunk it received to the remaining ranks, and waits for their chunks'
+    flags (orbit_peer_wait). Each GPU sends and receives ~one pyramid's worth of bytes through the switch instead of the
+    source sending world-1 copies or a ring passing it hand to hand: the NCCL broadcast of the 22.4 MB 4K pyramid took
+    150-340 us on 8 GPUs (profiles/r2_c3_timeline_n8.txt) and was the largest item of the sharded frame.
+    The caller guarantees what a collective would: no rank calls broadcast() for frame N+1 before every rank has finished
+    reading the pyramid of frame N (ShardedView.step_best: its closing fence)."""
+
+    FLAG_BYTES = 256     # word 0: "my chunk has arrived" (written by the source), word 1+q: "rank q's chunk has arrived"
+
+    def __init__(self, context, pyramid, src=0, group=None):
+        import ctypes as C
+        from . import _lib, layouts as L
+        self.C, self.L, self.lib, self.context, self.group, self.src = C, L, _lib.lib(), context, group, src
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        assert 2 <= self.world <= 16
+        self.pyr_bytes = (4 * int(pyramid.info.total_texels) + 15) // 16 * 16
+        nbytes = self.pyr_bytes + self.FLAG_BYTES
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(self.lib.orbit_peer_alloc(context._h, nbytes, C.byref(ptr), handle), "orbit_peer_alloc")
+        self.local = ptr.value
+        pyramid.rebind_external(self.local)
+        pyramid.texels.zero_()
+        class _Mem:
+            def __init__(self, p, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(p), False), "version": 2}
+        self._flag_mem = _Mem(self.local + self.pyr_bytes, self.FLAG_BYTES // 4)
+        self.flags = torch.as_tensor(self._flag_mem, device=context.device)
+        self.flags.zero_()
+        torch.cuda.synchronize(context.device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.peers = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.peers.append(self.local)
+            else:
+                q = C.c_void_p()
+                _lib.check(self.lib.orbit_peer_open(context._h, handles[r], C.byref(q)), "orbit_peer_open")
+                self.peers.append(q.value)
+        # chunk k (16-byte aligned) belongs to the k-th rank that is not the source
+        others = [r for r in range(self.world) if r != src]
+        per = (self.pyr_bytes // 16 + len(others) - 1) // len(others) * 16
+        self.chunk = {r: (min(i * per, self.pyr_bytes), min((i + 1) * per, self.pyr_bytes)) for i, r in enumerate(others)}
+        self.epoch = 0
+        dist.barrier(group=group)
+
+    def _put(self, transfers):
+        C = self.C
+        arr = (self.L.PeerPut * len(transfers))()
+        for a, (src, dst, nbytes, flag) in zip(arr, transfers):
+            a.src, a.dst, a.bytes, a.dst_flag = src, dst, nbytes, flag
+        rc = self.lib.orbit_peer_put(self.context._h, arr, len(transfers), self.epoch, C.c_void_p(torch.cuda.current_stream(self.context.device).cuda_stream))
+        if rc:
+            raise RuntimeError("orbit_peer_put: %d" % rc)
+
+    def _wait(self, first_word, n):
+        C = self.C
+        rc = self.lib.orbit_peer_wait(self.context._h, C.c_void_p(self.local + self.pyr_bytes + 4 * first_word), n, 1, self.epoch,
+                                      C.c_void_p(torch.cuda.current_stream(self.context.device).cuda_stream))
+        if rc:
+            raise RuntimeError("orbit_peer_wait: %d" % rc)
+
+    def broadcast(self):
+        """Enqueued on the current stream of every rank; on the source rank after the kernel that wrote the pyramid."""
+        self.epoch += 1
+        fo = self.pyr_bytes
+        if self.rank == self.src:
+            self._put([(self.local + b, self.peers[r] + b, e - b, self.peers[r] + fo) for r, (b, e) in self.chunk.items() if e > b])
+            return
+        b, e = self.chunk[self.rank]
+        # my own slot and the source's are satisfied by definition, so the final wait can take all `world` slots at once
+        self.flags[1 + self.rank] = self.epoch
+        self.flags[1 + self.src] = self.epoch
+        if e > b:
+            self._wait(0, 1)                                       # my chunk has arrived from the source
+        fwd = [(self.local + b, self.peers[q] + b, e - b, self.peers[q] + fo + 4 * (1 + self.rank))
+               for q in range(self.world) if q not in (self.src, self.rank)]
+        if fwd:
+            self._put(fwd)                                         # (an empty chunk still delivers its flag)
+        self._wait(1, self.world)                                  # every other rank's chunk has arrived
+
+    def close(self):
+        for r, p in enumerate(self.peers):
+            if r != self.rank:
+                self.lib.orbit_peer_close(self.context._h, self.C.c_void_p(p))
+        self.lib.orbit_peer_free(self.context._h, self.C.c_void_p(self.local))
+
+
 class ShardedView:
     """One huge view culled by `world` GPUs (BASELINE config C3). Rank 0 owns the depth buffer and builds the
     pyramid; every rank culls its entity-draw range with the CUDA passes; survivors are all-gathered."""
 
-    def __init__(self, context, scene, view, depth_np, rank, world):
+    def __init__(self, context, scene, view, depth_np, rank, world, root_weight=None):
+        """`root_weight`: rank 0's share of the meshlets relative to the other ranks' 1.0. Rank 0 also builds the pyramid and
+        emits both command lists (the early list's 229 MB of stores at C3 overlap its late test), so an equal share makes it the
+        straggler (profiles/r2_c3_timeline_n4.txt: late test 311 us against 200 us on the others); default 0.75 for world > 1
+        (ORBIT_ROOT_WEIGHT overrides)."""
+        import os
         from . import frame
         self.frame = frame
         self.context, self.view, self.rank, self.world = context, view, rank, world
         lod0 = scene.mesh_infos["mesh_lods"][:, 0, 1][scene.draws["mesh_index"]]
         self._lod0_records = (lod0.astype(np.int64) + 31) // 32
-        self.ranges = partition_draws(lod0, world)
+        if root_weight is None:
+            root_weight = float(os.environ.get("ORBIT_ROOT_WEIGHT", "0.75"))
+        self.ranges = partition_draws(lod0, world, [root_weight] + [1.0] * (world - 1) if world > 1 else None)
         b, e = self.ranges[rank]
         if b == e:            # empty range: keep the launch legal
             e = b
@@ -343,10 +444,16 @@ class ShardedView:
             self.gathered_late = torch.zeros(4 + DRAW_BYTES * self.total_dcap, dtype=torch.uint8, device=self.context.device)
         self._side = torch.cuda.Stream()                          # default = lowest priority
         self._crit = torch.cuda.Stream(priority=-1)
+        # the pyramid travels by one-sided NVLink puts (PyramidBroadcast) unless ORBIT_NCCL_PYRAMID=1 asks for the NCCL broadcast
+        import os
+        self.pyr_bcast = None
+        if self.world > 1 and not os.environ.get("ORBIT_NCCL_PYRAMID"):
+            self.pyr_bcast = PyramidBroadcast(self.context, self.vstate.depth_pyramid, src=0)
 
     def best_exchange_name(self):
         return ("16-byte record entries {draw mask, entity, meshlet offset} to rank 0 by NVLink peer stores (device-side counts), "
-                "rank 0 emits the commands of the combined list; the early list's exchange + emission overlap Hi-Z, its broadcast and the late pass")
+                "rank 0 emits the commands of the combined list; the early list's exchange + emission overlap Hi-Z, its broadcast and the late pass; "
+                + ("pyramid: scatter + forward by one-sided NVLink puts with completion flags" if self.pyr_bcast is not None else "pyramid: NCCL broadcast"))
 
     def step_best(self, marks=None):
         """early cull (test only) -> [side stream: entries -> rank 0, rank 0 emits the early list] || Hi-Z on rank 0 + broadcast ->
@@ -379,7 +486,10 @@ class ShardedView:
             if self.rank == 0:
                 pf.hiz()
             mark("hiz built")
-            broadcast_pyramid(self.vstate.depth_pyramid.texels, src=0)
+            if self.pyr_bcast is not None:
+                self.pyr_bcast.broadcast()
+            else:
+                broadcast_pyramid(self.vstate.depth_pyramid.texels, src=0)
             mark("pyramid broadcast")
             if not self.empty:
                 pf.entity(True); pf.meshlet_test(True, self.mx_late.local_masks)
@@ -409,3 +519,8 @@ class ShardedView:
             if hasattr(self, name):
                 getattr(self, name).close()
                 delattr(self, name)
+        if getattr(self, "pyr_bcast", None) is not None:      # the pyramid lives in its memory: nothing may use the view afterwards
+            torch.cuda.synchronize(self.context.device)
+            dist.barrier()
+            self.pyr_bcast.close()
+            self.pyr_bcast = None

@@ -244,6 +244,21 @@ class DepthPyramid:
         if (int(size[0]), int(size[1])) != self.size:
             self._make(size)
 
+    def rebind_external(self, device_ptr):
+        """Moves the pyramid onto caller-owned device memory of info.total_texels floats (orbit_hiz_wrap): peer-shareable
+        memory for the sharded view (multi_gpu.PyramidBroadcast), or an imported Vulkan allocation. Contents start undefined."""
+        class _Mem:     # torch.as_tensor understands __cuda_array_interface__
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        w, h = self.size
+        self._external = _Mem(device_ptr, int(self.info.total_texels))
+        self.texels = torch.as_tensor(self._external, device=self.context.device)
+        if self._h:
+            _lib.lib().orbit_hiz_destroy(self._h)
+            self._h = C.c_void_p()
+        _lib.check(_lib.lib().orbit_hiz_wrap(self.context._h, w, h, C.c_void_p(int(device_ptr)), C.byref(self._h)), "orbit_hiz_wrap")
+        self.usable = False
+
     def update(self, depth_buffer):
         """depth_buffer: float32 device tensor [H, W] (reverse-Z)."""
         h, w = depth_buffer.shape

@@ -106,7 +106,11 @@ pub struct OrbitClusterParams { pub info: OrbitClusterCullInfo, pub z_scale: f32
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
-pub struct OrbitStatus { pub dispatch_overflow: u32, pub draw_overflow: u32, pub light_index_overflow: u32, pub visibility_overflow: u32, pub asset_error: u32, pub reserved: [u32; 3] }
+pub struct OrbitStatus { pub dispatch_overflow: u32, pub draw_overflow: u32, pub light_index_overflow: u32, pub visibility_overflow: u32, pub asset_error: u32, pub peer_timeout: u32, pub reserved: [u32; 2] }
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct OrbitPeerPut { pub src: *const c_void, pub dst: *mut c_void, pub bytes: u64, pub dst_flag: *mut u32 }
 
 extern "C" {
     pub fn orbit_abi_version() -> i32;
@@ -131,6 +135,8 @@ extern "C" {
     pub fn orbit_light_cluster(ctx: *mut orbit_ctx, params: *const OrbitClusterParams, depth: *const f32, lights: *const c_void,
                                tile_masks: *mut c_void, depth_bounds: *mut c_void, unique_clusters: *mut c_void,
                                offset_count_image: *mut c_void, light_index_list: *mut c_void, capacity_indices: u64, stream: *mut c_void) -> i32;
+    pub fn orbit_peer_put(ctx: *mut orbit_ctx, puts: *const OrbitPeerPut, n_puts: u32, flag_value: u32, stream: *mut c_void) -> c_int;
+    pub fn orbit_peer_wait(ctx: *mut orbit_ctx, flags: *const u32, n_flags: u32, stride_words: u32, flag_value: u32, stream: *mut c_void) -> c_int;
     pub fn orbit_cull_pair_compatible(late: *const OrbitCullInfo, main_pass: *const OrbitCullInfo) -> c_int;
     pub fn orbit_entity_cull_late_main(ctx: *mut orbit_ctx, late: *const OrbitCullInfo, main_pass: *const OrbitCullInfo, scene: *const OrbitSceneBuffers,
                                        hiz: *const orbit_hiz, late_dispatch_buffer: *mut c_void, main_dispatch_buffer: *mut c_void,
@@ -182,6 +188,18 @@ impl Context {
                                                draw_command_buffer: *mut c_void, capacity_draws: u64, stream: *mut c_void) -> Result<(), Error> {
         check(orbit_meshlet_cull(self.0, cull, scene, hiz, meshlet_dispatch_buffer, capacity_records, draw_command_buffer,
                                  capacity_draws, std::ptr::null_mut(), stream))
+    }
+    /// The LATE cull of the depth prepass (forward.rs:266-403) + the MAIN pass's cull (forward.rs:518-548), fused. Ok(false):
+    /// the two CullInfos are not a compatible pair and nothing was launched — issue the four separate calls instead.
+    pub unsafe fn create_late_and_main_commands(&self, late: &OrbitCullInfo, main_pass: &OrbitCullInfo, scene: &OrbitSceneBuffers,
+                                                hiz: *const orbit_hiz, late_dispatch_buffer: *mut c_void, main_dispatch_buffer: *mut c_void,
+                                                capacity_records: u64, late_draw_command_buffer: *mut c_void,
+                                                main_draw_command_buffer: *mut c_void, capacity_draws: u64, stream: *mut c_void) -> Result<bool, Error> {
+        if orbit_cull_pair_compatible(late, main_pass) == 0 { return Ok(false); }
+        check(orbit_entity_cull_late_main(self.0, late, main_pass, scene, hiz, late_dispatch_buffer, main_dispatch_buffer, capacity_records, stream))?;
+        check(orbit_meshlet_cull_late_main(self.0, late, main_pass, scene, hiz, late_dispatch_buffer, capacity_records, late_draw_command_buffer,
+                                           main_draw_command_buffer, capacity_draws, std::ptr::null_mut(), std::ptr::null_mut(), stream))?;
+        Ok(true)
     }
 }
 impl Drop for Context { fn drop(&mut self) { unsafe { orbit_ctx_destroy(self.0) } } }

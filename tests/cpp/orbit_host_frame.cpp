@@ -6,7 +6,8 @@
 //   orbit_host_frame <dir>     reads <dir>/{meta,meshlets,mesh_infos,materials,entities,entity_draws,depth}.bin
 //                              and, when present, <dir>/{transforms,mesh_slots}.bin: the entity buffers are then produced on
 //                              the GPU by SceneData::update_scene (orbit_scene_update) instead of being uploaded
-//                              writes <dir>/f<k>_{early,late}_{dispatch,draws}.bin, entity_vis.bin, meshlet_vis.bin, hiz.bin
+//                              writes <dir>/f<k>_{early,late}_{dispatch,draws}.bin (k = 0, 1), f2_{early,late,main}_* (LATE + MAIN fused),
+//                              entity_vis.bin, meshlet_vis.bin, hiz.bin
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -115,6 +116,37 @@ int main(int argc, char** argv) {
             dump(tag + "_dispatch.bin", dispatch, 12 + 16 * (size_t)nrec);
             dump(tag + "_draws.bin", draws, 4 + 28 * (size_t)ndraw);
         }
+    }
+    {   // ---- frame 2: EARLY as before, then LATE + MAIN (forward.rs:518-548) through the fused wrapper
+        void *main_dispatch = nullptr, *main_draws = nullptr;
+        CU(cudaMalloc(&main_dispatch, dispatch_bytes)); CU(cudaMalloc(&main_draws, draw_bytes));
+        CU(cudaMemset(main_dispatch, 0, dispatch_bytes));
+        auto dump_pass = [&](const std::string& tag, void* disp, void* drw) {
+            uint32_t nrec = 0, ndraw = 0;
+            CU(cudaMemcpy(&nrec, disp, 4, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(&ndraw, drw, 4, cudaMemcpyDeviceToHost));
+            dump(tag + "_dispatch.bin", disp, 12 + 16 * (size_t)nrec);
+            dump(tag + "_draws.bin", drw, 4 + 28 * (size_t)ndraw);
+        };
+        CullInfo early = cull, late = cull;
+        early.occlusion_culling = OcclusionCullInfo{};
+        early.occlusion_culling.kind = OcclusionCullInfo::VisibilityRead;
+        early.occlusion_culling.visibility_buffer = entity_vis;
+        early.occlusion_culling.meshlet_visibility_buffer = meshlet_vis;
+        early.occlusion_culling.aspect_ratio = (float)m.width / (float)m.height;
+        create_meshlet_dispatch_command(ctx, assets, scene, early, dispatch, m.record_capacity, stream);
+        create_meshlet_draw_commands(ctx, assets, scene, early, dispatch, m.record_capacity, draws, m.draw_capacity, stream);
+        CU(cudaStreamSynchronize(stream));
+        dump_pass(dir + "/f2_early", dispatch, draws);
+        late.occlusion_culling = early.occlusion_culling;
+        late.occlusion_culling.kind = OcclusionCullInfo::VisibilityWrite;
+        pyramid.update(depth, stream);
+        late.occlusion_culling.depth_pyramid = pyramid.get_current();
+        const bool fused = create_late_and_main_commands(ctx, assets, scene, late, early /* MAIN = pass 1 again */, dispatch, main_dispatch,
+                                                         m.record_capacity, draws, main_draws, m.draw_capacity, stream);
+        if (!fused) { std::fprintf(stderr, "LATE / MAIN pair unexpectedly incompatible\n"); return 5; }
+        CU(cudaStreamSynchronize(stream));
+        dump_pass(dir + "/f2_late", dispatch, draws);
+        dump_pass(dir + "/f2_main", main_dispatch, main_draws);
     }
     dump(dir + "/entity_vis.bin", entity_vis, ev_words * 4);
     dump(dir + "/meshlet_vis.bin", meshlet_vis, mv_words * 4);

@@ -255,3 +255,44 @@ def test_record_mask_exchange_on_one_gpu(gpu_context, oracle):
     g = frame.depth_prepass_culling(ctx, whole, vs, view, d_depth)
     torch.cuda.synchronize()
     _frames_equal(oracle, g, oracle.depth_prepass_culling(hs, view, depth))
+
+
+def test_peer_put_and_wait_on_one_gpu(gpu_context):
+    """orbit_peer_put / orbit_peer_wait with the GPU as its own peer: several transfers in one launch deliver their bytes and
+    then their flags; a wait on delivered flags returns at once, a wait on a flag nobody writes gives up and reports
+    OrbitStatus::peer_timeout (orbit_ctx_poll_status -> ORBIT_ERR_CUDA) instead of hanging."""
+    import time
+    from orbit_b200 import _lib, layouts as L
+    ctx, lib = gpu_context, _lib.lib()
+    dev = ctx.device
+    n = 3
+    sizes = [16 * 1000, 16 * 70001, 16]
+    src = [torch.randint(0, 2 ** 31 - 1, (s // 4,), dtype=torch.int32, device=dev) for s in sizes]
+    dst = [torch.zeros(s // 4, dtype=torch.int32, device=dev) for s in sizes]
+    flags = torch.zeros(8, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for epoch in (1, 2):
+        for d in dst:
+            d.zero_()
+        puts = (L.PeerPut * n)()
+        for i in range(n):
+            puts[i].src, puts[i].dst, puts[i].bytes, puts[i].dst_flag = src[i].data_ptr(), dst[i].data_ptr(), sizes[i], flags.data_ptr() + 4 * (2 * i)
+        assert lib.orbit_peer_put(ctx._h, puts, n, epoch, stream) == 0
+        assert lib.orbit_peer_wait(ctx._h, C.c_void_p(flags.data_ptr()), n, 2, epoch, stream) == 0
+        torch.cuda.synchronize()
+        assert flags.cpu().tolist() == [epoch, 0, epoch, 0, epoch, 0, 0, 0]
+        assert all(torch.equal(a, b) for a, b in zip(src, dst))
+    st = L.Status()
+    assert lib.orbit_ctx_poll_status(ctx._h, C.byref(st)) == 0 and st.peer_timeout == 0
+    # misaligned / oversized requests are refused
+    puts[0].bytes = 24
+    assert lib.orbit_peer_put(ctx._h, puts, 1, 3, stream) != 0
+    assert lib.orbit_peer_put(ctx._h, puts, 17, 3, stream) != 0
+    # a flag that never arrives: bounded wait, status word set
+    t0 = time.time()
+    assert lib.orbit_peer_wait(ctx._h, C.c_void_p(flags.data_ptr() + 4), 1, 1, 99, stream) == 0
+    torch.cuda.synchronize()
+    assert time.time() - t0 < 30.0
+    rc = lib.orbit_ctx_poll_status(ctx._h, C.byref(st))
+    assert st.peer_timeout == 1 and rc != 0
+    assert lib.orbit_ctx_poll_status(ctx._h, C.byref(st)) == 0 and st.peer_timeout == 0      # cleared by the poll

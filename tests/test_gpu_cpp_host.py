@@ -51,9 +51,11 @@ def test_cpp_host_mirror_two_frames(tmp_path, oracle, with_scene_update):
         assert np.array_equal(np.fromfile(os.path.join(d, "entity_data_out.bin"), np.uint8), sc.entities.view(np.uint8).reshape(-1))
         assert np.array_equal(np.fromfile(os.path.join(d, "entity_draws_out.bin"), np.uint8), sc.entity_draws)
     hs = oracle.HostScene(sc)
-    for f in range(2):
+    for f in range(3):                 # frame 2 ends with LATE + MAIN through the fused wrapper (create_late_and_main_commands)
         o = oracle.depth_prepass_culling(hs, view, depth)
-        for k in ("early", "late"):
+        if f == 2:
+            o["main"] = oracle.main_pass_culling(hs, view)
+        for k in (("early", "late") if f < 2 else ("early", "late", "main")):
             ohdr, orecs = oracle.parse_dispatch(o[k][0]); on, od = oracle.parse_draws(o[k][1])
             g_disp = np.fromfile(os.path.join(d, "f%d_%s_dispatch.bin" % (f, k)), np.uint8)
             g_draw = np.fromfile(os.path.join(d, "f%d_%s_draws.bin" % (f, k)), np.uint8)

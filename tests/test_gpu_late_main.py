@@ -221,3 +221,45 @@ def test_incompatible_pairs_are_refused(gpu_context):
     assert lib.orbit_meshlet_cull_late_main(ctx._h, C.byref(g_late), C.byref(bad[1]), C.byref(sb), vs.depth_pyramid._h, p(a), rcap, p(da), p(db), dcap,
                                             None, None, stream) == INVALID
     assert lib.orbit_entity_cull_late_main(ctx._h, C.byref(g_late), C.byref(g_main), C.byref(sb), vs.depth_pyramid._h, p(a), p(a), rcap, stream) == INVALID
+
+
+def test_random_cameras_through_the_prepared_frame(gpu_context, oracle):
+    """Randomised differential run of the whole frame in the form bench.py times (EARLY, Hi-Z, fused LATE + MAIN through
+    PreparedFrame): a multi-LOD lattice, twelve random cameras (position, direction, field of view, resolution, LOD base),
+    each culled for two frames against visibility bits left by the previous camera; every buffer against the oracle."""
+    from orbit_b200 import frame
+    ctx = gpu_context
+    rng = np.random.default_rng(20260217)
+    sc, _ = scenes.config_c1(scale=0.5, lods=(100, 45, 12))
+    lo, hi = np.asarray(sc.aabb_min, np.float64), np.asarray(sc.aabb_max, np.float64)
+    ds = frame.DeviceScene.upload(ctx, sc)
+    hs = oracle.HostScene(sc)
+    states = {}
+    late_survivors = 0
+    for i in range(12):
+        w, h = [(640, 360), (1280, 720), (1000, 600), (1920, 1080)][int(rng.integers(4))]
+        eye = lo + (hi - lo) * rng.uniform(-0.1, 1.1, 3)
+        d = rng.normal(size=3); d[1] *= 0.3; d /= np.linalg.norm(d)
+        view = scenes.perspective_view(tuple(eye), tuple(d), w, h, fov_deg=float(rng.uniform(40.0, 110.0)))
+        view.lod_base = float(rng.choice([4.0, 16.0, 40.0]))
+        depth = scenes.make_depth(sc, view)
+        d_depth = torch.from_numpy(depth).to(ctx.device)
+        if (w, h) not in states:          # one visibility state per resolution (the pyramid belongs to it); the oracle shares ONE
+            states[(w, h)] = frame.ViewState(ctx, ds, (w, h), name="lm_rand_%dx%d" % (w, h))
+        vs = states[(w, h)]
+        # the oracle keeps one set of bits: copy them into this resolution's state so both sides start from the same history
+        vs.meshlet_visibility.copy_(torch.from_numpy(hs.meshlet_visibility.view(np.int32)).to(ctx.device).view(vs.meshlet_visibility.dtype)[:vs.meshlet_visibility.numel()])
+        vs.entity_visibility.copy_(torch.from_numpy(hs.entity_visibility.view(np.int32)).to(ctx.device).view(vs.entity_visibility.dtype)[:vs.entity_visibility.numel()])
+        pf = frame.PreparedFrame(ctx, ds, vs, view, d_depth, name="lm_rand_%d" % i, main_pass=True)
+        assert pf.fused
+        for f in range(2):
+            pf.launch()
+            torch.cuda.synchronize()
+            o = oracle.depth_prepass_culling(hs, view, depth)
+            o["main"] = oracle.main_pass_culling(hs, view)
+            for k, g in (("early", (pf.early_dispatch, pf.early_draws)), ("late", (pf.late_dispatch, pf.late_draws)), ("main", (pf.main_dispatch, pf.main_draws))):
+                n = _same(oracle, g, o[k], (i, f, k))
+                if k == "late":
+                    late_survivors += n[1]
+            _bits_equal(vs, hs, (i, f))
+    assert late_survivors > 0
