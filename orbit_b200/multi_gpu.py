@@ -343,8 +343,8 @@ class ShardedView:
     def __init__(self, context, scene, view, depth_np, rank, world, root_weight=None):
         """`root_weight`: rank 0's share of the meshlets relative to the other ranks' 1.0. Rank 0 also builds the pyramid and
         emits both command lists (the early list's 229 MB of stores at C3 overlap its late test), so an equal share makes it the
-        straggler (profiles/r2_c3_timeline_n4.txt: late test 311 us against 200 us on the others); default 0.75 for world > 1
-        (ORBIT_ROOT_WEIGHT overrides)."""
+        straggler (profiles/r2_c3_timeline_n4.txt: late test 311 us against 200 us on the others); default 0.5 for world > 1
+        (8 GPUs, frame end by the timeline tool: 461 us at 0.75, 445 at 0.5, 444 at 0.3; ORBIT_ROOT_WEIGHT overrides)."""
         import os
         from . import frame
         self.frame = frame
@@ -352,7 +352,7 @@ class ShardedView:
         lod0 = scene.mesh_infos["mesh_lods"][:, 0, 1][scene.draws["mesh_index"]]
         self._lod0_records = (lod0.astype(np.int64) + 31) // 32
         if root_weight is None:
-            root_weight = float(os.environ.get("ORBIT_ROOT_WEIGHT", "0.75"))
+            root_weight = float(os.environ.get("ORBIT_ROOT_WEIGHT", "0.5"))
         self.ranges = partition_draws(lod0, world, [root_weight] + [1.0] * (world - 1) if world > 1 else None)
         b, e = self.ranges[rank]
         if b == e:            # empty range: keep the launch legal
@@ -480,9 +480,6 @@ class ShardedView:
             with torch.cuda.stream(self._side):
                 self.mx_early.exchange(pf.early_dispatch)
                 mark("early entries on rank 0", self._side)
-                if self.rank == 0:
-                    self.mx_early.expand(pf.sb_early, self.gathered_early, self.total_dcap)
-                mark("early list emitted", self._side)
             if self.rank == 0:
                 pf.hiz()
             mark("hiz built")
@@ -491,6 +488,16 @@ class ShardedView:
             else:
                 broadcast_pyramid(self.vstate.depth_pyramid.texels, src=0)
             mark("pyramid broadcast")
+            # Rank 0 emits the early list (C3: 229 MB of stores) only after the pyramid has left: emitted beside the Hi-Z build
+            # it stretched that build from ~50 to 126 us on 8 GPUs — on the critical path of every rank — while beside rank
+            # 0's own (lighter) late test it only delays rank 0 (profiles/r2_c3_timeline_n8.txt)
+            if self.rank == 0:
+                sent = torch.cuda.Event()
+                sent.record(main)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(sent)
+                    self.mx_early.expand(pf.sb_early, self.gathered_early, self.total_dcap)
+            mark("early list emitted", self._side)
             if not self.empty:
                 pf.entity(True); pf.meshlet_test(True, self.mx_late.local_masks)
             else:
