@@ -342,9 +342,12 @@ class ShardedView:
 
     def __init__(self, context, scene, view, depth_np, rank, world, root_weight=None):
         """`root_weight`: rank 0's share of the meshlets relative to the other ranks' 1.0. Rank 0 also builds the pyramid and
-        emits both command lists (the early list's 229 MB of stores at C3 overlap its late test), so an equal share makes it the
-        straggler (profiles/r2_c3_timeline_n4.txt: late test 311 us against 200 us on the others); default 0.5 for world > 1
-        (8 GPUs, frame end by the timeline tool: 461 us at 0.75, 445 at 0.5, 444 at 0.3; ORBIT_ROOT_WEIGHT overrides)."""
+        emits both command lists (the early list's 229 MB of stores at C3 overlap its late test) — a fixed ~250 us of extra work,
+        so an equal share makes it the straggler once the per-rank test time is of that order (4 GPUs, equal shares: late test
+        311 us against 200 us on the others, profiles/r2_c3_timeline_n4.txt; 8 GPUs, frame end by the timeline tool: 461 us at
+        0.75, 445 at 0.5, 444 at 0.3), while on 2 GPUs half a share only moves the work to rank 1 (C3 with exchange: 769 us
+        with equal shares, 792 at 0.5). Default: max(0.25, 1.03 - 0.066 * world) — 0.9 / 0.77 / 0.5 on 2 / 4 / 8 GPUs;
+        ORBIT_ROOT_WEIGHT overrides."""
         import os
         from . import frame
         self.frame = frame
@@ -352,7 +355,7 @@ class ShardedView:
         lod0 = scene.mesh_infos["mesh_lods"][:, 0, 1][scene.draws["mesh_index"]]
         self._lod0_records = (lod0.astype(np.int64) + 31) // 32
         if root_weight is None:
-            root_weight = float(os.environ.get("ORBIT_ROOT_WEIGHT", "0.5"))
+            root_weight = float(os.environ.get("ORBIT_ROOT_WEIGHT", "%.3f" % max(0.25, 1.03 - 0.066 * world)))
         self.ranges = partition_draws(lod0, world, [root_weight] + [1.0] * (world - 1) if world > 1 else None)
         b, e = self.ranges[rank]
         if b == e:            # empty range: keep the launch legal
