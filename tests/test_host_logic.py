@@ -93,3 +93,22 @@ def test_partition_draws_balanced_and_aligned():
         assert max(sums) - min(sums) <= 2 * 32 * 400
     assert partition_draws([5, 5], 4)[-1][1] == 2
     assert sorted(sum((views_for_rank(256, r, 8) for r in range(8)), [])) == list(range(256))
+
+
+def test_partition_draws_with_weights():
+    """Rank 0 of a sharded view takes a lighter share (it also builds the pyramid and emits both lists): the ranges stay
+    contiguous, 32-aligned and complete, and the sums follow the weights."""
+    from orbit_b200.multi_gpu import partition_draws
+    rng = np.random.default_rng(1)
+    counts = rng.integers(1, 400, size=20011)
+    total = counts.sum()
+    for world, w0 in ((2, 0.9), (4, 0.77), (8, 0.5), (8, 0.0)):
+        weights = [w0] + [1.0] * (world - 1)
+        parts = partition_draws(counts, world, weights)
+        assert parts[0][0] == 0 and parts[-1][1] == len(counts)
+        for (b0, e0), (b1, e1) in zip(parts, parts[1:]):
+            assert e0 == b1 and b1 % 32 == 0
+        sums = np.array([counts[b:e].sum() for b, e in parts], dtype=np.float64)
+        want = total * np.array(weights) / sum(weights)
+        assert np.all(np.abs(sums - want) <= 2 * 32 * 400), (world, w0)
+    assert partition_draws(counts, 3, None) == partition_draws(counts, 3, [1, 1, 1])
