@@ -556,9 +556,17 @@ static int meshlet_stage(orbit_ctx* c, const OrbitCullInfo* cull, const OrbitSce
     const uint64_t grid = (uint64_t)c->sm_count * (uint64_t)per_sm;
     // emit kernel: two CTAs per SM (every CTA repeats the 2048-entry chunk scan; more CTAs only add to that)
     if (c->emit_occupancy <= 0) c->emit_occupancy = meshlet_emit_max_ctas_per_sm();
-    int emit_per_sm = c->emit_occupancy < 2 ? (c->emit_occupancy > 0 ? c->emit_occupancy : 1) : 2;
-    if (c->emit_ctas_per_sm >= 1 && c->emit_ctas_per_sm <= c->emit_occupancy) emit_per_sm = c->emit_ctas_per_sm;   // tuning knob
+    // emit kernel: as many CTAs per SM as fit (3) for long lists; two per SM take part when the list is short (decided on the
+    // device from the survivor count, see meshlet_emit_body)
+    int emit_per_sm = c->emit_occupancy > 0 ? c->emit_occupancy : 1;
+    if (emit_per_sm > 4) emit_per_sm = 4;
+    // even CTAs that leave at once cost launch time (C2 frame: +1.6 us over its three emit launches), so a dispatch buffer too
+    // small for a long list (capacity below 2^18 records = 8 M meshlets) gets the two per SM of the short case outright
+    if (max_records < (1u << 18) && emit_per_sm > 2) emit_per_sm = 2;
+    int emit_small_per_sm = emit_per_sm < 2 ? emit_per_sm : 2;
+    if (c->emit_ctas_per_sm >= 1 && c->emit_ctas_per_sm <= c->emit_occupancy) emit_per_sm = emit_small_per_sm = c->emit_ctas_per_sm;   // tuning knob
     const uint64_t emit_grid = (uint64_t)c->sm_count * (uint64_t)emit_per_sm;
+    p.emit_small_grid = (uint32_t)(c->sm_count * emit_small_per_sm);
     const bool skip_emit = test_only || c->debug_skip == 1;
     const bool pair = fused_main && !skip_emit;      // both lists leave in one emit launch
     CK(launch_meshlet_cull(p, c->debug_skip == 2 ? 0 : (int)grid, (skip_emit || pair) ? 0 : (int)emit_grid, (cudaStream_t)stream));
@@ -636,7 +644,9 @@ int orbit_draws_from_masks(orbit_ctx* c, const OrbitSceneBuffers* scene, const v
     p.region_counts = region_counts; p.region_stride = region_stride_records; p.n_regions = n_regions;
     p.trace_emit = next_trace(c);
     if (c->emit_occupancy <= 0) c->emit_occupancy = meshlet_emit_max_ctas_per_sm();
-    const int emit_per_sm = c->emit_occupancy < 2 ? (c->emit_occupancy > 0 ? c->emit_occupancy : 1) : 2;
+    int emit_per_sm = c->emit_occupancy > 0 ? c->emit_occupancy : 1;
+    if (emit_per_sm > 4) emit_per_sm = 4;
+    p.emit_small_grid = (uint32_t)(c->sm_count * (emit_per_sm < 2 ? emit_per_sm : 2));
     CK(launch_draws_from_masks(p, c->counters + 16, c->sm_count * 4, c->sm_count * emit_per_sm, (cudaStream_t)stream));
     c->launches += 2;
     return ORBIT_OK;

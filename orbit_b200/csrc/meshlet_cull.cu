@@ -970,6 +970,7 @@ __device__ __forceinline__ uint32_t select_set_bit(uint32_t m, uint32_t n) {
 //   3. the counts of the OTHER parity are zeroed for the next call and the parity word the next test kernel reads is
 //      flipped — no done-counter, fence or atomic on the way out (that exit chain was ~1/3 of this kernel's samples).
 constexpr int kEmitWarps = 8;
+constexpr uint32_t kEmitBulkSurvivors = 1u << 18;   // lists at least this long are emitted by every launched CTA
 constexpr uint32_t kMaxRegions = 16u;   // ranks of a sharded view (orbit_draws_from_masks)
 __device__ __forceinline__ void meshlet_emit_body(const MeshletCullParams& p) {
     __shared__ uint32_t s_prefix[kMaxChunks];            // inclusive survivor count up to chunk c
@@ -994,6 +995,20 @@ __device__ __forceinline__ void meshlet_emit_body(const MeshletCullParams& p) {
         return (size_t)k * p.region_stride + (rec - s_region[k]);
     };
     ORBIT_TRACE_STAMP(p.trace_emit, 3, 0);
+    // Long lists want every CTA the SM can hold (their walk is bound by the loads in flight: C5, 10 M survivors: 274 / 212 /
+    // 185 us per view with 1 / 2 / 3 CTAs per SM); for short ones more CTAs only repeat the chunk scan and thin out the shares
+    // (C2 frame: +2.4 us with 3 instead of 2 per SM). The launch is sized for the long case; a SURPLUS CTA first looks at the
+    // survivor count alone (12 bytes) and leaves at once when the list is short.
+    const bool surplus = p.emit_small_grid != 0u && blockIdx.x >= p.emit_small_grid;
+    if (surplus) {
+        const uint2 tt = __ldcg(reinterpret_cast<const uint2*>(p.draw_total));
+        const uint32_t par = __ldcg(p.chunk_parity + 1) & 1u;
+        if ((par ? tt.y : tt.x) < kEmitBulkSurvivors) {
+            // its share of the other parity's counters still has to be zeroed for the next call
+            for (uint32_t i = blockIdx.x * blockDim.x + tid; i < kMaxChunks; i += gridDim.x * blockDim.x) p.chunk_counts[(par ^ 1u) * kMaxChunks + i] = 0u;
+            return;
+        }
+    }
     // both halves of the chunk counts are requested before the parity is known: one round trip instead of two
     uint32_t v0[8], v1[8];
     {
@@ -1015,7 +1030,8 @@ __device__ __forceinline__ void meshlet_emit_body(const MeshletCullParams& p) {
     // zero the other parity's counters for the next call (it runs after this kernel in stream order)
     for (uint32_t i = blockIdx.x * blockDim.x + tid; i < kMaxChunks; i += gridDim.x * blockDim.x) p.chunk_counts[(parity ^ 1u) * kMaxChunks + i] = 0u;
     if (blockIdx.x == 0 && tid == 0) { p.draw_total[parity ^ 1u] = 0u; p.chunk_parity[0] = parity ^ 1u; }   // word A for the next call
-    const uint32_t gw = blockIdx.x * kEmitWarps + warp, GW = gridDim.x * kEmitWarps;
+    const uint32_t eff_grid = (grand_total >= kEmitBulkSurvivors || p.emit_small_grid == 0u) ? gridDim.x : min(gridDim.x, p.emit_small_grid);
+    const uint32_t gw = blockIdx.x * kEmitWarps + warp, GW = eff_grid * kEmitWarps;
     if (grand_total != 0u) {
         const uint32_t chunk_rec = 1u << chunk_shift_of(nrec);
         const uint32_t nchunks = (nrec + chunk_rec - 1u) / chunk_rec;
@@ -1179,34 +1195,53 @@ __device__ __forceinline__ void meshlet_emit_body(const MeshletCullParams& p) {
                         // step's commands — contiguous in the output — as consecutive words (seven 128-byte stores instead of seven
                         // 28-byte-strided ones that touch 28 sectors each; the emit kernel writes 28 B per survivor and was store-bound
                         // at C5 scale)
-                        for (uint32_t ol0 = l0; ol0 < l1; ol0 += 32u) {
-                            const uint32_t ol = ol0 + lane;
-                            __syncwarp();
-                            if (ol < l1) {
-                                uint32_t a = 0u, b = 31u;
+                        // Two batches of 32 outputs per iteration: both batches' command words are requested before the first is
+                        // staged, so a warp has two dependent L2 / DRAM round trips in flight instead of one (the walk of a long
+                        // list is one such round trip per 32 outputs per warp: at C5 scale — 10 M survivors, 130 batches per warp —
+                        // that chain, not bandwidth, set the kernel's 223 us).
+                        for (uint32_t ol0 = l0; ol0 < l1; ol0 += 64u) {
+                            uint4 cw[2]; uint32_t ent[2], midx[2]; bool act[2];
 #pragma unroll
-                                for (int it = 0; it < 5; ++it) {
-                                    const uint32_t mid = (a + b) >> 1;
-                                    if (sr[mid] > ol) b = mid; else a = mid + 1u;
+                            for (uint32_t k = 0; k < 2u; ++k) {
+                                const uint32_t ol = ol0 + 32u * k + lane;
+                                act[k] = ol < l1;
+                                cw[k] = make_uint4(0u, 0u, 0u, 0u); ent[k] = 0u; midx[k] = 0u;
+                                if (act[k]) {
+                                    uint32_t a = 0u, b = 31u;
+#pragma unroll
+                                    for (int it = 0; it < 5; ++it) {
+                                        const uint32_t mid = (a + b) >> 1;
+                                        if (sr[mid] > ol) b = mid; else a = mid + 1u;
+                                    }
+                                    const uint32_t r = a;
+                                    const uint32_t excl = r ? sr[r - 1u] : 0u;
+                                    const uint32_t j = select_set_bit(sr[32 + r], ol - excl);   // (ol-excl)-th survivor of the record
+                                    const uint32_t mo = sr[96 + r];
+                                    midx[k] = (mo & 0x7FFFFFFFu) + j;
+                                    ent[k] = sr[64 + r];
+                                    // command words: from the side array the test kernel filled (x,y,z = vertex_offset, data_offset, packed
+                                    // counts), or — pass 2, whose candidates do not carry them — from the meshlet itself
+                                    if (mo >> 31) { const uint4 mb = __ldg(p.meshlets + 2u * (size_t)midx[k] + 1); cw[k] = make_uint4(mb.y, mb.z, mb.w, 0u); }
+                                    else cw[k] = __ldcg(p.cmd_side + (size_t)(group_rec + r) * 32u + j);
                                 }
-                                const uint32_t r = a;
-                                const uint32_t excl = r ? sr[r - 1u] : 0u;
-                                const uint32_t j = select_set_bit(sr[32 + r], ol - excl);   // (ol-excl)-th survivor of the record
-                                const uint32_t mo = sr[96 + r];
-                                const uint32_t midx = (mo & 0x7FFFFFFFu) + j;
-                                // command words: from the side array the test kernel filled (x,y,z = vertex_offset, data_offset, packed
-                                // counts), or — pass 2, whose candidates do not carry them — from the meshlet itself
-                                uint4 cw;
-                                if (mo >> 31) { const uint4 mb = __ldg(p.meshlets + 2u * (size_t)midx + 1); cw = make_uint4(mb.y, mb.z, mb.w, 0u); }
-                                else cw = __ldcg(p.cmd_side + (size_t)(group_rec + r) * 32u + j);
-                                store_command(stage + lane * 7u, cw.x, cw.y, cw.z, sr[64 + r], midx);
                             }
-                            __syncwarp();
-                            const uint64_t first = (uint64_t)running + ol0;                 // index of this step's first command
-                            uint64_t n_out = min(32u, l1 - ol0);
-                            if (first >= p.capacity_draws) n_out = 0u; else if (first + n_out > p.capacity_draws) n_out = p.capacity_draws - first;
-                            uint32_t* const dst = p.draw_words + 1u + first * 7u;
-                            for (uint32_t w = lane; w < (uint32_t)n_out * 7u; w += 32u) dst[w] = stage[w];
+#pragma unroll
+                            for (uint32_t k = 0; k < 2u; ++k) {
+                                const uint32_t ob = ol0 + 32u * k;                               // first local output of this batch
+                                if (ob < l1) {                                                   // warp-uniform
+                                    // every lane builds its command (7 words) in shared memory, then the warp writes the batch's
+                                    // commands — contiguous in the output — as consecutive words (seven 128-byte stores instead of
+                                    // seven 28-byte-strided ones that touch 28 sectors each)
+                                    __syncwarp();
+                                    if (act[k]) store_command(stage + lane * 7u, cw[k].x, cw[k].y, cw[k].z, ent[k], midx[k]);
+                                    __syncwarp();
+                                    const uint64_t first = (uint64_t)running + ob;               // index of the batch's first command
+                                    uint64_t n_out = min(32u, l1 - ob);
+                                    if (first >= p.capacity_draws) n_out = 0u; else if (first + n_out > p.capacity_draws) n_out = p.capacity_draws - first;
+                                    uint32_t* const dst = p.draw_words + 1u + first * 7u;
+                                    for (uint32_t w = lane; w < (uint32_t)n_out * 7u; w += 32u) dst[w] = stage[w];
+                                }
+                            }
                         }
                     }
                     running += step_total;

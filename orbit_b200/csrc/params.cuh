@@ -54,6 +54,9 @@ struct MeshletCullParams {
     uint32_t* main_chunk_parity;      // [2], like chunk_parity
     uint32_t* main_draw_total;        // [2], like draw_total
     uint32_t main_alpha_mode_flags;
+    // emit kernel: CTAs that take part when the list is short (< kEmitBulkSurvivors); the launch is sized for long lists
+    // (occupancy: the walk of a long list is bound by the loads in flight), the surplus CTAs of a short one leave at once
+    uint32_t emit_small_grid;
 };
 
 struct EntityCullParams {
