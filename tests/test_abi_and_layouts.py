@@ -127,3 +127,34 @@ def test_host_driver_library_loads():
     h = _lib.host_lib()
     assert h.orbit_host_frame_loop(None, None, 0, None, 0, 0) == _lib.ERR_INVALID_ARGUMENT
     assert h.orbit_host_sizeof_frame() == C.sizeof(L.HostFrame) and h.orbit_host_sizeof_io() == C.sizeof(L.HostFrameIO)
+
+
+def test_cull_pair_compatibility_is_a_host_predicate():
+    """orbit_cull_pair_compatible needs no GPU: it decides from the two 400-byte structs whether the MAIN pass may be fused into
+    the LATE pass (same camera, planes, projection type and LOD parameters, both visibility buffers, pass 2 then pass 1)."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from orbit_b200 import _lib, layouts as L, scenes
+    import oracle_ref as O
+    lib = _lib.lib()
+    _, view = scenes.config_c1(scale=0.2)
+    late, main = O.gpu_cull_info(view, "write"), O.gpu_cull_info(view, "read")
+    ok = lambda a, b: lib.orbit_cull_pair_compatible(C.byref(a), C.byref(b))
+    assert ok(late, main) == 1 and ok(main, late) == 0 and ok(late, late) == 0 and ok(main, main) == 0
+    assert lib.orbit_cull_pair_compatible(None, C.byref(main)) == 0
+    assert ok(late, O.gpu_cull_info(view, "none")) == 0                                   # pass 0 is not pass 1
+    assert ok(late, O.gpu_cull_info(view, "read", meshlet_occlusion=False)) == 0          # needs the meshlet visibility buffer
+    assert ok(O.gpu_cull_info(view, "write", meshlet_occlusion=False), main) == 0
+    g = O.gpu_cull_info(view, "read"); g.alpha_mode_flags = 0b100
+    assert ok(late, g) == 1                                                                # another alpha filter is fine
+    for field, delta in (("lod_base", 1.0), ("lod_step", 0.5), ("min_mesh_lod", 1), ("max_mesh_lod", -1), ("cull_plane_count", -1), ("projection_type", 1)):
+        g = O.gpu_cull_info(view, "read")
+        setattr(g, field, getattr(g, field) + delta)
+        assert ok(late, g) == 0, field
+    g = O.gpu_cull_info(view, "read"); g.cull_planes[0][3] += 1e-3
+    assert ok(late, g) == 0
+    g = O.gpu_cull_info(view, "read"); g.lod_target_pos_view_space[1] += 1.0
+    assert ok(late, g) == 0
+    # fields only pass 2 reads (projection scale, near / far) are zero in a pass-1 struct and do not matter
+    g = O.gpu_cull_info(view, "read"); g.z_near = 123.0; g.p00_or_width_recip_x2 = 7.0
+    assert ok(late, g) == 1
