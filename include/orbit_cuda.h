@@ -49,7 +49,10 @@
 extern "C" {
 #endif
 
-#define ORBIT_ABI_VERSION 2
+/* 3: orbit_*_late_main + orbit_cull_pair_compatible, orbit_peer_put / orbit_peer_wait, OrbitStatus::peer_timeout (was reserved[0]),
+ *    orbit_record_masks_put / region form of orbit_draws_from_masks (replace orbit_record_masks_scatter_ranked).
+ * 2: device guards on every entry point, orbit_ctx_reserve, orbit_meshlet_test, scatter sources clamped to their capacity. */
+#define ORBIT_ABI_VERSION 3
 
 enum {
     ORBIT_OK = 0,

@@ -83,7 +83,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if handle.orbit_abi_version() != 2:
+        if handle.orbit_abi_version() != 3:
             raise ImportError("liborbit_b200.so ABI version mismatch")
         _lib = handle
     return _lib

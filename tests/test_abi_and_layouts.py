@@ -24,7 +24,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.orbit_abi_version() == 2
+    assert lib.orbit_abi_version() == 3
     assert lib.orbit_error_string(0) == b"ok"
 
 
